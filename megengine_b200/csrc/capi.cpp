@@ -1,0 +1,302 @@
+// C-ABI entry points (include/b200cb.h): algorithm table, heuristic, dispatch, error text.
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+#include "common.h"
+
+namespace b200cb {
+
+namespace {
+thread_local char g_last_error[256] = "";
+
+struct AlgoEntry {
+    const char* name;
+    uint32_t kernel;
+    uint32_t block_n;
+};
+// Order is part of the ABI: megdnn serialises Algorithm::Info::Desc{type, param, name} into its
+// persistent fastrun cache (dnn/include/megdnn/oprs/base.h:135-158) -- append only.
+const AlgoEntry g_algos[] = {
+        {"B200_IGEMM_TCGEN05_128x256", KERNEL_IGEMM, 256},
+        {"B200_IGEMM_TCGEN05_128x128", KERNEL_IGEMM, 128},
+        {"B200_IGEMM_TCGEN05_128x64", KERNEL_IGEMM, 64},
+        {"B200_DWCONV_DIRECT", KERNEL_DWCONV, 0},
+};
+constexpr int NUM_ALGOS = sizeof(g_algos) / sizeof(g_algos[0]);
+
+void fill_accounting(b200cb_plan* plan) {
+    const b200cb_desc& d = plan->desc;
+    const uint64_t icpg = d.ic / (d.group ? d.group : 1);
+    // flops = 2*N*OC*OH*OW*(IC/group)*FH*FW  (dnn/test/cuda/conv_test_utils.cpp:193)
+    plan->flops = 2ull * d.n * d.oc * d.oh * d.ow * icpg * d.fh * d.fw;
+    // algorithmic bytes: every tensor touched once; 1x1 strided convs only read
+    // the pixels they use
+    uint64_t src_pix = (uint64_t)d.ih * d.iw;
+    if (d.fh == 1 && d.fw == 1 && d.pad_h == 0 && d.pad_w == 0)
+        src_pix = (uint64_t)d.oh * d.ow;
+    uint64_t b = (uint64_t)d.n * src_pix * d.ic * dtype_size(d.src_dtype);
+    b += (uint64_t)d.oc * icpg * d.fh * d.fw * dtype_size(d.filter_dtype);
+    if (d.bias_mode == B200CB_BIAS_CHANNEL)
+        b += (uint64_t)d.oc * dtype_size(d.bias_dtype);
+    const uint64_t dst_elems = (uint64_t)d.n * d.oh * d.ow * d.oc;
+    if (d.bias_mode == B200CB_BIAS_FULL)
+        b += dst_elems * dtype_size(d.bias_dtype);
+    if (d.has_z)
+        b += dst_elems * dtype_size(d.z_dtype);
+    b += dst_elems * dtype_size(d.dst_dtype);
+    plan->bytes = b;
+}
+
+int validate_desc(const b200cb_desc* d) {
+    if (!d)
+        return B200CB_ERR_NULL;
+    if (d->group == 0 || d->ic % d->group != 0 || d->oc % d->group != 0)
+        return B200CB_UNSUPPORTED_SHAPE;
+    // output extent must match megdnn's infer_conv_shape (dnn/src/common/utils.cpp:130-138)
+    auto out_dim = [](uint32_t i, uint32_t f, uint32_t s, uint32_t p, uint32_t dl) -> int64_t {
+        int64_t eff = (int64_t)(f - 1) * dl + 1;
+        int64_t num = (int64_t)i + 2 * (int64_t)p - eff;
+        if (num < 0 || s == 0)
+            return -1;
+        return num / s + 1;
+    };
+    if (d->stride_h == 0 || d->stride_w == 0 || d->dilate_h == 0 || d->dilate_w == 0)
+        return B200CB_UNSUPPORTED_PARAM;
+    if (out_dim(d->ih, d->fh, d->stride_h, d->pad_h, d->dilate_h) != (int64_t)d->oh ||
+        out_dim(d->iw, d->fw, d->stride_w, d->pad_w, d->dilate_w) != (int64_t)d->ow)
+        return B200CB_UNSUPPORTED_SHAPE;
+    return B200CB_OK;
+}
+
+// crude per-tile cycle model used only to rank the tile widths (see DESIGN.md "heuristic")
+double igemm_cost(const b200cb_desc& d, uint32_t bn, int sms) {
+    const uint32_t in_es = d.src_dtype == B200CB_DT_QS8 ? 1 : 2;
+    const uint32_t kb_elems = IGEMM_KBYTES / in_es;
+    const double num_kb = (double)d.fh * d.fw * ((d.ic + kb_elems - 1) / kb_elems);
+    const double M = (double)d.n * d.oh * d.ow;
+    const double m_tiles = ceil(M / IGEMM_BLOCK_M);
+    const double n_tiles = ceil((double)d.oc / bn);
+    const double mma = 4.0 * (128.0 * bn / 256.0);                  // 4 MMAs of K=32B per k-block
+    const double feed = (IGEMM_BLOCK_M + bn) * 128.0 / 128.0;       // smem bytes / (128 B/clk)
+    const double per_kb = mma > feed ? mma : feed;
+    const double epi = 600.0 + 6.0 * bn;
+    double tile = num_kb * per_kb;
+    if (tile < epi)
+        tile = epi;  // epilogue-bound when K is tiny
+    const double waves = ceil(m_tiles * n_tiles / sms);
+    return waves * (tile + 400.0);
+}
+}  // namespace
+
+void set_last_error(const char* what, const char* detail) {
+    snprintf(g_last_error, sizeof(g_last_error), "%s: %s", what ? what : "", detail ? detail : "");
+}
+
+}  // namespace b200cb
+
+using namespace b200cb;
+
+extern "C" {
+
+int b200cb_algo_count(void) {
+    return NUM_ALGOS;
+}
+
+const char* b200cb_algo_name(int algo) {
+    if (algo < 0 || algo >= NUM_ALGOS)
+        return nullptr;
+    return g_algos[algo].name;
+}
+
+int b200cb_query_algo(const b200cb_desc* desc, int algo, b200cb_plan* plan) {
+    if (!desc || !plan)
+        return B200CB_ERR_NULL;
+    if (algo < 0 || algo >= NUM_ALGOS)
+        return B200CB_UNSUPPORTED_ALGO;
+    int rc = validate_desc(desc);
+    if (rc != B200CB_OK)
+        return rc;
+    memset(plan, 0, sizeof(*plan));
+    const AlgoEntry& a = g_algos[algo];
+    if (a.kernel == KERNEL_IGEMM)
+        rc = igemm_query(*desc, a.block_n, plan);
+    else
+        rc = dwconv_query(*desc, plan);
+    if (rc != B200CB_OK)
+        return rc;
+    plan->algo = algo;
+    fill_accounting(plan);
+    return B200CB_OK;
+}
+
+int b200cb_query(const b200cb_desc* desc, b200cb_plan* plan) {
+    if (!desc || !plan)
+        return B200CB_ERR_NULL;
+    int first_err = B200CB_UNSUPPORTED_ALGO;
+    int best = -1;
+    double best_cost = 0;
+    b200cb_plan tmp;
+    for (int a = 0; a < NUM_ALGOS; ++a) {
+        int rc = b200cb_query_algo(desc, a, &tmp);
+        if (rc != B200CB_OK) {
+            if (rc < 0)
+                return rc;
+            if (first_err == B200CB_UNSUPPORTED_ALGO)
+                first_err = rc;
+            continue;
+        }
+        double cost = g_algos[a].kernel == KERNEL_IGEMM ? igemm_cost(*desc, g_algos[a].block_n, 148) : 0.0;
+        if (best < 0 || cost < best_cost) {
+            best = a;
+            best_cost = cost;
+            *plan = tmp;
+        }
+    }
+    return best >= 0 ? B200CB_OK : first_err;
+}
+
+int b200cb_launch(
+        const b200cb_plan* plan, const void* src, const void* filter, const void* bias,
+        const void* z, void* dst, void* workspace, size_t workspace_bytes, void* stream) {
+    if (!plan)
+        return B200CB_ERR_NULL;
+    if (plan->magic != PLAN_MAGIC)
+        return B200CB_ERR_BAD_PLAN;
+    if (workspace_bytes < plan->workspace_bytes || (plan->workspace_bytes && !workspace))
+        return B200CB_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    switch (plan->kernel) {
+        case KERNEL_IGEMM:
+            return igemm_launch(*plan, src, filter, bias, z, dst, workspace, workspace_bytes, s);
+        case KERNEL_DWCONV:
+            return dwconv_launch(*plan, src, filter, bias, z, dst, s);
+        default:
+            return B200CB_ERR_BAD_PLAN;
+    }
+}
+
+int b200cb_plan_num_launches(const b200cb_plan* plan) {
+    if (!plan || plan->magic != PLAN_MAGIC)
+        return 0;
+    return 1;
+}
+
+size_t b200cb_preprocessed_filter_bytes(const b200cb_plan* plan) {
+    // KRSC filters are consumed in place by TMA; no algorithm needs a packed copy yet.
+    (void)plan;
+    return 0;
+}
+
+int b200cb_preprocess_filter(const b200cb_plan* plan, const void* filter, void* packed, void* stream) {
+    (void)filter;
+    (void)packed;
+    (void)stream;
+    if (!plan)
+        return B200CB_ERR_NULL;
+    if (plan->magic != PLAN_MAGIC)
+        return B200CB_ERR_BAD_PLAN;
+    return B200CB_OK;
+}
+
+namespace {
+struct HostLayout {
+    size_t src, filter, bias, z, dst, ws, total;
+    size_t src_b, filter_b, bias_b, z_b, dst_b;
+};
+size_t align256(size_t v) {
+    return (v + 255) & ~size_t(255);
+}
+HostLayout host_layout(const b200cb_plan* plan) {
+    const b200cb_desc& d = plan->desc;
+    HostLayout l{};
+    const size_t src_img = (size_t)d.ih * d.iw * d.ic;
+    l.src_b = (size_t)d.n * src_img * dtype_size(d.src_dtype);
+    l.filter_b = (size_t)d.oc * (d.ic / d.group) * d.fh * d.fw * dtype_size(d.filter_dtype);
+    const size_t dst_elems = (size_t)d.n * d.oh * d.ow * d.oc;
+    l.bias_b = d.bias_mode == B200CB_BIAS_CHANNEL ? (size_t)d.oc * dtype_size(d.bias_dtype)
+               : d.bias_mode == B200CB_BIAS_FULL  ? dst_elems * dtype_size(d.bias_dtype)
+                                                  : 0;
+    l.z_b = d.has_z ? dst_elems * dtype_size(d.z_dtype) : 0;
+    l.dst_b = dst_elems * dtype_size(d.dst_dtype);
+    size_t off = 0;
+    l.src = off, off += align256(l.src_b);
+    l.filter = off, off += align256(l.filter_b);
+    l.bias = off, off += align256(l.bias_b);
+    l.z = off, off += align256(l.z_b);
+    l.dst = off, off += align256(l.dst_b);
+    l.ws = off, off += align256(plan->workspace_bytes);
+    l.total = off;
+    return l;
+}
+}  // namespace
+
+size_t b200cb_host_scratch_bytes(const b200cb_plan* plan) {
+    if (!plan || plan->magic != PLAN_MAGIC)
+        return 0;
+    return host_layout(plan).total;
+}
+
+int b200cb_exec_host(
+        const b200cb_plan* plan, const void* src, const void* filter, const void* bias,
+        const void* z, void* dst, void* dev_scratch, size_t dev_scratch_bytes, void* stream) {
+    if (!plan || !src || !filter || !dst || !dev_scratch)
+        return B200CB_ERR_NULL;
+    if (plan->magic != PLAN_MAGIC)
+        return B200CB_ERR_BAD_PLAN;
+    const b200cb_desc& d = plan->desc;
+    if (d.src_batch_stride || d.dst_batch_stride || d.z_batch_stride)
+        return B200CB_UNSUPPORTED_SHAPE;  // host convenience path takes dense tensors only
+    HostLayout l = host_layout(plan);
+    if (dev_scratch_bytes < l.total)
+        return B200CB_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    char* base = static_cast<char*>(dev_scratch);
+    cudaError_t e = cudaMemcpyAsync(base + l.src, src, l.src_b, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(base + l.filter, filter, l.filter_b, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && l.bias_b)
+        e = cudaMemcpyAsync(base + l.bias, bias, l.bias_b, cudaMemcpyHostToDevice, s);
+    if (e == cudaSuccess && l.z_b)
+        e = cudaMemcpyAsync(base + l.z, z, l.z_b, cudaMemcpyHostToDevice, s);
+    if (e != cudaSuccess) {
+        set_last_error("exec_host H2D", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    int rc = b200cb_launch(
+            plan, base + l.src, base + l.filter, l.bias_b ? base + l.bias : nullptr,
+            l.z_b ? base + l.z : nullptr, base + l.dst, base + l.ws, plan->workspace_bytes, stream);
+    if (rc != B200CB_OK)
+        return rc;
+    e = cudaMemcpyAsync(dst, base + l.dst, l.dst_b, cudaMemcpyDeviceToHost, s);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(s);
+    if (e != cudaSuccess) {
+        set_last_error("exec_host D2H", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    return B200CB_OK;
+}
+
+const char* b200cb_strerror(int code) {
+    switch (code) {
+        case B200CB_OK: return "ok";
+        case B200CB_UNSUPPORTED_FORMAT: return "unsupported tensor format";
+        case B200CB_UNSUPPORTED_DTYPE: return "unsupported dtype combination";
+        case B200CB_UNSUPPORTED_SHAPE: return "unsupported shape";
+        case B200CB_UNSUPPORTED_PARAM: return "unsupported convolution parameter";
+        case B200CB_UNSUPPORTED_ALIGNMENT: return "channel count / stride not 16-byte aligned";
+        case B200CB_UNSUPPORTED_ALGO: return "no such algorithm / algorithm not applicable";
+        case B200CB_ERR_CUDA: return "CUDA runtime error";
+        case B200CB_ERR_DRIVER: return "CUDA driver error (tensor map encode)";
+        case B200CB_ERR_WORKSPACE: return "workspace too small";
+        case B200CB_ERR_BAD_PLAN: return "plan was not produced by b200cb_query";
+        case B200CB_ERR_NULL: return "null pointer argument";
+        default: return "unknown error";
+    }
+}
+
+const char* b200cb_last_error_detail(void) {
+    return g_last_error;
+}
+
+}  // extern "C"
