@@ -1,0 +1,161 @@
+"""Staged GPU diagnostics (run under gpurun): each stage runs in its own subprocess with a timeout
+so that a hung kernel cannot take the later stages with it.  Writes gpurun_out/diag.jsonl.
+
+    python -m tests.gpu_diag [stage ...]
+"""
+import json
+import os
+import subprocess
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+OUT = os.path.join(ROOT, "gpurun_out")
+
+
+def stage_cases(stage):
+    from megengine_b200 import _capi as C
+    from . import _cases as K
+    md = K.make_desc
+    if stage == "gemm_tiled":       # pointwise conv == plain GEMM through tiled TMA
+        return [("pw_bf16_1tile", md("bf16", 1, 64, 8, 16, 64, 1, bias_mode=C.BIAS_NONE), {}),
+                ("pw_bf16_bias", md("bf16", 1, 64, 8, 16, 64, 1), {}),
+                ("pw_bf16_k256_oc128", md("bf16", 2, 256, 16, 16, 128, 1, nonline=1), {}),
+                ("pw_bf16_oc256", md("bf16", 2, 128, 16, 16, 256, 1, nonline=1), {}),
+                ("pw_bf16_oc512_x256", md("bf16", 2, 128, 16, 16, 512, 1, nonline=1), {"algo": 0}),
+                ("pw_bf16_oc512_x128", md("bf16", 2, 128, 16, 16, 512, 1, nonline=1), {"algo": 1}),
+                ("pw_bf16_oc512_x64", md("bf16", 2, 128, 16, 16, 512, 1, nonline=1), {"algo": 2}),
+                ("pw_bf16_mtail", md("bf16", 3, 64, 7, 7, 64, 1, nonline=1), {}),
+                ("pw_bf16_z", md("bf16", 2, 64, 14, 14, 256, 1, nonline=1, has_z=True), {}),
+                ("pw_f16_z", md("f16", 2, 64, 14, 14, 256, 1, nonline=1, has_z=True), {}),
+                ("pw_bf16_ic16", md("bf16", 2, 16, 14, 14, 64, 1, nonline=1), {}),
+                ("pw_bf16_ic144_oc24", md("bf16", 2, 144, 14, 14, 24, 1, nonline=0), {})]
+    if stage == "gemm_im2col":      # same GEMMs forced through the im2col descriptor
+        return [("pwi_bf16_1tile", md("bf16", 1, 64, 8, 16, 64, 1, bias_mode=C.BIAS_NONE), {"im2col": True}),
+                ("pwi_bf16_mtail", md("bf16", 3, 64, 7, 7, 64, 1, nonline=1), {"im2col": True}),
+                ("pwi_bf16_k256", md("bf16", 2, 256, 16, 16, 128, 1, nonline=1), {"im2col": True}),
+                ("pwi_bf16_s2", md("bf16", 2, 64, 16, 16, 64, 1, stride=2), {})]
+    if stage == "conv":
+        return [("c3_bf16_p1", md("bf16", 2, 64, 14, 14, 64, 3, pad=1, nonline=1), {}),
+                ("c3_bf16_p0", md("bf16", 2, 64, 14, 14, 64, 3, pad=0, nonline=1), {}),
+                ("c3_bf16_s2", md("bf16", 2, 64, 15, 15, 64, 3, stride=2, pad=1, nonline=1), {}),
+                ("c3_bf16_asym", md("bf16", 2, 64, 12, 17, 64, 3, pad=1, pad_w=0, stride=1, stride_w=2), {}),
+                ("c5_bf16_p2", md("bf16", 2, 32, 13, 13, 64, 5, pad=2, nonline=3), {}),
+                ("c7_bf16_s2_ic8", md("bf16", 1, 8, 32, 32, 64, 7, stride=2, pad=3, nonline=1), {}),
+                ("c3_bf16_z_oc256", md("bf16", 2, 128, 14, 14, 256, 3, pad=1, nonline=1, has_z=True), {}),
+                ("c3_bf16_dil2", md("bf16", 2, 64, 14, 14, 64, 3, pad=2, dilate=2), {}),
+                ("c3_bf16_flip", md("bf16", 2, 64, 9, 9, 64, 3, pad=1, mode=1), {}),
+                ("c3_f16", md("f16", 2, 64, 14, 14, 128, 3, pad=1, nonline=1, has_z=True), {}),
+                ("c3_bf16_big", md("bf16", 8, 128, 28, 28, 128, 3, pad=1, nonline=1), {})]
+    if stage == "int8":
+        sc = (1.2, 1.3, None, 0.7, 19.99)
+        return [("q_pw", md("qs8", 2, 128, 14, 14, 64, 1, nonline=0, scales=sc), {}),
+                ("q_pw_oc256_relu", md("qs8", 2, 128, 14, 14, 256, 1, nonline=1, scales=sc), {}),
+                ("q_c3_z_relu", md("qs8", 2, 64, 14, 14, 128, 3, pad=1, nonline=1, has_z=True, scales=sc), {}),
+                ("q_c3_z_hswish", md("qs8", 2, 64, 14, 14, 128, 3, pad=1, nonline=3, has_z=True,
+                                     scales=(0.11, 0.23, None, 0.37, 0.41)), {"int_range": 127}),
+                ("q_c3_s2_nobias", md("qs8", 3, 32, 15, 15, 64, 3, stride=2, pad=1, nonline=1,
+                                      bias_mode=C.BIAS_NONE, scales=sc), {}),
+                ("q_pw_qs32", md("qs8", 2, 64, 14, 14, 64, 1, dst_kind="qs32"), {}),
+                ("q_c3_stress", md("qs8", 2, 256, 14, 14, 256, 3, pad=1, nonline=1, has_z=True,
+                                   scales=(0.013, 0.021, None, 0.05, 0.9)), {"int_range": 127, "bias_range": 5000})]
+    if stage == "dw":
+        out = []
+        for kind in ("bf16", "f16", "f32", "qs8"):
+            out += [("dw3s1_" + kind, K.dw_desc(kind, 2, 32, 14, 14, 1, has_z=True), {}),
+                    ("dw3s2_" + kind, K.dw_desc(kind, 2, 96, 15, 15, 2), {}),
+                    ("dw5s1_" + kind, K.dw_desc(kind, 2, 48, 9, 9, 1, f=5, nonline=3), {}),
+                    ("dw3s1_c144_" + kind, K.dw_desc(kind, 3, 144, 7, 7, 1), {})]
+        out.append(("dw7_generic_bf16", K.dw_desc("bf16", 2, 32, 12, 12, 1, f=7), {}))
+        return out
+    raise SystemExit("unknown stage " + stage)
+
+
+def analyse(d, got, want_f32_or_int, info):
+    """where are the wrong outputs? rows (pixels) vs columns (channels) histogram."""
+    from megengine_b200 import _capi as C
+    from . import _oracle as O
+    oc = d.oc
+    if d.dst_dtype in (C.DT_QS8, C.DT_QS32):
+        bad = (got != want_f32_or_int)
+    else:
+        g = O.to_f32(got, d.dst_dtype)
+        bad = ~(O.megdnn_rel_err(g, want_f32_or_int) <= info["tol"])
+    bad = bad.reshape(-1, oc)
+    rows = np.nonzero(bad.any(axis=1))[0]
+    cols = np.nonzero(bad.any(axis=0))[0]
+    info["bad_rows"] = int(rows.size)
+    info["bad_cols"] = int(cols.size)
+    info["rows_head"] = rows[:24].tolist()
+    info["cols_head"] = cols[:24].tolist()
+    info["shape"] = [int(bad.shape[0]), int(oc)]
+
+
+def run_stage(stage):
+    import torch
+    from megengine_b200 import _capi as C
+    from . import _cases as K, _gpu as G, _oracle as O
+    assert torch.cuda.is_available()
+    for name, d, opt in stage_cases(stage):
+        rec = {"stage": stage, "case": name, "desc": K.desc_str(d)}
+        try:
+            src, flt, bias, z = K.gen_inputs(d, 1234, int_range=opt.get("int_range", 8),
+                                             bias_range=opt.get("bias_range", 50))
+            want = O.oracle_convbias(d, src, flt, bias, z)
+            want_f32 = None
+            if d.dst_dtype in (C.DT_BF16, C.DT_F16):
+                want_f32 = K.fp32_reference(d, src, flt, bias, z)
+            t0 = time.time()
+            got, plan = G.run_gpu(d, src, flt, bias, z, algo=opt.get("algo"), force_im2col=opt.get("im2col", False))
+            rec["algo"] = C.load().b200cb_algo_name(plan.algo).decode()
+            rec["stages"] = plan.stages
+            rec["a_mode"] = 1 if opt.get("im2col") else plan.a_mode
+            ok, info = G.compare(d, got, want, want_f32)
+            rec["ok"] = bool(ok)
+            rec.update(info)
+            if not ok:
+                analyse(d, got, want_f32 if want_f32 is not None else
+                        (O.to_f32(want, d.dst_dtype) if d.dst_dtype == C.DT_F32 else want), rec)
+            rec["sec"] = round(time.time() - t0, 3)
+        except Exception as e:  # noqa: BLE001
+            rec["ok"] = False
+            rec["error"] = repr(e)[:400]
+        print(json.dumps(rec), flush=True)
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    stages = sys.argv[1:] or ["gemm_tiled", "gemm_im2col", "conv", "int8", "dw"]
+    if os.environ.get("B200CB_DIAG_CHILD"):
+        run_stage(stages[0])
+        return
+    path = os.path.join(OUT, "diag.jsonl")
+    with open(path, "a") as f:
+        for st in stages:
+            env = dict(os.environ, B200CB_DIAG_CHILD="1")
+            t0 = time.time()
+            try:
+                r = subprocess.run([sys.executable, "-m", "tests.gpu_diag", st], env=env, cwd=ROOT,
+                                   capture_output=True, text=True, timeout=240)
+                out, err, code = r.stdout, r.stderr, r.returncode
+            except subprocess.TimeoutExpired as e:
+                out = (e.stdout or b"").decode() if isinstance(e.stdout, bytes) else (e.stdout or "")
+                err, code = "TIMEOUT", -9
+            f.write(out)
+            summary = {"stage": st, "exit": code, "sec": round(time.time() - t0, 1), "stderr_tail": err[-600:]}
+            f.write(json.dumps(summary) + "\n")
+            f.flush()
+            lines = [json.loads(l) for l in out.splitlines() if l.startswith("{")]
+            nok = sum(1 for l in lines if l.get("ok"))
+            print("[%s] %d/%d ok, exit %d, %.1fs" % (st, nok, len(lines), code, time.time() - t0))
+            for l in lines:
+                if not l.get("ok"):
+                    print("   FAIL", json.dumps(l)[:900])
+            if code != 0:
+                print("   stderr:", err[-600:])
+
+
+if __name__ == "__main__":
+    main()
