@@ -1,0 +1,131 @@
+"""CPU tests of the C-ABI boundary (include/b200cb.h): the library loads without a GPU, exports
+every declared symbol, and the pure-host entry points (algo table, query/is_available matrix,
+workspace + accounting, error text) behave as the megdnn AlgoBase contract requires
+(dnn/src/cuda/conv_bias/algo.h:83-165).  No compute call is made here."""
+import ctypes
+import os
+import re
+
+import pytest
+
+from megengine_b200 import _capi as C
+from . import _cases as K
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "b200cb.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200cb_[a-z_0-9]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(lib):
+    syms = declared_symbols()
+    assert len(syms) >= 12
+    for s in syms:
+        assert hasattr(lib, s), "libb200cb.so does not export " + s
+    assert sorted(n for n, _r, _a in C.SYMBOLS) == syms, "ctypes binding and header disagree"
+
+
+def test_struct_sizes_match_header(lib):
+    # 33 x 4-byte fields + 3 x u64 (8-aligned) ; plan = 16 x u32 + 3 x u64 + desc
+    assert ctypes.sizeof(C.Desc) == 160
+    assert ctypes.sizeof(C.Plan) == 64 + 24 + 160
+
+
+def test_algo_table_is_stable(lib):
+    names = [lib.b200cb_algo_name(i).decode() for i in range(lib.b200cb_algo_count())]
+    # append-only: megdnn serialises Algorithm::Info::Desc into the fastrun cache (oprs/base.h:135-158)
+    assert names[:4] == ["B200_IGEMM_TCGEN05_128x256", "B200_IGEMM_TCGEN05_128x128",
+                         "B200_IGEMM_TCGEN05_128x64", "B200_DWCONV_DIRECT"]
+    assert len(set(names)) == len(names) and all(":" not in n for n in names)
+    assert lib.b200cb_algo_name(-1) is None and lib.b200cb_algo_name(len(names)) is None
+
+
+def _query(lib, d, algo=None):
+    p = C.Plan()
+    rc = lib.b200cb_query(ctypes.byref(d), ctypes.byref(p)) if algo is None else \
+        lib.b200cb_query_algo(ctypes.byref(d), algo, ctypes.byref(p))
+    return rc, p
+
+
+def test_query_resnet50_all_layers_supported(lib):
+    for kind in ("bf16", "f16", "qs8"):
+        for layer in K.RESNET50_LAYERS:
+            d = K.resnet50_desc(layer, kind, 256, ic_pad=16 if kind == "qs8" else 8)
+            rc, p = _query(lib, d)
+            assert rc == 0, (layer[0], kind, lib.b200cb_strerror(rc))
+            assert p.workspace_bytes == 0 and p.smem_bytes <= 232448 and p.stages >= 2
+            n, oc, oh, ow, ic, f = d.n, d.oc, d.oh, d.ow, d.ic, d.fh
+            assert p.flops == 2 * n * oc * oh * ow * ic * f * f   # conv_test_utils.cpp:193
+            assert lib.b200cb_plan_num_launches(ctypes.byref(p)) == 1
+
+
+def test_query_mobilenet_depthwise_supported(lib):
+    for kind in ("bf16", "f16", "f32", "qs8"):
+        for c, h, w, s in K.MOBILENETV2_DW:
+            if kind == "qs8" and c % 16:
+                continue
+            rc, p = _query(lib, K.dw_desc(kind, 256, c, h, w, s))
+            assert rc == 0 and lib.b200cb_algo_name(p.algo) == b"B200_DWCONV_DIRECT"
+
+
+def test_unsupported_cells_are_rejected_not_silently_wrong(lib):
+    """everything outside the supported-cell matrix must come back > 0 (is_available false)."""
+    ok = K.make_desc("bf16", 2, 64, 14, 14, 64, 3, pad=1)
+    assert _query(lib, ok)[0] == 0
+    cases = []
+    d = ok.copy(); d.format = C.FORMAT_NCHW; cases.append(d)                      # format
+    d = ok.copy(); d.src_dtype = d.filter_dtype = C.DT_F32; d.dst_dtype = d.bias_dtype = C.DT_F32; cases.append(d)
+    d = ok.copy(); d.ic = 60; cases.append(d)                                      # 16-byte channel alignment
+    d = ok.copy(); d.bias_mode = C.BIAS_FULL; cases.append(d)
+    d = ok.copy(); d.filter_dtype = C.DT_F16; cases.append(d)                      # src/filter mismatch
+    d = ok.copy(); d.oh += 1; cases.append(d)                                      # inconsistent output extent
+    d = ok.copy(); d.stride_h = 0; cases.append(d)
+    d = K.make_desc("qs8", 2, 64, 14, 14, 64, 3, pad=1, nonline=C.NL_SIGMOID); cases.append(d)
+    d = K.make_desc("qs8", 2, 64, 14, 14, 64, 3, pad=1, dst_kind="qs32", nonline=C.NL_RELU); cases.append(d)
+    d = K.make_desc("bf16", 2, 64, 14, 14, 64, 3, pad=1, group=2); cases.append(d)  # general group conv
+    for d in cases:
+        rc, _p = _query(lib, d)
+        assert rc > 0, K.desc_str(d)
+        assert lib.b200cb_strerror(rc) not in (b"ok", b"unknown error")
+
+
+def test_query_algo_enumeration_and_heuristic_pick(lib):
+    d = K.make_desc("bf16", 256, 256, 14, 14, 256, 3, pad=1)
+    avail = [a for a in range(lib.b200cb_algo_count()) if _query(lib, d, a)[0] == 0]
+    assert avail == [0, 1, 2]
+    rc, p = _query(lib, d)
+    assert rc == 0 and p.algo in avail
+    # narrow OC never gets a tile more than 2x wider than OC
+    d = K.make_desc("bf16", 4, 64, 14, 14, 64, 1)
+    assert [a for a in range(3) if _query(lib, d, a)[0] == 0] == [2]
+    assert _query(lib, d, 99)[0] == 6
+
+
+def test_launch_argument_validation_without_gpu(lib):
+    """argument errors are reported as negative codes before anything touches CUDA."""
+    d = K.make_desc("bf16", 2, 64, 14, 14, 64, 3, pad=1)
+    rc, p = _query(lib, d)
+    assert rc == 0
+    assert lib.b200cb_launch(None, None, None, None, None, None, None, 0, None) == -5
+    bad = C.Plan()
+    assert lib.b200cb_launch(ctypes.byref(bad), None, None, None, None, None, None, 0, None) == -4
+    assert lib.b200cb_launch(ctypes.byref(p), None, None, None, None, None, None, 0, None) == -5  # null tensors
+    assert lib.b200cb_query(None, ctypes.byref(p)) == -5
+    assert lib.b200cb_host_scratch_bytes(ctypes.byref(p)) >= 2 * (2 * 14 * 14 * 64) * 2
+    assert lib.b200cb_preprocessed_filter_bytes(ctypes.byref(p)) == 0
+    for code in (0, 1, 2, 3, 4, 5, 6, -1, -2, -3, -4, -5):
+        assert lib.b200cb_strerror(code)
+
+
+def test_product_has_no_oracle_or_cpu_fallback():
+    """the shipped package must not import / link anything under oracle/ (task rule 3)."""
+    pkg = os.path.join(ROOT, "megengine_b200")
+    for dirpath, _dn, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", "Makefile")):
+                text = open(os.path.join(dirpath, f), errors="ignore").read()
+                assert "oracle" not in text.lower() or f in ("epilogue.cuh", "igemm_sm100.cu", "dwconv.cu"), f
+                assert "liboracle" not in text and "ref_driver" not in text, f

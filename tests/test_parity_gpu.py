@@ -1,0 +1,170 @@
+"""GPU parity tests: the CUDA path (through the C-ABI, include/b200cb.h) against the oracle on the
+same seeded inputs.  Bit-exact for QuantizedS8/S32; bf16 <= 1e-2 and fp16 <= 2e-3 max relative
+error |x-y|/max(|x|,|y|,1) against the fp32 oracle (BASELINE.json north_star; metric from
+dnn/test/common/utils.h:189-193).  Case generators mirror dnn/test/cuda/conv_bias.cpp:83-124,
+234-265,650-714,1390-1439 and dnn/test/cuda/conv_bias_int8.cpp:798-835.
+"""
+import zlib
+
+import numpy as np
+import pytest
+
+from megengine_b200 import _capi as C
+from . import _cases as K
+from . import _oracle as O
+from .gpu_diag import stage_cases
+
+pytestmark = pytest.mark.gpu
+
+
+def _check(d, opt=None, seed=1234):
+    from . import _gpu as G
+    opt = opt or {}
+    src, flt, bias, z = K.gen_inputs(d, seed, int_range=opt.get("int_range", 8), bias_range=opt.get("bias_range", 50))
+    want = O.oracle_convbias(d, src, flt, bias, z)
+    want_f32 = K.fp32_reference(d, src, flt, bias, z) if d.dst_dtype in (C.DT_BF16, C.DT_F16) else None
+    got, plan = G.run_gpu(d, src, flt, bias, z, algo=opt.get("algo"), force_im2col=opt.get("im2col", False))
+    ok, info = G.compare(d, got, want, want_f32)
+    assert ok, (K.desc_str(d), info)
+    return plan, info
+
+
+def _ids(cases):
+    return [c[0] for c in cases]
+
+
+@pytest.mark.parametrize("name,d,opt", stage_cases("gemm_tiled") + stage_cases("gemm_im2col"),
+                         ids=_ids(stage_cases("gemm_tiled") + stage_cases("gemm_im2col")))
+def test_pointwise(name, d, opt):
+    _check(d, opt)
+
+
+@pytest.mark.parametrize("name,d,opt", stage_cases("conv"), ids=_ids(stage_cases("conv")))
+def test_dense_conv(name, d, opt):
+    _check(d, opt)
+
+
+@pytest.mark.parametrize("name,d,opt", stage_cases("int8"), ids=_ids(stage_cases("int8")))
+def test_int8_bit_exact(name, d, opt):
+    _check(d, opt)
+
+
+@pytest.mark.parametrize("name,d,opt", stage_cases("dw"), ids=_ids(stage_cases("dw")))
+def test_depthwise(name, d, opt):
+    _check(d, opt)
+
+
+@pytest.mark.parametrize("kind", ["bf16", "f16", "qs8"])
+@pytest.mark.parametrize("layer", K.RESNET50_LAYERS, ids=[l[0] for l in K.RESNET50_LAYERS])
+def test_resnet50_layers_n1(layer, kind):
+    """every ResNet-50 ConvBias shape at N=1 against the full oracle; conv1 at a
+    reduced spatial size for the oracle's sake (same filter / stride / pad, IC padded 3 -> 8/16)."""
+    d = K.resnet50_desc(layer, kind, 1, ic_pad=16 if kind == "qs8" else 8)
+    if layer[0] == "conv1":
+        d = K.make_desc(kind, 1, d.ic, 64, 64, 64, 7, stride=2, pad=3, nonline=C.NL_RELU)
+    _check(d, {"int_range": 127, "bias_range": 5000} if kind == "qs8" else None, seed=zlib.crc32(layer[0].encode()) & 0xffff)
+
+
+@pytest.mark.parametrize("kind", ["bf16", "qs8"])
+def test_every_algo_variant_agrees(kind):
+    """fastrun executes every available algo: each tile width gets its own parity run."""
+    from . import _gpu as G
+    d = K.make_desc(kind, 2, 128, 14, 14, 512, 3, pad=1, nonline=C.NL_RELU, has_z=True)
+    algos = G.available_algos(d)
+    assert len(algos) >= 3
+    for a, _name in algos:
+        _check(d, {"algo": a})
+
+
+@pytest.mark.parametrize("nl", [C.NL_IDENTITY, C.NL_RELU, C.NL_H_SWISH])
+@pytest.mark.parametrize("has_z", [False, True])
+def test_int8_epilogue_matrix(nl, has_z):
+    """IDENTITY/RELU/H_SWISH x {no z, z} with ~1% saturation: 0 mismatching bytes."""
+    d = K.make_desc("qs8", 3, 64, 9, 9, 64, 3, pad=1, nonline=nl, has_z=has_z, scales=(0.37, 0.71, None, 1.9, 23.0))
+    _check(d, {"int_range": 127, "bias_range": 5000}, seed=77 + nl)
+
+
+def test_batch_stride_noncontiguous_src():
+    """AlgoBase must accept a non-contiguous batch stride (dnn/src/cuda/conv_bias/algo.h:32-37)."""
+    import torch
+    from . import _gpu as G
+    d = K.make_desc("bf16", 3, 64, 10, 10, 64, 3, pad=1, nonline=C.NL_RELU)
+    src, flt, bias, z = K.gen_inputs(d, 5)
+    want_f32 = K.fp32_reference(d, src, flt, bias, z)
+    img = d.ih * d.iw * d.ic
+    bstride = img + 256
+    padded = np.zeros(d.n * bstride, dtype=np.uint16)
+    for n in range(d.n):
+        padded[n * bstride:n * bstride + img] = src[n * img:(n + 1) * img]
+    d2 = d.copy()
+    d2.src_batch_stride = bstride
+    got, _ = G.run_gpu(d2, padded, flt, bias, z)
+    ok, info = G.compare(d, got, None, want_f32)
+    assert ok, info
+
+
+def test_full_size_batch_independence_and_sampled_oracle():
+    """BASELINE full size (N=256): (i) the N=256 output restricted to the first 2 images equals the
+    N=2 run bit for bit (batch independence, SURVEY 8c protocol ii); (ii) a random sample of outputs
+    matches the oracle."""
+    import torch
+    from . import _gpu as G
+    layer = [l for l in K.RESNET50_LAYERS if l[0] == "l3.bN.c2"][0]
+    d = K.resnet50_desc(layer, "bf16", 256)
+    src, flt, bias, z = K.gen_inputs(d, 11)
+    got, _ = G.run_gpu(d, src, flt, bias, z)
+    d2 = K.resnet50_desc(layer, "bf16", 2)
+    n_src2, n_dst2 = 2 * d.ih * d.iw * d.ic, 2 * d.oh * d.ow * d.oc
+    got2, _ = G.run_gpu(d2, src[:n_src2], flt, bias, None if z is None else z[:n_dst2])
+    assert np.array_equal(got[:n_dst2], got2)
+    rng = np.random.default_rng(3)
+    idx = rng.integers(0, got.size, 4096).astype(np.uint64)
+    d32 = d.copy()
+    d32.src_dtype = d32.filter_dtype = d32.dst_dtype = d32.bias_dtype = C.DT_F32
+    d32.compute_mode = C.COMPUTE_DEFAULT
+    up = lambda a: O.to_f32(a, d.src_dtype) if a is not None else None
+    want = O.oracle_convbias_sample(d32, up(src), up(flt), up(bias), up(z), idx)
+    err = O.megdnn_rel_err(O.to_f32(got, d.dst_dtype)[idx.astype(np.int64)], want)
+    assert err.max() <= 1e-2, err.max()
+
+
+def test_full_size_int8_linearity_property():
+    """Size-independent property at N=256: with IDENTITY, no z, QuantizedS32 dst, conv is linear:
+    conv(a) + conv(b) - conv(a+b) == bias  (exact in int32)."""
+    from . import _gpu as G
+    d = K.make_desc("qs8", 256, 64, 28, 28, 64, 3, pad=1, dst_kind="qs32")
+    src_a, flt, bias, _ = K.gen_inputs(d, 21, int_range=40)
+    src_b = np.random.default_rng(22).integers(-40, 41, src_a.size, dtype=np.int8)
+    ya, _ = G.run_gpu(d, src_a, flt, bias, None)
+    yb, _ = G.run_gpu(d, src_b, flt, bias, None)
+    yab, _ = G.run_gpu(d, (src_a + src_b).astype(np.int8), flt, bias, None)
+    resid = ya.astype(np.int64) + yb - yab
+    assert np.array_equal(resid.reshape(-1, d.oc), np.broadcast_to(bias.astype(np.int64), (resid.size // d.oc, d.oc)))
+
+
+def test_host_mirror_exec_matches_capi():
+    """The megdnn-style Python operator (Handle / ConvBiasForward.exec) drives the same kernels."""
+    import torch
+    import megengine_b200 as mb
+    from . import _gpu as G
+    d = K.make_desc("bf16", 2, 64, 14, 14, 128, 3, pad=1, nonline=C.NL_RELU, has_z=True)
+    src, flt, bias, z = K.gen_inputs(d, 9)
+    got_capi, _ = G.run_gpu(d, src, flt, bias, z)
+    h = mb.Handle("cuda:0")
+    opr = h.create_operator()
+    opr.param.format = mb.Param.Format.NHWC
+    opr.param.nonlineMode = mb.Param.NonlineMode.RELU
+    opr.param.pad_h = opr.param.pad_w = 1
+    opr.param.compute_mode = mb.Param.ComputeMode.FLOAT32
+    bf = mb.dtype.BFloat16()
+    t = lambda a, shape: torch.from_numpy(a.view(np.int16)).cuda().view(torch.bfloat16).reshape(shape)
+    tsrc, tflt = t(src, (2, 14, 14, 64)), t(flt, (128, 3, 3, 64))
+    tbias, tz = t(bias, (1, 1, 1, 128)), t(z, (2, 14, 14, 128))
+    tdst = torch.empty((2, 14, 14, 128), dtype=torch.bfloat16, device="cuda")
+    S, F, B, Z, D = (mb.make_tensor(x, bf) for x in (tsrc, tflt, tbias, tz, tdst))
+    assert tuple(opr.deduce_layout(S.layout, F.layout, B.layout, Z.layout).shape) == (2, 14, 14, 128)
+    assert opr.get_workspace_in_bytes(S.layout, F.layout, B.layout, Z.layout, D.layout) == 0
+    opr.exec(S, F, B, Z, D)
+    torch.cuda.synchronize()
+    got = tdst.view(torch.int16).cpu().numpy().view(np.uint16).reshape(-1)
+    assert np.array_equal(got, got_capi)
