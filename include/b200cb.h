@@ -22,6 +22,9 @@
  *   b200cb_algo_count/name/query_algo
  *                        <- AlgoPack::all_algos + get_all_algorithms
  *                           dnn/src/cuda/conv_bias/algo.cpp:7-108, opr_impl.cpp:30-42
+ *   b200cb_plan_use_preprocessed_filter
+ *                        <- ConvBiasForward::exec(..., preprocessed_filter, ...)
+ *                           dnn/include/megdnn/oprs/nn.h:381-391,400-447
  *   b200cb_strerror      <- megdnn_throw / cuda_check message text
  *                           dnn/src/cuda/utils.cuh:16-29
  *
@@ -136,6 +139,11 @@ size_t b200cb_preprocessed_filter_bytes(const b200cb_plan* plan);
 int b200cb_preprocess_filter(
         const b200cb_plan* plan, const void* filter, void* packed, void* stream);
 
+/* Marks `plan` as running on a filter already packed by b200cb_preprocess_filter (megdnn's
+ * exec(..., preprocessed_filter, ...) path, dnn/include/megdnn/oprs/nn.h:400-447): b200cb_launch then
+ * takes the packed buffer as `filter` and the plan's workspace_bytes drops to what that case needs. */
+int b200cb_plan_use_preprocessed_filter(b200cb_plan* plan);
+
 /* number of kernels b200cb_launch enqueues for this plan (for launch accounting) */
 int b200cb_plan_num_launches(const b200cb_plan* plan);
 
@@ -146,6 +154,10 @@ size_t b200cb_host_scratch_bytes(const b200cb_plan* plan);
 int b200cb_exec_host(
         const b200cb_plan* plan, const void* src, const void* filter, const void* bias,
         const void* z, void* dst, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
+
+/* Device self-tests (synchronise `stream`). which == 0: the requantize epilogue's reciprocal-based
+ * division against IEEE division over all 2^32 dividends; *mismatches must come back 0. */
+int b200cb_selftest(int which, void* stream, uint64_t* mismatches);
 
 const char* b200cb_strerror(int code);
 /* text of the last CUDA/driver failure on this thread ("" if none) */

@@ -72,7 +72,9 @@ SYMBOLS = [
      [ctypes.POINTER(Plan), _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
     ("b200cb_preprocessed_filter_bytes", ctypes.c_size_t, [ctypes.POINTER(Plan)]),
     ("b200cb_preprocess_filter", ctypes.c_int, [ctypes.POINTER(Plan), _P, _P, _P]),
+    ("b200cb_plan_use_preprocessed_filter", ctypes.c_int, [ctypes.POINTER(Plan)]),
     ("b200cb_plan_num_launches", ctypes.c_int, [ctypes.POINTER(Plan)]),
+    ("b200cb_selftest", ctypes.c_int, [ctypes.c_int, _P, ctypes.POINTER(ctypes.c_uint64)]),
     ("b200cb_host_scratch_bytes", ctypes.c_size_t, [ctypes.POINTER(Plan)]),
     ("b200cb_exec_host", ctypes.c_int,
      [ctypes.POINTER(Plan), _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),

@@ -72,7 +72,7 @@ int validate_desc(const b200cb_desc* d) {
 double igemm_cost(const b200cb_desc& d, uint32_t bn, int sms) {
     const uint32_t in_es = d.src_dtype == B200CB_DT_QS8 ? 1 : 2;
     const uint32_t kb_elems = IGEMM_KBYTES / in_es;
-    const double num_kb = (double)d.fh * d.fw * ((d.ic + kb_elems - 1) / kb_elems);
+    const double num_kb = (double)d.fh * d.fw * ((d.ic + kb_elems - 1) / kb_elems);  // 128-byte K-blocks
     const double M = (double)d.n * d.oh * d.ow;
     const double m_tiles = ceil(M / IGEMM_BLOCK_M);
     const double n_tiles = ceil((double)d.oc / bn);
@@ -178,24 +178,45 @@ int b200cb_launch(
 int b200cb_plan_num_launches(const b200cb_plan* plan) {
     if (!plan || plan->magic != PLAN_MAGIC)
         return 0;
+    // W-folded stem without weight preprocess: filter re-pack + conv
+    if (plan->kernel == KERNEL_IGEMM && plan->reserved[4] && !plan->reserved[3])
+        return 2;
     return 1;
 }
 
 size_t b200cb_preprocessed_filter_bytes(const b200cb_plan* plan) {
-    // KRSC filters are consumed in place by TMA; no algorithm needs a packed copy yet.
-    (void)plan;
-    return 0;
+    // KRSC filters are consumed in place by TMA; only the W-folded stem needs a packed copy.
+    if (!plan || plan->magic != PLAN_MAGIC || plan->kernel != KERNEL_IGEMM)
+        return 0;
+    return igemm_packed_filter_bytes(*plan);
 }
 
 int b200cb_preprocess_filter(const b200cb_plan* plan, const void* filter, void* packed, void* stream) {
-    (void)filter;
-    (void)packed;
-    (void)stream;
     if (!plan)
         return B200CB_ERR_NULL;
     if (plan->magic != PLAN_MAGIC)
         return B200CB_ERR_BAD_PLAN;
+    if (plan->kernel != KERNEL_IGEMM || !plan->reserved[4])
+        return B200CB_OK;  // nothing to pack
+    if (!filter || !packed)
+        return B200CB_ERR_NULL;
+    return igemm_pack_filter(*plan, filter, packed, static_cast<cudaStream_t>(stream));
+}
+
+int b200cb_plan_use_preprocessed_filter(b200cb_plan* plan) {
+    if (!plan)
+        return B200CB_ERR_NULL;
+    if (plan->magic != PLAN_MAGIC)
+        return B200CB_ERR_BAD_PLAN;
+    if (plan->kernel == KERNEL_IGEMM && plan->reserved[4]) {
+        plan->reserved[3] = 1;
+        plan->workspace_bytes = 0;
+    }
     return B200CB_OK;
+}
+
+int b200cb_selftest(int which, void* stream, uint64_t* mismatches) {
+    return igemm_selftest(which, static_cast<cudaStream_t>(stream), mismatches);
 }
 
 namespace {

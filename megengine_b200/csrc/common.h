@@ -19,9 +19,8 @@ enum : int { KIND_BF16 = 0, KIND_F16 = 1, KIND_S8 = 2 };
 constexpr uint32_t MAX_DYN_SMEM = 232448;  // 227 KB opt-in limit per CTA on sm_100
 constexpr uint32_t IGEMM_BLOCK_M = 128;
 constexpr uint32_t IGEMM_KBYTES = 128;     // one k-block = one 128-byte swizzle row per pixel
-constexpr uint32_t IGEMM_HDR_BYTES = 2048; // barriers + tmem ptr + bias slice
 constexpr uint32_t IGEMM_EPI_BUF_BYTES = 16384;
-constexpr uint32_t IGEMM_MAX_STAGES = 8;
+constexpr uint32_t IGEMM_MAX_STAGES = 16;
 
 void set_last_error(const char* what, const char* detail);
 
@@ -41,6 +40,10 @@ int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan);
 int igemm_launch(
         const b200cb_plan& plan, const void* src, const void* filter, const void* bias,
         const void* z, void* dst, void* workspace, size_t workspace_bytes, cudaStream_t stream);
+// weight preprocess of the W-folded stem: packed size (0 = none needed) and the packing launch
+size_t igemm_packed_filter_bytes(const b200cb_plan& plan);
+int igemm_pack_filter(const b200cb_plan& plan, const void* filter, void* packed, cudaStream_t stream);
+int igemm_selftest(int which, cudaStream_t stream, uint64_t* mismatches);
 
 int dwconv_query(const b200cb_desc& d, b200cb_plan* plan);
 int dwconv_launch(

@@ -35,7 +35,7 @@ struct DwParams {
     uint64_t total_pg;  // N * OH * OWG
     uint64_t src_bstride, z_bstride, dst_bstride;  // elements
     uint32_t flip, has_bias, has_z, nonline;
-    float s_bias, s_z, s_dst;
+    RequantParams rq;
 };
 
 namespace {
@@ -279,7 +279,7 @@ __global__ void __launch_bounds__(256) dwconv_nhwc_kernel(const DwParams p) {
                     for (int b = 0; b < 4; ++b) {
                         const int32_t sfb = acc[t][4 * w + b] + bias[4 * w + b];
                         const int32_t zq = (int32_t)(int8_t)((zw[w] >> (8 * b)) & 0xff);
-                        const int32_t q = requant_s8(sfb, p.s_bias, p.has_z != 0, zq, p.s_z, p.nonline, p.s_dst);
+                        const int32_t q = requant_s8(sfb, zq, p.nonline, p.rq);
                         packed |= ((uint32_t)q & 0xff) << (8 * b);
                     }
                     o[w] = packed;
@@ -431,7 +431,7 @@ int dwconv_launch(
     p.has_bias = d.bias_mode != B200CB_BIAS_NONE;
     p.has_z = d.has_z;
     p.nonline = d.nonline_mode;
-    p.s_bias = d.bias_scale, p.s_z = d.z_scale, p.s_dst = d.dst_scale;
+    p.rq = make_requant(d);
 
     const uint32_t slices = p.CV / p.CVB;
     const uint64_t iters = (p.total_pg + p.PGB - 1) / p.PGB;

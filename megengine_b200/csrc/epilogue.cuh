@@ -10,9 +10,8 @@
 
 namespace b200cb {
 
-__device__ __forceinline__ float act_f(float x, uint32_t nl) {
-    if (nl == B200CB_NL_RELU)
-        return x <= 0.f ? 0.f : x;
+// H_SWISH / SIGMOID (the rare modes); RELU / IDENTITY are handled branch-free by the callers.
+__device__ __forceinline__ float act_generic(float x, uint32_t nl) {
     if (nl == B200CB_NL_H_SWISH)
         return __fmul_rn(__fmul_rn(x, fminf(fmaxf(__fadd_rn(x, 3.f), 0.f), 6.f)), 1.f / 6.f);
     if (nl == B200CB_NL_SIGMOID)
@@ -20,17 +19,57 @@ __device__ __forceinline__ float act_f(float x, uint32_t nl) {
     return x;
 }
 
+__device__ __forceinline__ float act_f(float x, uint32_t nl) {
+    if (nl == B200CB_NL_RELU)
+        return x <= 0.f ? 0.f : x;
+    if (nl == B200CB_NL_IDENTITY)
+        return x;
+    return act_generic(x, nl);
+}
+
+// Scalars of the QuantizedS8 requantize epilogue, prepared once on the host.
+struct RequantParams {
+    float s_bias;   // scale of the QuantizedS32 bias / accumulator tensor
+    float s_z;      // scale of z
+    float s_dst;    // scale of dst
+    float inv_dst;  // RN(1 / s_dst) when `fast_div`, unused otherwise
+    uint32_t fast_div;
+};
+
+// host: fills RequantParams from the descriptor's scales (defined in igemm_sm100.cu)
+RequantParams make_requant(const b200cb_desc& d);
+
+// r / s, correctly rounded (== IEEE fp32 division, what the oracle's `x / scale` computes).
+// Fast path: Markstein's sequence with y = RN(1/s) precomputed -- q0 = RN(r*y); e = r - q0*s (exact,
+// one FMA); q = RN(q0 + e*y) is the correctly rounded quotient whenever nothing overflows or
+// underflows.  Quotients too large for that guarantee saturate in the clamp that follows anyway, so
+// q0 is returned for them; b200cb_selftest(0) sweeps all 2^32 dividends against __fdiv_rn on the GPU.
+__device__ __forceinline__ float div_by_scale(float r, const RequantParams& q) {
+    if (q.fast_div) {
+        const float q0 = __fmul_rn(r, q.inv_dst);
+        const float e = __fmaf_rn(-q0, q.s_dst, r);
+        const float q1 = __fmaf_rn(e, q.inv_dst, q0);
+        return fabsf(q0) < 1048576.f ? q1 : q0;
+    }
+    return __fdiv_rn(r, q.s_dst);
+}
+
 // QuantizedS8 requantize, bit-exact restatement of the oracle: every step is one
-// IEEE fp32 RN operation, no FMA contraction, true division, roundf = half away from zero.
-__device__ __forceinline__ int32_t requant_s8(
-        int32_t sfb, float s_bias, bool has_z, int32_t zq, float s_z, uint32_t nl, float s_dst) {
-    float r = __fmul_rn(__int2float_rn(sfb), s_bias);
-    if (has_z)
-        r = __fadd_rn(r, __fmul_rn(__int2float_rn(zq), s_z));
-    r = act_f(r, nl);
-    float q = roundf(__fdiv_rn(r, s_dst));
-    q = fminf(fmaxf(-128.f, q), 127.f);
-    return __float2int_rn(q);
+// IEEE fp32 RN operation, no FMA contraction across steps, true division, roundf = half away.
+//   r = float(acc + bias) * s_bias  [+ float(z) * s_z]  ->  activation  ->  sat_s8(roundf(r / s_dst))
+// Without z the callers pass zq == 0 with s_z == 0: r + (+0) == r (a -0 becomes +0, which rounds to
+// the same int8).
+__device__ __forceinline__ float dequant_acc(int32_t sfb, int32_t zq, const RequantParams& q) {
+    const float r = __fmul_rn(__int2float_rn(sfb), q.s_bias);
+    return __fadd_rn(r, __fmul_rn(__int2float_rn(zq), q.s_z));
+}
+__device__ __forceinline__ int32_t quant_s8(float r, const RequantParams& q) {
+    float v = roundf(div_by_scale(r, q));
+    v = fminf(fmaxf(-128.f, v), 127.f);
+    return __float2int_rn(v);
+}
+__device__ __forceinline__ int32_t requant_s8(int32_t sfb, int32_t zq, uint32_t nl, const RequantParams& q) {
+    return quant_s8(act_f(dequant_acc(sfb, zq, q), nl), q);
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
@@ -49,6 +88,5 @@ __device__ __forceinline__ float f16lo(uint32_t v) {
 __device__ __forceinline__ float f16hi(uint32_t v) {
     return __half2float(__ushort_as_half(static_cast<unsigned short>(v >> 16)));
 }
-
 
 }  // namespace b200cb

@@ -1,23 +1,32 @@
 // Dense NHWC ConvBias as an implicit GEMM on Blackwell tensor cores (sm_100a).
 //
 //   GEMM view: M = N*OH*OW output pixels, N = OC, K = FH*FW*IC.
-//   A (activations) tiles: TMA im2col mode straight from the NHWC tensor -- 128 pixels x 128 bytes
+//   A (activations) tiles: TMA im2col mode straight from the NHWC tensor -- 128 pixels x KB bytes
 //     of channels per (filter tap, channel block); padding / stride / image wrap-around are done
-//     by the TMA unit (zero fill), so no im2col buffer ever exists in HBM.
-//   B (filter, KRSC) tiles: tiled TMA, BLOCK_N output channels x 128 bytes.
+//     by the TMA unit (zero fill), so no im2col buffer ever exists in HBM.  Pointwise stride-1
+//     convs use a plain tiled map over the (IC, M) matrix.
+//   B (filter, KRSC) tiles: tiled TMA, BLOCK_N output channels x KB bytes.
+//   K-block width KB is 128, 64 or 32 bytes (swizzle mode 128B / 64B / 32B) so that layers with few
+//     input channels do not multiply zero padding.  Stride-2 convs with <= 16 bytes of channels
+//     (the network stem, IC padded 3 -> 8) are "W-folded": pixel pairs are viewed as 2*IC channels,
+//     which turns the FWx stride-2 window into a ceil((FW+1)/2)x stride-1 window over a tensor of
+//     half the width; the filter is re-packed accordingly (workspace or weight-preprocess).
 //   MMA: tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=32 bytes per instruction, fp32 (bf16/fp16)
 //     or int32 (int8) accumulators in TMEM, double buffered so the epilogue of tile i overlaps
 //     the main loop of tile i+1.
-//   Epilogue: tcgen05.ld -> registers -> (+bias, +z, activation, requantize) -> swizzled smem
-//     -> TMA store. z tiles are prefetched by TMA into smem by a dedicated warp.
+//   Epilogue: 4 (16-bit) or 8 (int8) warps, each fully independent: tcgen05.ld of its 32 TMEM lanes
+//     -> registers -> (+bias, +z, activation, requantize) -> its own swizzled smem slab -> its own
+//     TMA store.  z tiles are prefetched by TMA into smem by a dedicated warp.
 //
 // Replaces (does not call) the reference algos listed in SURVEY.md 8(a13):
 //   dnn/src/cuda/conv_bias/implicit_gemm_int8_nhwc_imma.cpp, cudnn_conv_bias_activation.cpp,
 //   bfloat16.cpp.  Epilogue arithmetic follows the naive oracle
-//   dnn/src/naive/conv_bias/opr_impl.cpp:21-98 (see oracle/convbias_oracle.c).
+//   dnn/src/naive/conv_bias/opr_impl.cpp:21-98.
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
+#include <math.h>
 #include <stdio.h>
+#include <string.h>
 #include "common.h"
 #include "ptx.cuh"
 #include "epilogue.cuh"
@@ -27,20 +36,22 @@ namespace b200cb {
 struct IgemmParams {
     CUtensorMap tmA;  // activations: im2col (C,W,H,N) or tiled (C, M)
     CUtensorMap tmB;  // filter (IC, FH*FW, OC)
-    CUtensorMap tmD;  // dst (OC, M)
-    CUtensorMap tmZ;  // z   (OC, M)
+    CUtensorMap tmD;  // dst (OC, M), box = EPI_N x 32 rows (one epilogue warp)
+    CUtensorMap tmZ;  // z   (OC, M), box = EPI_N x 128 rows
     const void* bias;
-    uint32_t M, OC, IC;
-    uint32_t OH, OW;
-    uint32_t FH, FW;
+    uint32_t M, OC;
+    uint32_t OHW, OW;
+    uint32_t FW, num_taps;
     int32_t stride_h, stride_w, pad_h, pad_w, dil_h, dil_w;
-    uint32_t num_kc;  // channel blocks per tap
+    uint32_t num_kc;   // channel blocks per tap
+    uint32_t kb_bytes; // bytes of K per pipeline stage row: 128 / 64 / 32
+    uint32_t kb_elems;
     uint32_t m_tiles, n_tiles;
     uint32_t stages;
-    uint32_t a_mode;  // 0 tiled, 1 im2col
-    uint32_t flip;    // mode == CONVOLUTION
+    uint32_t a_mode;   // 0 tiled, 1 im2col
+    uint32_t flip;     // mode == CONVOLUTION
     uint32_t has_bias, has_z, nonline;
-    float s_bias, s_z, s_dst;
+    RequantParams rq;
 };
 
 namespace {
@@ -51,49 +62,63 @@ template <int KIND, int OUT32>
 struct Traits {
     static constexpr int IN_ES = (KIND == KIND_S8) ? 1 : 2;
     static constexpr int OUT_ES = OUT32 ? 4 : IN_ES;
-    static constexpr int KB_ELEMS = IGEMM_KBYTES / IN_ES;
     static constexpr int EPI_N = OUT32 ? 32 : 64;       // columns per epilogue chunk
     static constexpr int ROW_BYTES = EPI_N * OUT_ES;    // 128 (16-bit, 32-bit) or 64 (int8)
+    static constexpr int GROUPS = (KIND == KIND_S8 && !OUT32) ? 2 : 1;  // epilogue warp groups
+    static constexpr int THREADS = 128 + 128 * GROUPS;
+    static constexpr int SLAB_BYTES = 32 * ROW_BYTES;   // one warp's staging slab (32 rows)
+    static_assert(4 * GROUPS * 2 * SLAB_BYTES == 32768, "slab area is 32 KiB");
 };
 
+// shared memory map (offsets from the 1024-aligned base)
+constexpr uint32_t OFF_FULL = 0;       // [16] x 8
+constexpr uint32_t OFF_EMPTY = 128;    // [16] x 8
+constexpr uint32_t OFF_TFULL = 256;    // [2]
+constexpr uint32_t OFF_TEMPTY = 272;   // [2]
+constexpr uint32_t OFF_ZFULL = 288;    // [2]
+constexpr uint32_t OFF_ZEMPTY = 304;   // [2]
+constexpr uint32_t OFF_TMEM = 320;
+constexpr uint32_t OFF_BIAS = 1024;    // (4 * GROUPS) warps x BN x 4 bytes, rounded up to 1 KiB
+constexpr uint32_t SLABS_BYTES = 32768;  // (4 * GROUPS) warps x 2 slabs x SLAB_BYTES == 32 KiB always
+__host__ __device__ constexpr uint32_t off_sd(uint32_t groups, uint32_t bn) {
+    return OFF_BIAS + ((4 * groups * bn * 4 + 1023u) & ~1023u);
+}
+// z staging: 2 x 16 KiB right after the slabs (only if has_z), then the pipeline stages
+
 template <int KIND, int BN, int OUT32>
-__global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ IgemmParams p) {
+__global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
+        igemm_kernel(const __grid_constant__ IgemmParams p) {
     using T = Traits<KIND, OUT32>;
-    constexpr uint32_t A_BYTES = IGEMM_BLOCK_M * IGEMM_KBYTES;  // 16 KiB
-    constexpr uint32_t B_BYTES = BN * IGEMM_KBYTES;
-    constexpr uint32_t STAGE_BYTES = A_BYTES + B_BYTES;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
     constexpr uint32_t NUM_CHUNKS = BN / T::EPI_N;
-    constexpr uint32_t UMMA_LAYOUT_SW128 = 2;
     constexpr uint32_t IDESC =
             (KIND == KIND_S8) ? umma_idesc(2, 1, 128, BN)
                               : umma_idesc(1, KIND == KIND_BF16 ? 1 : 0, 128, BN);
 
-    extern __shared__ uint8_t smem_raw[];
-    const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-    uint8_t* smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    const uint32_t smem_base = smem_u32(smem_raw);
+    uint8_t* smem_gen = smem_raw;
+    if (smem_base & 1023u)
+        __trap();  // swizzled TMA / UMMA tiles need a 1024-byte aligned window
+    constexpr uint32_t OFF_SD = off_sd(T::GROUPS, BN);
+    constexpr uint32_t OFF_SZ = OFF_SD + SLABS_BYTES;
 
-    // header layout
-    const uint32_t bar_full = smem_base;               // [MAX_STAGES] x 8
-    const uint32_t bar_empty = smem_base + 64;         // [MAX_STAGES] x 8
-    const uint32_t bar_tfull = smem_base + 128;        // [2]
-    const uint32_t bar_tempty = smem_base + 144;       // [2]
-    const uint32_t bar_zfull = smem_base + 160;        // [2]
-    const uint32_t bar_zempty = smem_base + 176;       // [2]
-    const uint32_t tmem_slot = smem_base + 192;
-    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + 192);
-    uint32_t* sbias = reinterpret_cast<uint32_t*>(smem_gen + 1024);  // BN x 4 bytes
+    const uint32_t bar_full = smem_base + OFF_FULL;
+    const uint32_t bar_empty = smem_base + OFF_EMPTY;
+    const uint32_t bar_tfull = smem_base + OFF_TFULL;
+    const uint32_t bar_tempty = smem_base + OFF_TEMPTY;
+    const uint32_t bar_zfull = smem_base + OFF_ZFULL;
+    const uint32_t bar_zempty = smem_base + OFF_ZEMPTY;
+    volatile uint32_t* tmem_slot_gen = reinterpret_cast<volatile uint32_t*>(smem_gen + OFF_TMEM);
 
-    const uint32_t sD = smem_base + IGEMM_HDR_BYTES;                       // 2 x 16 KiB
-    const uint32_t sZ = sD + 2 * IGEMM_EPI_BUF_BYTES;                      // 2 x 16 KiB (if has_z)
-    const uint32_t sStage = sZ + (p.has_z ? 2 * IGEMM_EPI_BUF_BYTES : 0);  // stages
-    uint8_t* sD_gen = smem_gen + IGEMM_HDR_BYTES;
-    uint8_t* sZ_gen = sD_gen + 2 * IGEMM_EPI_BUF_BYTES;
+    const uint32_t a_bytes = IGEMM_BLOCK_M * p.kb_bytes;
+    const uint32_t stage_bytes = a_bytes + BN * p.kb_bytes;
+    const uint32_t sZ = smem_base + OFF_SZ;
+    const uint32_t sStage = sZ + (p.has_z ? 2 * IGEMM_EPI_BUF_BYTES : 0);
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
-    const uint32_t num_taps = p.FH * p.FW;
-    const uint32_t num_kb = num_taps * p.num_kc;
+    const uint32_t num_kb = p.num_taps * p.num_kc;
     const uint32_t total_tiles = p.m_tiles * p.n_tiles;
 
     if (warp == 0 && lane == 0) {
@@ -110,14 +135,14 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
         }
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 4);  // one arrive per epilogue warp
+            mbar_init(bar_tempty + 8 * i, 4 * T::GROUPS);  // one arrive per epilogue warp
             mbar_init(bar_zfull + 8 * i, 1);
-            mbar_init(bar_zempty + 8 * i, 1);
+            mbar_init(bar_zempty + 8 * i, 4);               // the 4 warps of the consuming group
         }
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(tmem_slot, TMEM_COLS);
+        tmem_alloc(smem_base + OFF_TMEM, TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -128,27 +153,26 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     if (warp == 0) {
         // ============================ TMA producer (A, B) ============================
         uint32_t stage = 0, phase = 0;
-        const uint32_t OHW = p.OH * p.OW;
         for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const uint32_t m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
             const int32_t m0 = static_cast<int32_t>(m_blk * IGEMM_BLOCK_M);
             const int32_t n0 = static_cast<int32_t>(n_blk * BN);
-            const uint32_t img = static_cast<uint32_t>(m0) / OHW;
-            const uint32_t rem = static_cast<uint32_t>(m0) % OHW;
+            const uint32_t img = static_cast<uint32_t>(m0) / p.OHW;
+            const uint32_t rem = static_cast<uint32_t>(m0) % p.OHW;
             const int32_t base_h = static_cast<int32_t>(rem / p.OW) * p.stride_h - p.pad_h;
             const int32_t base_w = static_cast<int32_t>(rem % p.OW) * p.stride_w - p.pad_w;
-            for (uint32_t tap = 0; tap < num_taps; ++tap) {
-                const uint32_t fh = tap / p.FW, fw = tap % p.FW;
+            uint32_t fh = 0, fw = 0;
+            for (uint32_t tap = 0; tap < p.num_taps; ++tap) {
                 // mode CONVOLUTION reads the spatially flipped filter tap for the same src pixel
-                const uint32_t btap = p.flip ? (num_taps - 1 - tap) : tap;
+                const uint32_t btap = p.flip ? (p.num_taps - 1 - tap) : tap;
                 for (uint32_t kc = 0; kc < p.num_kc; ++kc) {
                     mbar_wait(bar_empty + 8 * stage, phase ^ 1);
                     if (lane == 0) {
                         const uint32_t full = bar_full + 8 * stage;
-                        const uint32_t sa = sStage + stage * STAGE_BYTES;
-                        const uint32_t sb = sa + A_BYTES;
-                        const int32_t c0 = static_cast<int32_t>(kc * T::KB_ELEMS);
-                        mbar_arrive_expect_tx(full, STAGE_BYTES);
+                        const uint32_t sa = sStage + stage * stage_bytes;
+                        const uint32_t sb = sa + a_bytes;
+                        const int32_t c0 = static_cast<int32_t>(kc * p.kb_elems);
+                        mbar_arrive_expect_tx(full, stage_bytes);
                         if (p.a_mode == 0) {
                             tma_load_2d(sa, &p.tmA, full, c0, m0);
                         } else {
@@ -165,11 +189,19 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                         phase ^= 1;
                     }
                 }
+                if (++fw == p.FW) {
+                    fw = 0;
+                    ++fh;
+                }
             }
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+        const uint32_t mma_per_kb = p.kb_bytes / 32;
+        // UMMA layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B; SBO = 8 rows
+        const uint32_t layout = p.kb_bytes == 128 ? 2u : (p.kb_bytes == 64 ? 4u : 6u);
+        const uint32_t sbo = 8 * p.kb_bytes;
         for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
@@ -178,12 +210,11 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                 mbar_wait(bar_full + 8 * stage, phase);
                 tc_fence_after();
                 if (lane == 0) {
-                    const uint32_t sa = sStage + stage * STAGE_BYTES;
-                    const uint32_t sb = sa + A_BYTES;
-#pragma unroll
-                    for (uint32_t k = 0; k < IGEMM_KBYTES / 32; ++k) {
-                        const uint64_t adesc = umma_smem_desc(sa + k * 32, 1024, UMMA_LAYOUT_SW128);
-                        const uint64_t bdesc = umma_smem_desc(sb + k * 32, 1024, UMMA_LAYOUT_SW128);
+                    const uint32_t sa = sStage + stage * stage_bytes;
+                    const uint32_t sb = sa + a_bytes;
+                    for (uint32_t k = 0; k < mma_per_kb; ++k) {
+                        const uint64_t adesc = umma_smem_desc(sa + k * 32, sbo, layout);
+                        const uint64_t bdesc = umma_smem_desc(sb + k * 32, sbo, layout);
                         if constexpr (KIND == KIND_S8)
                             mma_i8(taddr, adesc, bdesc, IDESC, (kb | k) != 0);
                         else
@@ -206,7 +237,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
     } else if (warp == 2) {
         // ============================ z prefetch (TMA) ============================
         if (p.has_z) {
-            uint32_t zb = 0, zphase = 0;
+            uint32_t cnt = 0;
             for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
                 const uint32_t m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
                 const int32_t m0 = static_cast<int32_t>(m_blk * IGEMM_BLOCK_M);
@@ -214,6 +245,7 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                     const uint32_t col0 = n_blk * BN + c * T::EPI_N;
                     if (col0 >= p.OC)
                         break;
+                    const uint32_t zb = cnt & 1, zphase = (cnt >> 1) & 1;
                     mbar_wait(bar_zempty + 8 * zb, zphase ^ 1);
                     if (lane == 0) {
                         mbar_arrive_expect_tx(bar_zfull + 8 * zb, IGEMM_BLOCK_M * T::ROW_BYTES);
@@ -222,23 +254,33 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                                 static_cast<int32_t>(col0), m0);
                     }
                     __syncwarp();
-                    zb ^= 1;
-                    if (zb == 0)
-                        zphase ^= 1;
+                    ++cnt;
                 }
             }
         }
     } else if (warp >= 4) {
         // ============================ epilogue ============================
-        const uint32_t et = threadIdx.x - 128;  // 0..127 == row of the tile == TMEM lane
+        // warp e = warp - 4: TMEM lane quadrant (e & 3) == rows [32*(e&3), +32) of the tile;
+        // group (e >> 2) handles the chunks c with c % GROUPS == group.
+        const uint32_t e = warp - 4;
         const uint32_t quad = warp & 3;
-        uint32_t acc = 0, acc_phase = 0, zb = 0, zphase = 0, db = 0;
+        const uint32_t group = e >> 2;
+        const uint32_t row = quad * 32 + lane;            // row of the tile == TMEM lane
+        uint32_t* sbias = reinterpret_cast<uint32_t*>(smem_gen + OFF_BIAS) + e * BN;
+        const uint32_t slab_u32 = smem_base + OFF_SD + e * 2 * T::SLAB_BYTES;
+        uint8_t* slab_gen = smem_gen + OFF_SD + e * 2 * T::SLAB_BYTES;
+        const uint8_t* sZ_gen = smem_gen + OFF_SZ;
+        // RELU: x <= 0 ? 0 : x;  IDENTITY: the same select against -inf (a no-op) -- branch-free
+        const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
+        const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
+        uint32_t acc = 0, acc_phase = 0, cnt = 0, db = 0;
         for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const uint32_t m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
             const int32_t m0 = static_cast<int32_t>(m_blk * IGEMM_BLOCK_M);
             const uint32_t n0 = n_blk * BN;
-            // bias slice of this tile -> smem (as fp32 for float kinds, int32 for int8)
-            for (uint32_t i = et; i < BN; i += 128) {
+            // bias slice of this tile -> the warp's private smem (fp32 for float kinds, int32 for int8)
+            __syncwarp();
+            for (uint32_t i = lane; i < BN; i += 32) {
                 uint32_t v = 0;
                 if (p.has_bias && n0 + i < p.OC) {
                     if constexpr (KIND == KIND_S8) {
@@ -254,29 +296,44 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                 }
                 sbias[i] = v;
             }
-            named_bar_sync(1, 128);
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
-            tc_fence_after();
+            __syncwarp();
             uint32_t nchunks = 0;
+#pragma unroll
             for (uint32_t c = 0; c < NUM_CHUNKS; ++c)
                 if (n0 + c * T::EPI_N < p.OC)
                     nchunks = c + 1;
-            for (uint32_t c = 0; c < nchunks; ++c) {
+            // last chunk this warp's group owns (decides when TMEM can be handed back)
+            int32_t last_c = -1;
+            for (uint32_t c = group; c < nchunks; c += T::GROUPS)
+                last_c = static_cast<int32_t>(c);
+            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            tc_fence_after();
+            if (last_c < 0) {
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    mbar_arrive(bar_tempty + 8 * acc);
+            }
+#pragma unroll 1
+            for (uint32_t c = 0; c < nchunks; ++c, ++cnt) {
+                if (T::GROUPS > 1 && (c % T::GROUPS) != group)
+                    continue;
                 const uint32_t col0 = n0 + c * T::EPI_N;
-                // staging buffer db must have been drained by the TMA store issued 2 chunks ago
-                if (et == 0)
+                const uint32_t zb = cnt & 1, zphase = (cnt >> 1) & 1;
+                // slab db must have been drained by the TMA store issued 2 chunks ago
+                if (lane == 0)
                     tma_store_wait_read<1>();
-                named_bar_sync(1, 128);
+                __syncwarp();
                 if (p.has_z)
                     mbar_wait(bar_zfull + 8 * zb, zphase);
-                uint8_t* drow = sD_gen + db * IGEMM_EPI_BUF_BYTES;
-                const uint8_t* zrow = sZ_gen + zb * IGEMM_EPI_BUF_BYTES;
+                uint8_t* drow = slab_gen + db * T::SLAB_BYTES + lane * T::ROW_BYTES;
+                const uint8_t* zrow = sZ_gen + zb * IGEMM_EPI_BUF_BYTES + row * T::ROW_BYTES;
 #pragma unroll
                 for (uint32_t h = 0; h < T::EPI_N / 32; ++h) {
                     uint32_t r[32];
                     tmem_ld_32x32(tmem_base + ((quad * 32) << 16) + acc * BN + c * T::EPI_N + h * 32, r);
                     tmem_ld_wait();
-                    if (c == nchunks - 1 && h == T::EPI_N / 32 - 1) {
+                    if (static_cast<int32_t>(c) == last_c && h == T::EPI_N / 32 - 1) {
                         // accumulator fully drained into registers: hand TMEM back to the MMA warp
                         tc_fence_before();
                         __syncwarp();
@@ -285,90 +342,135 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
                     }
                     const uint32_t* bcol = sbias + c * T::EPI_N + h * 32;
                     constexpr uint32_t COLS_PER_16B = 16 / T::OUT_ES;
+                    constexpr uint32_t PIECES = 32 / COLS_PER_16B;  // 16-byte pieces per 32 columns
+                    if constexpr (KIND == KIND_S8 && OUT32) {
+                        // QuantizedS32 destination: dst = acc + bias (IDENTITY, no z)
 #pragma unroll
-                    for (uint32_t j = 0; j < 32 / COLS_PER_16B; ++j) {
-                        // 16-byte piece j of this half-chunk of row `et`
-                        const uint32_t off = ptx::swizzle_off<T::ROW_BYTES>(
-                                et * T::ROW_BYTES + h * 32 * T::OUT_ES + j * 16);
-                        uint4 zv = make_uint4(0, 0, 0, 0);
-                        if (p.has_z)
-                            zv = *reinterpret_cast<const uint4*>(zrow + off);
-                        uint4 ov;
-                        if constexpr (KIND == KIND_S8 && OUT32) {
-                            // QuantizedS32 destination: dst = acc + bias (IDENTITY, no z)
-                            const uint32_t* rr = r + j * 4;
-                            const uint32_t* bb = bcol + j * 4;
-                            ov.x = rr[0] + bb[0];
-                            ov.y = rr[1] + bb[1];
-                            ov.z = rr[2] + bb[2];
-                            ov.w = rr[3] + bb[3];
-                        } else if constexpr (KIND == KIND_S8) {
-                            const uint32_t* rr = r + j * 16;
-                            const uint32_t* bb = bcol + j * 16;
-                            uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+                        for (uint32_t j = 0; j < PIECES; ++j) {
+                            const uint4 bv = *reinterpret_cast<const uint4*>(bcol + j * 4);
+                            uint4 ov;
+                            ov.x = r[j * 4 + 0] + bv.x;
+                            ov.y = r[j * 4 + 1] + bv.y;
+                            ov.z = r[j * 4 + 2] + bv.z;
+                            ov.w = r[j * 4 + 3] + bv.w;
+                            const uint32_t off = (h * PIECES + j) ^ (lane & 7);
+                            *reinterpret_cast<uint4*>(drow + off * 16) = ov;
+                        }
+                    } else if constexpr (KIND == KIND_S8) {
+                        float x[32];
+#pragma unroll
+                        for (uint32_t j = 0; j < PIECES; ++j) {
+                            // 64-byte rows, SWIZZLE_64B: 16-byte piece index ^= (row >> 1) & 3
+                            const uint32_t off = (h * PIECES + j) ^ ((lane >> 1) & 3);
+                            uint4 zv = make_uint4(0, 0, 0, 0);
+                            if (p.has_z)
+                                zv = *reinterpret_cast<const uint4*>(zrow + off * 16);
+                            const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+                            for (uint32_t w = 0; w < 4; ++w) {
+                                const uint4 bv = *reinterpret_cast<const uint4*>(bcol + j * 16 + w * 4);
+                                const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                                for (uint32_t b = 0; b < 4; ++b) {
+                                    const int32_t sfb = static_cast<int32_t>(r[j * 16 + w * 4 + b] + bb[b]);
+                                    const int32_t zq = static_cast<int32_t>(
+                                            static_cast<int8_t>((zw[w] >> (8 * b)) & 0xff));
+                                    // no z: zq == 0 and s_z == 0, r + (+0) leaves r unchanged
+                                    x[j * 16 + w * 4 + b] = dequant_acc(sfb, zq, p.rq);
+                                }
+                            }
+                        }
+                        if (generic_act) {
+#pragma unroll
+                            for (uint32_t i = 0; i < 32; ++i)
+                                x[i] = act_generic(x[i], p.nonline);
+                        } else {
+#pragma unroll
+                            for (uint32_t i = 0; i < 32; ++i)
+                                x[i] = x[i] <= act_lo ? act_lo : x[i];
+                        }
+#pragma unroll
+                        for (uint32_t j = 0; j < PIECES; ++j) {
+                            const uint32_t off = (h * PIECES + j) ^ ((lane >> 1) & 3);
                             uint32_t ow[4];
 #pragma unroll
                             for (uint32_t w = 0; w < 4; ++w) {
                                 uint32_t packed = 0;
 #pragma unroll
-                                for (uint32_t b = 0; b < 4; ++b) {
-                                    const int32_t sfb = static_cast<int32_t>(rr[w * 4 + b] + bb[w * 4 + b]);
-                                    const int32_t zq = static_cast<int32_t>(
-                                            static_cast<int8_t>((zw[w] >> (8 * b)) & 0xff));
-                                    const int32_t q = requant_s8(
-                                            sfb, p.s_bias, p.has_z != 0, zq, p.s_z, p.nonline, p.s_dst);
-                                    packed |= (static_cast<uint32_t>(q) & 0xff) << (8 * b);
-                                }
+                                for (uint32_t b = 0; b < 4; ++b)
+                                    packed |= (static_cast<uint32_t>(quant_s8(x[j * 16 + w * 4 + b], p.rq)) & 0xff)
+                                              << (8 * b);
                                 ow[w] = packed;
                             }
-                            ov = make_uint4(ow[0], ow[1], ow[2], ow[3]);
-                        } else {
-                            const uint32_t* rr = r + j * 8;
-                            const uint32_t* bb = bcol + j * 8;
-                            uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
-                            uint32_t ow[4];
+                            *reinterpret_cast<uint4*>(drow + off * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                        }
+                    } else {
+                        float x[32];
 #pragma unroll
-                            for (uint32_t w = 0; w < 4; ++w) {
-                                float x0 = __uint_as_float(rr[2 * w]) + __uint_as_float(bb[2 * w]);
-                                float x1 = __uint_as_float(rr[2 * w + 1]) + __uint_as_float(bb[2 * w + 1]);
-                                if (p.has_z) {
+                        for (uint32_t j = 0; j < 8; ++j) {
+                            const uint4 bv = *reinterpret_cast<const uint4*>(bcol + j * 4);
+                            x[j * 4 + 0] = __uint_as_float(r[j * 4 + 0]) + __uint_as_float(bv.x);
+                            x[j * 4 + 1] = __uint_as_float(r[j * 4 + 1]) + __uint_as_float(bv.y);
+                            x[j * 4 + 2] = __uint_as_float(r[j * 4 + 2]) + __uint_as_float(bv.z);
+                            x[j * 4 + 3] = __uint_as_float(r[j * 4 + 3]) + __uint_as_float(bv.w);
+                        }
+                        if (p.has_z) {
+#pragma unroll
+                            for (uint32_t j = 0; j < PIECES; ++j) {
+                                const uint32_t off = (h * PIECES + j) ^ (lane & 7);
+                                const uint4 zv = *reinterpret_cast<const uint4*>(zrow + off * 16);
+                                const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+                                for (uint32_t w = 0; w < 4; ++w) {
                                     if constexpr (KIND == KIND_BF16) {
-                                        x0 += bf16lo(zw[w]);
-                                        x1 += bf16hi(zw[w]);
+                                        x[j * 8 + 2 * w] += bf16lo(zw[w]);
+                                        x[j * 8 + 2 * w + 1] += bf16hi(zw[w]);
                                     } else {
-                                        x0 += f16lo(zw[w]);
-                                        x1 += f16hi(zw[w]);
+                                        x[j * 8 + 2 * w] += f16lo(zw[w]);
+                                        x[j * 8 + 2 * w + 1] += f16hi(zw[w]);
                                     }
                                 }
-                                x0 = act_f(x0, p.nonline);
-                                x1 = act_f(x1, p.nonline);
-                                ow[w] = (KIND == KIND_BF16) ? pack_bf16x2(x0, x1) : pack_f16x2(x0, x1);
                             }
-                            ov = make_uint4(ow[0], ow[1], ow[2], ow[3]);
                         }
-                        *reinterpret_cast<uint4*>(drow + off) = ov;
+                        if (generic_act) {
+#pragma unroll
+                            for (uint32_t i = 0; i < 32; ++i)
+                                x[i] = act_generic(x[i], p.nonline);
+                        } else {
+#pragma unroll
+                            for (uint32_t i = 0; i < 32; ++i)
+                                x[i] = x[i] <= act_lo ? act_lo : x[i];
+                        }
+#pragma unroll
+                        for (uint32_t j = 0; j < PIECES; ++j) {
+                            uint32_t ow[4];
+#pragma unroll
+                            for (uint32_t w = 0; w < 4; ++w)
+                                ow[w] = (KIND == KIND_BF16)
+                                                ? pack_bf16x2(x[j * 8 + 2 * w], x[j * 8 + 2 * w + 1])
+                                                : pack_f16x2(x[j * 8 + 2 * w], x[j * 8 + 2 * w + 1]);
+                            const uint32_t off = (h * PIECES + j) ^ (lane & 7);
+                            *reinterpret_cast<uint4*>(drow + off * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                        }
                     }
                 }
                 fence_proxy_async_smem();
-                named_bar_sync(1, 128);
-                if (et == 0) {
-                    tma_store_2d(&p.tmD, sD + db * IGEMM_EPI_BUF_BYTES, static_cast<int32_t>(col0), m0);
-                    tma_store_commit();
+                __syncwarp();
+                if (lane == 0) {
                     if (p.has_z)
                         mbar_arrive(bar_zempty + 8 * zb);
+                    tma_store_2d(
+                            &p.tmD, slab_u32 + db * T::SLAB_BYTES, static_cast<int32_t>(col0),
+                            m0 + static_cast<int32_t>(quad * 32));
+                    tma_store_commit();
                 }
                 db ^= 1;
-                if (p.has_z) {
-                    zb ^= 1;
-                    if (zb == 0)
-                        zphase ^= 1;
-                }
             }
             acc ^= 1;
             if (acc == 0)
                 acc_phase ^= 1;
         }
-        if (et == 0)
+        if (lane == 0)
             tma_store_wait<0>();
     }
 
@@ -378,6 +480,53 @@ __global__ void __launch_bounds__(256, 1) igemm_kernel(const __grid_constant__ I
         tc_fence_after();
         tmem_dealloc(tmem_base, TMEM_COLS);
     }
+}
+
+// Re-packs a KRSC filter for the W-folded stem (see file header): (OC, FH, FW, IC) ->
+// (OC, FH, FW2, 2*IC) where folded tap t2, channel half hf holds original tap fw = 2*t2 + hf - shift
+// (zero when outside [0, FW)).  One thread per output element.
+template <typename E>
+__global__ void fold_filter_kernel(
+        const E* __restrict__ src, E* __restrict__ dst, uint32_t OC, uint32_t FH, uint32_t FW,
+        uint32_t IC, uint32_t FW2, uint32_t shift) {
+    const uint32_t total = OC * FH * FW2 * 2 * IC;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t c2 = i % (2 * IC);
+        const uint32_t t2 = (i / (2 * IC)) % FW2;
+        const uint32_t fh = (i / (2 * IC * FW2)) % FH;
+        const uint32_t oc = i / (2 * IC * FW2 * FH);
+        const int32_t fw = static_cast<int32_t>(2 * t2 + c2 / IC) - static_cast<int32_t>(shift);
+        E v = E(0);
+        if (fw >= 0 && fw < static_cast<int32_t>(FW))
+            v = src[((static_cast<size_t>(oc) * FH + fh) * FW + fw) * IC + c2 % IC];
+        dst[i] = v;
+    }
+}
+
+// Self-test 0: sweeps every fp32 dividend against a set of scales and counts the cases where the
+// fast division of the requantize epilogue differs from IEEE division (a) as a quotient, when the
+// quotient is below the saturation guard, or (b) after roundf + clamp to int8.
+__global__ void selftest_div_kernel(const float* scales, int nscales, unsigned long long* bad) {
+    unsigned long long local = 0;
+    for (int si = 0; si < nscales; ++si) {
+        RequantParams q;
+        q.s_bias = 1.f, q.s_z = 0.f, q.s_dst = scales[si], q.inv_dst = 1.0f / scales[si], q.fast_div = 1;
+        RequantParams ref = q;
+        ref.fast_div = 0;
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+             i < (1ull << 32); i += (unsigned long long)gridDim.x * blockDim.x) {
+            const float r = __uint_as_float(static_cast<uint32_t>(i));
+            if (!isfinite(r))
+                continue;
+            const float a = div_by_scale(r, q), b = div_by_scale(r, ref);
+            if (fabsf(b) < 524288.f && __float_as_uint(a) != __float_as_uint(b))
+                ++local;
+            if (quant_s8(r, q) != quant_s8(r, ref))
+                ++local;
+        }
+    }
+    if (local)
+        atomicAdd(bad, local);
 }
 
 template <int KIND, int BN, int OUT32>
@@ -393,15 +542,96 @@ cudaError_t launch_variant(const IgemmParams& p, uint32_t grid, uint32_t smem, c
             return e;
         attr_set[dev] = true;
     }
-    kern<<<grid, 256, smem, stream>>>(p);
+    kern<<<grid, Traits<KIND, OUT32>::THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }
 
-uint32_t stage_bytes(uint32_t bn) {
-    return IGEMM_BLOCK_M * IGEMM_KBYTES + bn * IGEMM_KBYTES;
+// geometry actually fed to the kernel (differs from the descriptor when the conv is W-folded)
+struct Geometry {
+    uint32_t ic, iw, fw, stride_w;
+    int32_t pad_w_lo, pad_w_hi;
+    uint32_t fold_shift;  // zero taps prepended to the filter row
+    bool folded;
+};
+
+Geometry make_geometry(const b200cb_desc& d, uint32_t in_es) {
+    Geometry g;
+    g.ic = d.ic, g.iw = d.iw, g.fw = d.fw, g.stride_w = d.stride_w;
+    g.pad_w_lo = (int32_t)d.pad_w;
+    g.pad_w_hi = (int32_t)d.pad_w;
+    g.fold_shift = 0;
+    g.folded = false;
+    if (d.stride_w == 2 && d.dilate_w == 1 && d.iw % 2 == 0 && d.ic * in_es <= 16 &&
+        d.mode == B200CB_MODE_CROSS_CORRELATION && d.src_batch_stride == 0) {
+        // window of output ow covers pixels [2*ow - pad, 2*ow - pad + FW); extend it to an even start
+        // and an even length: pixel pairs [ow - pad_lo2, ow - pad_lo2 + FW2)
+        const uint32_t shift = d.pad_w & 1;
+        const uint32_t fw_ext = d.fw + shift;
+        const uint32_t fw2 = (fw_ext + 1) / 2;
+        const int32_t pad_lo2 = (int32_t)((d.pad_w + shift) / 2);
+        const int32_t iw2 = (int32_t)(d.iw / 2);
+        const int32_t pad_hi2 = (int32_t)d.ow + (int32_t)fw2 - 1 - iw2 - pad_lo2;
+        g.ic = d.ic * 2, g.iw = d.iw / 2, g.fw = fw2, g.stride_w = 1;
+        g.pad_w_lo = pad_lo2, g.pad_w_hi = pad_hi2;
+        g.fold_shift = shift;
+        g.folded = true;
+    }
+    return g;
+}
+
+uint32_t pick_kb_bytes(uint32_t ic_bytes) {
+    return ic_bytes > 64 ? 128u : (ic_bytes > 32 ? 64u : 32u);
+}
+
+uint32_t fixed_smem(uint32_t groups, uint32_t bn, bool has_z) {
+    return off_sd(groups, bn) + SLABS_BYTES + (has_z ? 2 * IGEMM_EPI_BUF_BYTES : 0);
 }
 
 }  // namespace
+
+RequantParams make_requant(const b200cb_desc& d) {
+    RequantParams q;
+    // absent bias: the accumulator's own scale s_src * s_flt (float product, dnn/src/common/utils.cpp:218-236)
+    q.s_bias = d.bias_dtype == B200CB_DT_QS32 ? d.bias_scale : d.src_scale * d.filter_scale;
+    q.s_z = d.has_z ? d.z_scale : 0.f;
+    q.s_dst = d.dst_scale;
+    const float y = 1.0f / d.dst_scale;
+    q.inv_dst = y;
+    q.fast_div = (isnormal(d.dst_scale) && isnormal(y) && d.dst_scale > 0.f) ? 1u : 0u;
+    return q;
+}
+
+int igemm_selftest(int which, cudaStream_t stream, uint64_t* mismatches) {
+    if (which != 0 || !mismatches)
+        return B200CB_UNSUPPORTED_PARAM;
+    const float h_scales[8] = {19.99f, 0.3f, 0.41f, 0.9f, 1.0f, 0.11f, 3.0e-3f, 1.7e4f};
+    float* d_scales = nullptr;
+    unsigned long long* d_bad = nullptr;
+    cudaError_t e = cudaMalloc(&d_scales, sizeof(h_scales));
+    if (e == cudaSuccess)
+        e = cudaMalloc(&d_bad, sizeof(unsigned long long));
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(d_scales, h_scales, sizeof(h_scales), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess)
+        e = cudaMemsetAsync(d_bad, 0, sizeof(unsigned long long), stream);
+    if (e == cudaSuccess) {
+        selftest_div_kernel<<<148 * 16, 256, 0, stream>>>(d_scales, 8, d_bad);
+        e = cudaGetLastError();
+    }
+    unsigned long long bad = 0;
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(&bad, d_bad, sizeof(bad), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess)
+        e = cudaStreamSynchronize(stream);
+    cudaFree(d_scales);
+    cudaFree(d_bad);
+    if (e != cudaSuccess) {
+        set_last_error("selftest", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    *mismatches = bad;
+    return B200CB_OK;
+}
 
 // --------------------------------------------------------------------------- host side
 int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
@@ -444,6 +674,10 @@ int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
             return B200CB_UNSUPPORTED_DTYPE;
         if (d.has_z && d.z_dtype != d.dst_dtype)
             return B200CB_UNSUPPORTED_DTYPE;
+        // fp16/bf16 kernels accumulate in fp32 (ComputeMode::FLOAT32); fp16 DEFAULT means fp16
+        // accumulation in the oracle (naive/conv_bias/opr_impl.cpp:266) -- not this algorithm.
+        if (kind == KIND_F16 && d.compute_mode != B200CB_COMPUTE_FLOAT32)
+            return B200CB_UNSUPPORTED_PARAM;
     }
     if (d.bias_mode == B200CB_BIAS_FULL)
         return B200CB_UNSUPPORTED_PARAM;
@@ -481,9 +715,16 @@ int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
     if (block_n > 64 && block_n / 2 >= d.oc)
         return B200CB_UNSUPPORTED_SHAPE;
 
-    const uint32_t fixed = 1024 + IGEMM_HDR_BYTES + 2 * IGEMM_EPI_BUF_BYTES +
-                           (d.has_z ? 2 * IGEMM_EPI_BUF_BYTES : 0);
-    uint32_t stages = (MAX_DYN_SMEM - fixed) / stage_bytes(block_n);
+    b200cb_desc dd = d;
+    if (d.src_batch_stride == src_img)
+        dd.src_batch_stride = 0;
+    const Geometry g = make_geometry(dd, in_es);
+    if (g.folded && (g.pad_w_hi - (int32_t)(g.fw - 1) < -128 || g.pad_w_lo > 127))
+        return B200CB_UNSUPPORTED_PARAM;
+    const uint32_t kb_bytes = pick_kb_bytes(g.ic * in_es);
+    const uint32_t stage_b = (IGEMM_BLOCK_M + block_n) * kb_bytes;
+    const uint32_t fixed = fixed_smem((kind == KIND_S8 && !out32) ? 2 : 1, block_n, d.has_z);
+    uint32_t stages = (MAX_DYN_SMEM - fixed) / stage_b;
     if (stages > IGEMM_MAX_STAGES)
         stages = IGEMM_MAX_STAGES;
     if (stages < 2)
@@ -494,30 +735,66 @@ int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
     plan->block_n = block_n;
     plan->stages = stages;
     plan->grid = 0;  // resolved at launch from the device's SM count
-    plan->smem_bytes = fixed + stages * stage_bytes(block_n);
+    plan->smem_bytes = fixed + stages * stage_b;
     const bool pointwise = d.fh == 1 && d.fw == 1 && d.stride_h == 1 && d.stride_w == 1 &&
-                           d.pad_h == 0 && d.pad_w == 0 &&
-                           (d.src_batch_stride == 0 || d.src_batch_stride == src_img);
+                           d.pad_h == 0 && d.pad_w == 0 && dd.src_batch_stride == 0;
     plan->a_mode = pointwise ? 0 : 1;
     for (auto& r : plan->reserved)
         r = 0;
     plan->reserved[0] = static_cast<uint32_t>(kind);
     plan->reserved[1] = out32 ? 1 : 0;
-    plan->workspace_bytes = 0;
+    plan->reserved[3] = 0;  // 1: `filter` passed to launch is already packed (weight preprocess)
+    plan->reserved[4] = g.folded ? 1 : 0;
+    plan->reserved[5] = kb_bytes;
+    // folded stem: the re-packed filter lives in the workspace unless it was preprocessed
+    plan->workspace_bytes =
+            g.folded ? (((uint64_t)d.oc * d.fh * g.fw * g.ic * in_es + 255) & ~255ull) : 0;
     plan->desc = d;
+    return B200CB_OK;
+}
+
+size_t igemm_packed_filter_bytes(const b200cb_plan& plan) {
+    if (!plan.reserved[4])
+        return 0;
+    const b200cb_desc& d = plan.desc;
+    const uint32_t in_es = plan.reserved[0] == KIND_S8 ? 1 : 2;
+    const Geometry g = make_geometry(d, in_es);
+    return (size_t)d.oc * d.fh * g.fw * g.ic * in_es;
+}
+
+int igemm_pack_filter(const b200cb_plan& plan, const void* filter, void* packed, cudaStream_t stream) {
+    if (!plan.reserved[4])
+        return B200CB_OK;
+    const b200cb_desc& d = plan.desc;
+    const uint32_t in_es = plan.reserved[0] == KIND_S8 ? 1 : 2;
+    const Geometry g = make_geometry(d, in_es);
+    const uint32_t total = d.oc * d.fh * g.fw * g.ic;
+    const uint32_t blocks = (total + 255) / 256;
+    if (in_es == 1)
+        fold_filter_kernel<int8_t><<<blocks, 256, 0, stream>>>(
+                static_cast<const int8_t*>(filter), static_cast<int8_t*>(packed), d.oc, d.fh, d.fw,
+                d.ic, g.fw, g.fold_shift);
+    else
+        fold_filter_kernel<uint16_t><<<blocks, 256, 0, stream>>>(
+                static_cast<const uint16_t*>(filter), static_cast<uint16_t*>(packed), d.oc, d.fh,
+                d.fw, d.ic, g.fw, g.fold_shift);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("fold_filter launch", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
     return B200CB_OK;
 }
 
 int igemm_launch(
         const b200cb_plan& plan, const void* src, const void* filter, const void* bias,
-        const void* z, void* dst, void* /*workspace*/, size_t /*workspace_bytes*/,
+        const void* z, void* dst, void* workspace, size_t /*workspace_bytes*/,
         cudaStream_t stream) {
     const b200cb_desc& d = plan.desc;
     const int kind = static_cast<int>(plan.reserved[0]);
     const bool out32 = plan.reserved[1] != 0;
     const uint32_t in_es = kind == KIND_S8 ? 1 : 2;
     const uint32_t out_es = out32 ? 4 : in_es;
-    const uint32_t kb_elems = IGEMM_KBYTES / in_es;
     const uint32_t epi_n = out32 ? 32 : 64;
     const uint32_t row_bytes = epi_n * out_es;
     const uint32_t BN = plan.block_n;
@@ -528,6 +805,26 @@ int igemm_launch(
     if (!src || !filter || !dst || (d.bias_mode != B200CB_BIAS_NONE && !bias) || (d.has_z && !z))
         return B200CB_ERR_NULL;
 
+    b200cb_desc dd = d;
+    const uint64_t src_img = (uint64_t)d.ih * d.iw * d.ic;
+    if (d.src_batch_stride == src_img)
+        dd.src_batch_stride = 0;
+    const Geometry g = make_geometry(dd, in_es);
+    const uint32_t kb_bytes = pick_kb_bytes(g.ic * in_es);
+    const uint32_t kb_elems = kb_bytes / in_es;
+    const CUtensorMapSwizzle in_swz = kb_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                                      : kb_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                       : CU_TENSOR_MAP_SWIZZLE_32B;
+    const void* flt = filter;
+    if (g.folded && !plan.reserved[3]) {
+        if (!workspace)
+            return B200CB_ERR_WORKSPACE;
+        int rc = igemm_pack_filter(plan, filter, workspace, stream);
+        if (rc != B200CB_OK)
+            return rc;
+        flt = workspace;
+    }
+
     IgemmParams p;
     memset(&p, 0, sizeof(p));
     const uint64_t M = (uint64_t)d.n * d.oh * d.ow;
@@ -536,28 +833,27 @@ int igemm_launch(
                             : (kind == KIND_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16
                                                  : CU_TENSOR_MAP_DATA_TYPE_FLOAT16);
     const CUtensorMapDataType out_dt = out32 ? CU_TENSOR_MAP_DATA_TYPE_INT32 : in_dt;
-    const uint64_t src_bstride = d.src_batch_stride ? d.src_batch_stride : (uint64_t)d.ih * d.iw * d.ic;
+    const uint64_t src_bstride = d.src_batch_stride ? d.src_batch_stride : src_img;
     CUresult cr;
     if (a_mode == 0) {
         uint64_t dims[2] = {d.ic, M};
         uint64_t strides[1] = {(uint64_t)d.ic * in_es};
         uint32_t box[2] = {kb_elems, IGEMM_BLOCK_M};
         cr = encode_tiled(
-                &p.tmA, in_dt, 2, src, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                &p.tmA, in_dt, 2, src, dims, strides, box, nullptr, in_swz,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     } else {
-        uint64_t dims[4] = {d.ic, d.iw, d.ih, d.n};
+        uint64_t dims[4] = {g.ic, g.iw, d.ih, d.n};
         uint64_t strides[3] = {
-                (uint64_t)d.ic * in_es, (uint64_t)d.iw * d.ic * in_es, src_bstride * in_es};
-        int lower[2] = {-(int)d.pad_w, -(int)d.pad_h};
+                (uint64_t)g.ic * in_es, (uint64_t)g.iw * g.ic * in_es, src_bstride * in_es};
+        int lower[2] = {-g.pad_w_lo, -(int)d.pad_h};
         int upper[2] = {
-                (int)d.pad_w - (int)((d.fw - 1) * d.dilate_w),
+                g.pad_w_hi - (int)((g.fw - 1) * d.dilate_w),
                 (int)d.pad_h - (int)((d.fh - 1) * d.dilate_h)};
-        uint32_t estr[4] = {1, d.stride_w, d.stride_h, 1};
+        uint32_t estr[4] = {1, g.stride_w, d.stride_h, 1};
         cr = encode_im2col(
                 &p.tmA, in_dt, 4, src, dims, strides, lower, upper, kb_elems, IGEMM_BLOCK_M, estr,
-                CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-                src_bstride * in_es * d.n);
+                in_swz, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, src_bstride * in_es * d.n);
     }
     if (cr != CUDA_SUCCESS) {
         char buf[96];
@@ -566,11 +862,11 @@ int igemm_launch(
         return B200CB_ERR_DRIVER;
     }
     {
-        uint64_t dims[3] = {d.ic, (uint64_t)d.fh * d.fw, d.oc};
-        uint64_t strides[2] = {(uint64_t)d.ic * in_es, (uint64_t)d.fh * d.fw * d.ic * in_es};
+        uint64_t dims[3] = {g.ic, (uint64_t)d.fh * g.fw, d.oc};
+        uint64_t strides[2] = {(uint64_t)g.ic * in_es, (uint64_t)d.fh * g.fw * g.ic * in_es};
         uint32_t box[3] = {kb_elems, 1, BN};
         cr = encode_tiled(
-                &p.tmB, in_dt, 3, filter, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                &p.tmB, in_dt, 3, flt, dims, strides, box, nullptr, in_swz,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
         if (cr != CUDA_SUCCESS) {
             char buf[64];
@@ -583,12 +879,13 @@ int igemm_launch(
         const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
         uint64_t dims[2] = {d.oc, M};
         uint64_t strides[1] = {(uint64_t)d.oc * out_es};
-        uint32_t box[2] = {epi_n, IGEMM_BLOCK_M};
+        uint32_t box_d[2] = {epi_n, 32};
+        uint32_t box_z[2] = {epi_n, IGEMM_BLOCK_M};
         cr = encode_tiled(
-                &p.tmD, out_dt, 2, dst, dims, strides, box, nullptr, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE);
+                &p.tmD, out_dt, 2, dst, dims, strides, box_d, nullptr, swz, CU_TENSOR_MAP_L2_PROMOTION_NONE);
         if (cr == CUDA_SUCCESS && d.has_z)
             cr = encode_tiled(
-                    &p.tmZ, out_dt, 2, z, dims, strides, box, nullptr, swz,
+                    &p.tmZ, out_dt, 2, z, dims, strides, box_z, nullptr, swz,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
         if (cr != CUDA_SUCCESS) {
             char buf[64];
@@ -600,18 +897,19 @@ int igemm_launch(
     p.bias = bias;
     p.M = (uint32_t)M;
     p.OC = d.oc;
-    p.IC = d.ic;
-    p.OH = d.oh;
+    p.OHW = d.oh * d.ow;
     p.OW = d.ow;
-    p.FH = d.fh;
-    p.FW = d.fw;
+    p.FW = g.fw;
+    p.num_taps = d.fh * g.fw;
     p.stride_h = d.stride_h;
-    p.stride_w = d.stride_w;
+    p.stride_w = g.stride_w;
     p.pad_h = d.pad_h;
-    p.pad_w = d.pad_w;
+    p.pad_w = g.pad_w_lo;
     p.dil_h = d.dilate_h;
     p.dil_w = d.dilate_w;
-    p.num_kc = (d.ic + kb_elems - 1) / kb_elems;
+    p.kb_bytes = kb_bytes;
+    p.kb_elems = kb_elems;
+    p.num_kc = (g.ic + kb_elems - 1) / kb_elems;
     p.m_tiles = (uint32_t)((M + IGEMM_BLOCK_M - 1) / IGEMM_BLOCK_M);
     p.n_tiles = (d.oc + BN - 1) / BN;
     p.stages = plan.stages;
@@ -620,9 +918,7 @@ int igemm_launch(
     p.has_bias = d.bias_mode != B200CB_BIAS_NONE;
     p.has_z = d.has_z;
     p.nonline = d.nonline_mode;
-    p.s_bias = d.bias_scale;
-    p.s_z = d.z_scale;
-    p.s_dst = d.dst_scale;
+    p.rq = make_requant(d);
 
     const uint64_t total = (uint64_t)p.m_tiles * p.n_tiles;
     uint32_t grid = plan.grid ? plan.grid : (uint32_t)device_sm_count();

@@ -48,7 +48,18 @@ def stage_cases(stage):
                 ("c3_bf16_dil2", md("bf16", 2, 64, 14, 14, 64, 3, pad=2, dilate=2), {}),
                 ("c3_bf16_flip", md("bf16", 2, 64, 9, 9, 64, 3, pad=1, mode=1), {}),
                 ("c3_f16", md("f16", 2, 64, 14, 14, 128, 3, pad=1, nonline=1, has_z=True), {}),
-                ("c3_bf16_big", md("bf16", 8, 128, 28, 28, 128, 3, pad=1, nonline=1), {})]
+                ("c3_bf16_big", md("bf16", 8, 128, 28, 28, 128, 3, pad=1, nonline=1), {}),
+                # narrow K-blocks (SWIZZLE_64B / 32B) and the W-folded stride-2 stem
+                ("c3_bf16_ic32_sw64", md("bf16", 2, 32, 14, 14, 64, 3, pad=1, nonline=1), {}),
+                ("c3_bf16_ic16_sw32", md("bf16", 2, 16, 14, 14, 64, 3, pad=1, nonline=1, has_z=True), {}),
+                ("c3_bf16_ic24_sw64_tail", md("bf16", 2, 24, 14, 14, 64, 3, pad=1), {}),
+                ("c3_bf16_ic8_s1", md("bf16", 2, 8, 14, 14, 64, 3, pad=1, nonline=1), {}),
+                ("fold_c7_bf16_ic8", md("bf16", 2, 8, 30, 30, 64, 7, stride=2, pad=3, nonline=1), {}),
+                ("fold_c3_bf16_ic8_p1", md("bf16", 2, 8, 18, 18, 64, 3, stride=2, pad=1, nonline=1), {}),
+                ("fold_c3_bf16_ic8_p0", md("bf16", 2, 8, 18, 18, 64, 3, stride=2, pad=0), {}),
+                ("fold_c5_f16_ic8_p2", md("f16", 2, 8, 20, 20, 128, 5, stride=2, pad=2, nonline=1), {}),
+                ("fold_c2_bf16_ic8_p0", md("bf16", 1, 8, 16, 16, 64, 2, stride=2, pad=0), {}),
+                ("nofold_c3_bf16_ic8_oddw", md("bf16", 2, 8, 17, 17, 64, 3, stride=2, pad=1), {})]
     if stage == "int8":
         sc = (1.2, 1.3, None, 0.7, 19.99)
         return [("q_pw", md("qs8", 2, 128, 14, 14, 64, 1, nonline=0, scales=sc), {}),
@@ -60,7 +71,14 @@ def stage_cases(stage):
                                       bias_mode=C.BIAS_NONE, scales=sc), {}),
                 ("q_pw_qs32", md("qs8", 2, 64, 14, 14, 64, 1, dst_kind="qs32"), {}),
                 ("q_c3_stress", md("qs8", 2, 256, 14, 14, 256, 3, pad=1, nonline=1, has_z=True,
-                                   scales=(0.013, 0.021, None, 0.05, 0.9)), {"int_range": 127, "bias_range": 5000})]
+                                   scales=(0.013, 0.021, None, 0.05, 0.9)), {"int_range": 127, "bias_range": 5000}),
+                ("q_fold_c7_ic16", md("qs8", 2, 16, 30, 30, 64, 7, stride=2, pad=3, nonline=1, scales=sc),
+                 {"int_range": 127}),
+                ("q_c3_ic32_sw32", md("qs8", 2, 32, 14, 14, 64, 3, pad=1, nonline=1, has_z=True, scales=sc), {}),
+                ("q_c3_ic64_sw64_oc512", md("qs8", 2, 64, 14, 14, 512, 3, pad=1, nonline=3, has_z=True,
+                                            scales=(0.11, 0.23, None, 0.37, 0.41)), {"int_range": 127}),
+                ("q_pw_oc192_tail", md("qs8", 3, 128, 7, 7, 192, 1, nonline=1, has_z=True, scales=sc), {"algo": 1}),
+                ("q_denormal_dst_scale", md("qs8", 1, 64, 7, 7, 64, 1, scales=(0.1, 0.2, None, 0.3, 1e-39)), {})]
     if stage == "dw":
         out = []
         for kind in ("bf16", "f16", "f32", "qs8"):

@@ -168,3 +168,63 @@ def test_host_mirror_exec_matches_capi():
     torch.cuda.synchronize()
     got = tdst.view(torch.int16).cpu().numpy().view(np.uint16).reshape(-1)
     assert np.array_equal(got, got_capi)
+
+
+def test_requant_division_selftest():
+    """the epilogue's reciprocal-based division == IEEE division for all 2^32 dividends (8 scales)."""
+    import ctypes
+    import torch
+    lib = C.load()
+    bad = ctypes.c_uint64(123)
+    rc = lib.b200cb_selftest(0, torch.cuda.current_stream().cuda_stream, ctypes.byref(bad))
+    assert rc == 0 and bad.value == 0, (rc, bad.value)
+
+
+@pytest.mark.parametrize("kind", ["bf16", "qs8"])
+def test_stem_weight_preprocess_path(kind):
+    """exec_preprocess + exec(preprocessed_filter) (nn.h:400-447) == the workspace path, bit for bit."""
+    import ctypes
+    import torch
+    from . import _gpu as G
+    lib = C.load()
+    d = K.make_desc(kind, 2, 16 if kind == "qs8" else 8, 30, 30, 64, 7, stride=2, pad=3, nonline=C.NL_RELU,
+                    scales=(1.2, 1.3, None, 0.7, 19.99))
+    src, flt, bias, z = K.gen_inputs(d, 17, int_range=127)
+    want, plan = G.run_gpu(d, src, flt, bias, z)
+    assert plan.workspace_bytes > 0 and lib.b200cb_plan_num_launches(ctypes.byref(plan)) == 2
+    nbytes = lib.b200cb_preprocessed_filter_bytes(ctypes.byref(plan))
+    assert nbytes == d.oc * d.fh * 4 * (2 * d.ic) * (1 if kind == "qs8" else 2)
+    tflt = G.to_dev(flt)
+    packed = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.b200cb_preprocess_filter(ctypes.byref(plan), tflt.data_ptr(), packed.data_ptr(), s) == 0
+    assert lib.b200cb_plan_use_preprocessed_filter(ctypes.byref(plan)) == 0
+    assert plan.workspace_bytes == 0 and lib.b200cb_plan_num_launches(ctypes.byref(plan)) == 1
+    tsrc, tbias = G.to_dev(src), G.to_dev(bias)
+    tdst = torch.zeros(O.dst_elems(d), dtype=torch.int8 if kind == "qs8" else torch.int16, device="cuda")
+    G.launch(plan, tsrc, packed, tbias, None, tdst)
+    torch.cuda.synchronize()
+    got = tdst.cpu().numpy()
+    assert np.array_equal(got.view(want.dtype), want)
+
+
+@pytest.mark.parametrize("meta,want", __import__("tests.golden.make_golden", fromlist=["load"]).load(),
+                         ids=[m["name"] for m, _ in __import__("tests.golden.make_golden", fromlist=["load"]).load()])
+def test_gpu_matches_golden_reference_outputs(meta, want):
+    """CUDA path vs the committed outputs of the reference's own naive operator (tests/golden)."""
+    from . import _gpu as G
+    from .golden import make_golden as GG
+    d = GG.dict_to_desc(meta["desc"])
+    rc, _ = G.plan_for(d)
+    if rc != 0:
+        pytest.skip("cell outside the B200 algo family's is_available matrix: " + C.strerror(rc))
+    opt = meta["opt"]
+    src, flt, bias, z = K.gen_inputs(d, meta["seed"], int_range=opt.get("int_range", 8),
+                                     bias_range=opt.get("bias_range", 50))
+    got, _ = G.run_gpu(d, src, flt, bias, z)
+    if d.dst_dtype in (C.DT_QS8, C.DT_QS32):
+        assert np.array_equal(got, want)
+    else:
+        want_f32 = K.fp32_reference(d, src, flt, bias, z) if d.dst_dtype != C.DT_F32 else None
+        ok, info = G.compare(d, got, want, want_f32)
+        assert ok, info
