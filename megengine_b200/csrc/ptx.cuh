@@ -83,6 +83,14 @@ __device__ __forceinline__ void tma_load_3d(
             "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
             : "memory");
 }
+__device__ __forceinline__ void tma_load_4d(
+        uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1, int32_t c2, int32_t c3) {
+    asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5, %6}], [%2];" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+            : "memory");
+}
 // im2col mode, NHWC tensor seen as (C, W, H, N): coordinates are the channel start and the
 // *base pixel* (top-left tap of the window, may be negative); {off_w, off_h} select the tap.
 __device__ __forceinline__ void tma_load_im2col_4d(
@@ -100,6 +108,14 @@ __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int
             "cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
                     reinterpret_cast<uint64_t>(tmap)),
             "r"(src), "r"(c0), "r"(c1)
+            : "memory");
+}
+__device__ __forceinline__ void tma_store_3d(
+        const void* tmap, uint32_t src, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+            "cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(
+                    reinterpret_cast<uint64_t>(tmap)),
+            "r"(src), "r"(c0), "r"(c1), "r"(c2)
             : "memory");
 }
 __device__ __forceinline__ void tma_store_commit() {
@@ -193,6 +209,19 @@ __device__ __forceinline__ uint64_t umma_smem_desc(uint32_t saddr, uint32_t sbo_
     uint64_t d = 0;
     d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
     d |= static_cast<uint64_t>(1) << 16;
+    d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(layout & 7) << 61;
+    return d;
+}
+// K-major operand without swizzle ("interleaved" core matrices): a core matrix is 8 rows x 16 bytes
+// stored as 128 contiguous bytes; LBO = byte distance between the two core matrices of one K=32-byte
+// step, SBO = byte distance between consecutive 8-row groups.
+__device__ __forceinline__ uint64_t umma_smem_desc_lbo(
+        uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((saddr >> 4) & 0x3FFF);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFF) << 16;
     d |= static_cast<uint64_t>((sbo_bytes >> 4) & 0x3FFF) << 32;
     d |= static_cast<uint64_t>(1) << 46;
     d |= static_cast<uint64_t>(layout & 7) << 61;

@@ -59,6 +59,16 @@ def stage_cases(stage):
                 ("fold_c3_bf16_ic8_p0", md("bf16", 2, 8, 18, 18, 64, 3, stride=2, pad=0), {}),
                 ("fold_c5_f16_ic8_p2", md("f16", 2, 8, 20, 20, 128, 5, stride=2, pad=2, nonline=1), {}),
                 ("fold_c2_bf16_ic8_p0", md("bf16", 1, 8, 16, 16, 64, 2, stride=2, pad=0), {}),
+                ("stem_c3_bf16_wide_ow150", md("bf16", 1, 8, 20, 300, 64, 3, stride=2, pad=1, nonline=1), {}),
+                ("stem_c3_bf16_oc32_z", md("bf16", 2, 8, 18, 18, 32, 3, stride=2, pad=1, nonline=1, has_z=True), {}),
+                ("stem_c7_f16_ic8_hswish", md("f16", 1, 8, 34, 34, 64, 7, stride=2, pad=3, nonline=3), {}),
+                # rows mode (resident input rows + resident filter)
+                ("rows_c3_bf16_56", md("bf16", 2, 64, 56, 56, 64, 3, pad=1, nonline=1), {}),
+                ("rows_c3_bf16_7x7_n3", md("bf16", 3, 64, 7, 7, 64, 3, pad=1, nonline=1), {}),
+                ("rows_c5_f16_oc32", md("f16", 2, 64, 20, 13, 32, 5, pad=2, nonline=3), {}),
+                ("rows_c3_bf16_padh0", md("bf16", 2, 64, 12, 17, 64, 3, pad=0, pad_w=1), {}),
+                ("rows_c1x3_bf16", md("bf16", 2, 64, 9, 30, 64, 1, fw=3, pad=0, pad_w=1, nonline=1), {}),
+                ("rows_c3_bf16_ic128_oc16", md("bf16", 1, 128, 10, 10, 16, 3, pad=1), {}),
                 ("nofold_c3_bf16_ic8_oddw", md("bf16", 2, 8, 17, 17, 64, 3, stride=2, pad=1), {})]
     if stage == "int8":
         sc = (1.2, 1.3, None, 0.7, 19.99)
