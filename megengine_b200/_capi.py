@@ -7,7 +7,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libb200cb.so")
+LIB_PATH = os.environ.get("B200CB_LIB") or os.path.join(_HERE, "lib", "libb200cb.so")
 
 # enums (values == megdnn's, see include/b200cb.h)
 FORMAT_NCHW, FORMAT_NHWC, FORMAT_NCHW4 = 0, 1, 3

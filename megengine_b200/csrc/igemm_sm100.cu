@@ -26,6 +26,7 @@
 #include <cuda_fp16.h>
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.h"
 #include "ptx.cuh"
@@ -62,11 +63,46 @@ struct IgemmParams {
     uint32_t flip;     // mode == CONVOLUTION
     uint32_t has_bias, has_z, nonline;
     RequantParams rq;
+    long long* dbg;   // -DB200CB_DEBUG_TIMING builds only: 148 x 3 roles x 9 counters
 };
 
 namespace {
 
 using namespace ptx;
+
+// Optional in-kernel wait-time accounting (build with -DB200CB_DEBUG_TIMING, see tools/): each warp
+// role accumulates the cycles it spends blocked on each mbarrier class; CTA 0..gridDim write 8 counters.
+#ifdef B200CB_DEBUG_TIMING
+#define TIMED_WAIT(slot, bar, parity)                  \
+    do {                                               \
+        const long long t0__ = clock64();              \
+        mbar_wait(bar, parity);                        \
+        dbg_acc[slot] += clock64() - t0__;             \
+    } while (0)
+#else
+#define TIMED_WAIT(slot, bar, parity) mbar_wait(bar, parity)
+#endif
+
+// UMMA shared-memory descriptor split into its 32-bit halves so that the single MMA-issuing thread
+// advances operands with one integer add instead of rebuilding 64-bit descriptors:
+//   lo = (addr >> 4) | (LBO >> 4) << 16        hi = (SBO >> 4) | version 1 << 14 | layout << 29
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+    return ((saddr >> 4) & 0x3FFFu) | ((lbo_bytes >> 4) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
+    return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+template <int KIND>
+__device__ __forceinline__ void mma_issue(
+        uint32_t taddr, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+        uint32_t accumulate) {
+    const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | a_lo;
+    const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | b_lo;
+    if constexpr (KIND == KIND_S8)
+        mma_i8(taddr, adesc, bdesc, idesc, accumulate);
+    else
+        mma_f16(taddr, adesc, bdesc, idesc, accumulate);
+}
 
 template <int KIND, int OUT32>
 struct Traits {
@@ -136,6 +172,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
+#ifdef B200CB_DEBUG_TIMING
+    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    const long long dbg_t0 = clock64();
+#endif
     const uint32_t num_kb = p.num_taps * p.num_kc;
     const uint32_t total_tiles = p.m_tiles * p.n_tiles;
 
@@ -173,7 +213,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         // ============================ TMA producer, stem mode ============================
         // the whole (packed) filter once, then per tile the FH input rows it needs, de-interleaved
         // into even / odd pixel planes: [parity][fh][pixel pair][16 bytes], no swizzle
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(bar_bres, p.stem_fh * BN * 128u);
             for (uint32_t fh = 0; fh < p.stem_fh; ++fh)
                 tma_load_3d(sBres + fh * BN * 128u, &p.tmB, bar_bres, 0, static_cast<int32_t>(fh), 0);
@@ -184,8 +224,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             const uint32_t img = row3 / p.OH, oh = row3 % p.OH;
             const int32_t j0 = static_cast<int32_t>(seg * IGEMM_BLOCK_M) - p.stem_pad_lo2;
             const int32_t ih0 = static_cast<int32_t>(oh) * p.stride_h - p.pad_h;
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            if (lane == 0) {
+            TIMED_WAIT(0, bar_empty + 8 * stage, phase ^ 1);
+            if (elect_one()) {
                 const uint32_t full = bar_full + 8 * stage;
                 const uint32_t sa = sStage + stage * stage_bytes;
                 mbar_arrive_expect_tx(full, stage_bytes);
@@ -201,27 +241,27 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     } else if (warp == 1 && stem) {
         // ============================ MMA issuer, stem mode ============================
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-        mbar_wait(bar_bres, 0);
+        TIMED_WAIT(6, bar_bres, 0);
         for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-            mbar_wait(bar_full + 8 * stage, phase);
+            TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
+            TIMED_WAIT(2, bar_full + 8 * stage, phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t taddr = tmem_base + acc * BN;
                 const uint32_t sa = sStage + stage * stage_bytes;
+                // A: rows = output pixels (16 bytes apart), K = [even pixel 8ch | odd pixel 8ch]:
+                // no swizzle, LBO = parity-plane distance, SBO = 128 B; one entry (16 B) per tap pair
+                const uint32_t a_hi = desc_hi(128, 0), b_hi = desc_hi(1024, 2);
+                uint32_t a_lo = desc_lo(sa, plane_bytes);
+                uint32_t b_lo = desc_lo(sBres, 16);
                 uint32_t first = 0;
                 for (uint32_t fh = 0; fh < p.stem_fh; ++fh) {
                     for (uint32_t t2 = 0; t2 < p.stem_fw2; ++t2) {
-                        // A: rows = output pixels (16 bytes apart), K = [even pixel 8ch | odd pixel 8ch]
-                        const uint64_t adesc = umma_smem_desc_lbo(
-                                sa + (fh * p.stem_nj + t2) * 16, plane_bytes, 128, 0);
-                        const uint64_t bdesc = umma_smem_desc(sBres + fh * BN * 128u + t2 * 32, 1024, 2);
-                        if constexpr (KIND == KIND_S8)
-                            mma_i8(taddr, adesc, bdesc, IDESC, first);
-                        else
-                            mma_f16(taddr, adesc, bdesc, IDESC, first);
+                        mma_issue<KIND>(taddr, a_lo + t2, a_hi, b_lo + 2 * t2, b_hi, IDESC, first);
                         first = 1;
                     }
+                    a_lo += p.stem_nj;        // next filter row: stem_nj entries further
+                    b_lo += BN * 128u / 16u;  // next 128-byte K row block of the resident filter
                 }
                 mma_commit(bar_empty + 8 * stage);
                 mma_commit(bar_tfull + 8 * acc);
@@ -237,7 +277,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         }
     } else if (warp == 0 && rows) {
         // ============================ TMA producer, rows mode ============================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_arrive_expect_tx(bar_bres, bres_bytes);
             for (uint32_t tap = 0; tap < p.num_taps; ++tap)
                 for (uint32_t kc = 0; kc < p.num_kc; ++kc)
@@ -249,8 +289,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const uint32_t img = tile / p.tiles_per_img, t = tile % p.tiles_per_img;
             const uint32_t r0 = (t * IGEMM_BLOCK_M) / p.PW;  // first (padded) input row of the slab
-            mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-            if (lane == 0) {
+            TIMED_WAIT(0, bar_empty + 8 * stage, phase ^ 1);
+            if (elect_one()) {
                 const uint32_t full = bar_full + 8 * stage;
                 const uint32_t sa = sStage + stage * stage_bytes;
                 mbar_arrive_expect_tx(full, stage_bytes);
@@ -270,41 +310,40 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         // tap (fh, fw) of output m' reads slab entry m' - r0*PW + fh*PW + fw: a pure row shift of the
         // A descriptor (128-byte rows, SWIZZLE_128B keyed on absolute smem address bits)
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-        mbar_wait(bar_bres, 0);
+        TIMED_WAIT(6, bar_bres, 0);
         for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
             const uint32_t t = tile % p.tiles_per_img;
             const uint32_t off0 = (t * IGEMM_BLOCK_M) % p.PW;
-            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
-            mbar_wait(bar_full + 8 * stage, phase);
+            TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
+            TIMED_WAIT(2, bar_full + 8 * stage, phase);
             tc_fence_after();
-            if (lane == 0) {
+            if (elect_one()) {
                 const uint32_t taddr = tmem_base + acc * BN;
                 const uint32_t sa = sStage + stage * stage_bytes;
+                // The slab row a tap starts on is usually not a multiple of 8: the 128B swizzle is
+                // keyed on absolute smem address bits (as TMA wrote it), so a plain row-shifted start
+                // address is correct (base-offset field 0; verified on B200 against the oracle).
+                const uint32_t ab_hi = desc_hi(1024, 2);
+                const uint32_t plane16 = plane_bytes >> 4;
+                uint32_t row_lo = desc_lo(sa + off0 * 128u, 16);  // tap (fh, 0)
+                uint32_t b_lo = desc_lo(sBres, 16);
                 uint32_t first = 0;
-                uint32_t fh = 0, fw = 0;
-                for (uint32_t tap = 0; tap < p.num_taps; ++tap) {
-                    const uint32_t arow = sa + (off0 + fh * p.PW + fw) * 128u;
-                    for (uint32_t kc = 0; kc < p.num_kc; ++kc) {
-                        const uint32_t sb = sBres + (tap * p.num_kc + kc) * BN * 128u;
+                for (uint32_t fh = 0; fh < p.num_taps / p.FW; ++fh) {
+                    uint32_t tap_lo = row_lo;
+                    for (uint32_t fw = 0; fw < p.FW; ++fw) {
+                        uint32_t a_lo = tap_lo;
+                        for (uint32_t kc = 0; kc < p.num_kc; ++kc) {
 #pragma unroll
-                        for (uint32_t k = 0; k < 4; ++k) {
-                            // the slab row the matrix starts on is usually not a multiple of 8: the
-                            // 128B swizzle is keyed on absolute smem address bits (as TMA wrote it),
-                            // so a plain row-shifted start address is correct (base-offset field 0;
-                            // verified on B200 against the oracle)
-                            const uint64_t adesc = umma_smem_desc(arow + kc * plane_bytes + k * 32, 1024, 2);
-                            const uint64_t bdesc = umma_smem_desc(sb + k * 32, 1024, 2);
-                            if constexpr (KIND == KIND_S8)
-                                mma_i8(taddr, adesc, bdesc, IDESC, first);
-                            else
-                                mma_f16(taddr, adesc, bdesc, IDESC, first);
-                            first = 1;
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                mma_issue<KIND>(taddr, a_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC, first);
+                                first = 1;
+                            }
+                            a_lo += plane16;
+                            b_lo += BN * 128u / 16u;
                         }
+                        tap_lo += 8;  // next pixel: 128 bytes
                     }
-                    if (++fw == p.FW) {
-                        fw = 0;
-                        ++fh;
-                    }
+                    row_lo += p.PW * 8;  // next input row
                 }
                 mma_commit(bar_empty + 8 * stage);
                 mma_commit(bar_tfull + 8 * acc);
@@ -334,8 +373,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 // mode CONVOLUTION reads the spatially flipped filter tap for the same src pixel
                 const uint32_t btap = p.flip ? (p.num_taps - 1 - tap) : tap;
                 for (uint32_t kc = 0; kc < p.num_kc; ++kc) {
-                    mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-                    if (lane == 0) {
+                    TIMED_WAIT(0, bar_empty + 8 * stage, phase ^ 1);
+                    if (elect_one()) {
                         const uint32_t full = bar_full + 8 * stage;
                         const uint32_t sa = sStage + stage * stage_bytes;
                         const uint32_t sb = sa + a_bytes;
@@ -369,25 +408,20 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         const uint32_t mma_per_kb = p.kb_bytes / 32;
         // UMMA layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B; SBO = 8 rows
         const uint32_t layout = p.kb_bytes == 128 ? 2u : (p.kb_bytes == 64 ? 4u : 6u);
-        const uint32_t sbo = 8 * p.kb_bytes;
+        const uint32_t ab_hi = desc_hi(8 * p.kb_bytes, layout);
         for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+            TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN;
             for (uint32_t kb = 0; kb < num_kb; ++kb) {
-                mbar_wait(bar_full + 8 * stage, phase);
+                TIMED_WAIT(2, bar_full + 8 * stage, phase);
                 tc_fence_after();
-                if (lane == 0) {
+                if (elect_one()) {
                     const uint32_t sa = sStage + stage * stage_bytes;
                     const uint32_t sb = sa + a_bytes;
-                    for (uint32_t k = 0; k < mma_per_kb; ++k) {
-                        const uint64_t adesc = umma_smem_desc(sa + k * 32, sbo, layout);
-                        const uint64_t bdesc = umma_smem_desc(sb + k * 32, sbo, layout);
-                        if constexpr (KIND == KIND_S8)
-                            mma_i8(taddr, adesc, bdesc, IDESC, (kb | k) != 0);
-                        else
-                            mma_f16(taddr, adesc, bdesc, IDESC, (kb | k) != 0);
-                    }
+                    const uint32_t a_lo = desc_lo(sa, 16), b_lo = desc_lo(sb, 16);
+                    for (uint32_t k = 0; k < mma_per_kb; ++k)
+                        mma_issue<KIND>(taddr, a_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC, (kb | k) != 0);
                     mma_commit(bar_empty + 8 * stage);
                     if (kb == num_kb - 1)
                         mma_commit(bar_tfull + 8 * acc);
@@ -414,8 +448,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     if (col0 >= p.OC)
                         break;
                     const uint32_t zb = cnt & 1, zphase = (cnt >> 1) & 1;
-                    mbar_wait(bar_zempty + 8 * zb, zphase ^ 1);
-                    if (lane == 0) {
+                    TIMED_WAIT(5, bar_zempty + 8 * zb, zphase ^ 1);
+                    if (elect_one()) {
                         mbar_arrive_expect_tx(bar_zfull + 8 * zb, IGEMM_BLOCK_M * T::ROW_BYTES);
                         if (stem)
                             tma_load_3d(
@@ -481,7 +515,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             int32_t last_c = -1;
             for (uint32_t c = group; c < nchunks; c += T::GROUPS)
                 last_c = static_cast<int32_t>(c);
-            mbar_wait(bar_tfull + 8 * acc, acc_phase);
+            TIMED_WAIT(3, bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
             if (last_c < 0) {
                 tc_fence_before();
@@ -496,11 +530,17 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 const uint32_t col0 = n0 + c * T::EPI_N;
                 const uint32_t zb = cnt & 1, zphase = (cnt >> 1) & 1;
                 // slab db must have been drained by the TMA store issued 2 chunks ago
+#ifdef B200CB_DEBUG_TIMING
+                const long long tsw__ = clock64();
+#endif
                 if (lane == 0)
                     tma_store_wait_read<1>();
                 __syncwarp();
+#ifdef B200CB_DEBUG_TIMING
+                dbg_acc[7] += clock64() - tsw__;
+#endif
                 if (p.has_z)
-                    mbar_wait(bar_zfull + 8 * zb, zphase);
+                    TIMED_WAIT(4, bar_zfull + 8 * zb, zphase);
                 uint8_t* drow = slab_gen + db * T::SLAB_BYTES + lane * T::ROW_BYTES;
                 const uint8_t* zrow = sZ_gen + zb * IGEMM_EPI_BUF_BYTES + row * T::ROW_BYTES;
 #pragma unroll
@@ -685,6 +725,14 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             tma_store_wait<0>();
     }
 
+#ifdef B200CB_DEBUG_TIMING
+    if (p.dbg && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
+        long long* o = p.dbg + (static_cast<size_t>(blockIdx.x) * 3 + (warp == 4 ? 2 : warp)) * 9;
+        for (int i = 0; i < 8; ++i)
+            o[i] = dbg_acc[i];
+        o[8] = clock64() - dbg_t0;
+    }
+#endif
     tc_fence_before();
     __syncthreads();
     if (warp == 2) {
@@ -1236,6 +1284,10 @@ int igemm_launch(
     p.has_z = d.has_z;
     p.nonline = d.nonline_mode;
     p.rq = make_requant(d);
+#ifdef B200CB_DEBUG_TIMING
+    if (const char* e = getenv("B200CB_DBG_PTR"))
+        p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 16));
+#endif
 
     const uint64_t total = (uint64_t)p.m_tiles * p.n_tiles;
     uint32_t grid = plan.grid ? plan.grid : (uint32_t)device_sm_count();
