@@ -156,7 +156,8 @@ int b200cb_exec_host(
         const void* z, void* dst, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 
 /* Device self-tests (synchronise `stream`). which == 0: the requantize epilogue's reciprocal-based
- * division against IEEE division over all 2^32 dividends; *mismatches must come back 0. */
+ * division against IEEE division over all 2^32 dividends; which == 1: the ALU-only quantize of the
+ * fast int8 epilogue against roundf(IEEE division) + clamp.  *mismatches must come back 0. */
 int b200cb_selftest(int which, void* stream, uint64_t* mismatches);
 
 const char* b200cb_strerror(int code);

@@ -68,6 +68,45 @@ __device__ __forceinline__ int32_t quant_s8(float r, const RequantParams& q) {
     v = fminf(fmaxf(-128.f, v), 127.f);
     return __float2int_rn(v);
 }
+// ---- the same arithmetic on the FMA / ALU pipes only ------------------------------------------
+// The generic sequence above costs four conversion-pipe instructions per element (I2F.S8, FRND,
+// F2I, ...), and that pipe issues 16 lanes / clk / SM: it, not HBM, bounded the int8 epilogue.  The
+// helpers below produce bit-identical results with FADD / FMNMX / PRMT / LOP3 only; they require
+// `fast_div == 2` (host-checked: every quotient is finite, see make_requant).
+
+// byte `b` of `w_xor80` (an int8x4 word XOR 0x80808080) -> exact float of the signed byte:
+// PRMT builds the bits of 2^23 + (z + 128), one exact FADD removes the offset.
+template <int B>
+__device__ __forceinline__ float s8_to_float(uint32_t w_xor80) {
+    return __uint_as_float(__byte_perm(w_xor80, 0x4B000000u, 0x7540u | B)) - 8388736.f;
+}
+// r / s_dst without the overflow guard (fast_div == 2)
+__device__ __forceinline__ float div_by_scale_noguard(float r, const RequantParams& q) {
+    const float q0 = __fmul_rn(r, q.inv_dst);
+    const float e = __fmaf_rn(-q0, q.s_dst, r);
+    return __fmaf_rn(e, q.inv_dst, q0);
+}
+// sat_s8(roundf(v)) for v >= 0 (RELU output), result in the LOW BYTE of the return value.
+// roundf(v) == floor(v + 0.5) for v >= 0; the add is done round-toward-zero so that it can never
+// round up across an integer, and 2^23 + t rounded down leaves floor(t) in the low mantissa bits.
+__device__ __forceinline__ uint32_t round_sat_s8_nonneg(float v) {
+    const float c = fminf(v, 127.f);
+    const float t = __fadd_rz(c, 0.5f);
+    return __float_as_uint(__fadd_rd(t, 8388608.f));
+}
+// any sign: magnitude as above, then a two's-complement negate of the low byte
+__device__ __forceinline__ uint32_t round_sat_s8_signed(float v) {
+    const float c = fminf(fmaxf(v, -128.f), 127.f);
+    const float t = __fadd_rz(fabsf(c), 0.5f);
+    const uint32_t m = __float_as_uint(__fadd_rd(t, 8388608.f));
+    const uint32_t s = static_cast<uint32_t>(static_cast<int32_t>(__float_as_uint(c)) >> 31);
+    return (m ^ s) - s;
+}
+// low bytes of four words -> one int8x4 word
+__device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
+}
+
 __device__ __forceinline__ int32_t requant_s8(int32_t sfb, int32_t zq, uint32_t nl, const RequantParams& q) {
     return quant_s8(act_f(dequant_acc(sfb, zq, q), nl), q);
 }

@@ -180,6 +180,17 @@ def test_requant_division_selftest():
     assert rc == 0 and bad.value == 0, (rc, bad.value)
 
 
+def test_requant_fast_quantize_selftest():
+    """the ALU-only quantize of the fast int8 epilogue (unguarded Markstein division, magic-number
+    round-half-away, clamp) == roundf(IEEE division) + clamp for all dividends with |quotient| < 2^60."""
+    import ctypes
+    import torch
+    lib = C.load()
+    bad = ctypes.c_uint64(123)
+    rc = lib.b200cb_selftest(1, torch.cuda.current_stream().cuda_stream, ctypes.byref(bad))
+    assert rc == 0 and bad.value == 0, (rc, bad.value)
+
+
 @pytest.mark.parametrize("kind", ["bf16", "qs8"])
 def test_stem_weight_preprocess_path(kind):
     """exec_preprocess + exec(preprocessed_filter) (nn.h:400-447) == the workspace path, bit for bit."""
