@@ -68,23 +68,16 @@ int validate_desc(const b200cb_desc* d) {
     return B200CB_OK;
 }
 
-// crude per-tile cycle model used only to rank the tile widths (see DESIGN.md "heuristic")
+// Heuristic rank of an implicit-GEMM tile width (lower is better), from the measured sweep
+// (tools/sweep_resnet.py, profiles/): the widest tile that is not wider than OC wins whenever it still
+// yields at least one tile per SM -- operand traffic per flop falls with the tile width and the
+// kernels are shared-memory / L2 feed bound -- and below that the tile count is what matters.
 double igemm_cost(const b200cb_desc& d, uint32_t bn, int sms) {
-    const uint32_t in_es = d.src_dtype == B200CB_DT_QS8 ? 1 : 2;
-    const uint32_t kb_elems = IGEMM_KBYTES / in_es;
-    const double num_kb = (double)d.fh * d.fw * ((d.ic + kb_elems - 1) / kb_elems);  // 128-byte K-blocks
     const double M = (double)d.n * d.oh * d.ow;
-    const double m_tiles = ceil(M / IGEMM_BLOCK_M);
-    const double n_tiles = ceil((double)d.oc / bn);
-    const double mma = 4.0 * (128.0 * bn / 256.0);                  // 4 MMAs of K=32B per k-block
-    const double feed = (IGEMM_BLOCK_M + bn) * 128.0 / 128.0;       // smem bytes / (128 B/clk)
-    const double per_kb = mma > feed ? mma : feed;
-    const double epi = 600.0 + 6.0 * bn;
-    double tile = num_kb * per_kb;
-    if (tile < epi)
-        tile = epi;  // epilogue-bound when K is tiny
-    const double waves = ceil(m_tiles * n_tiles / sms);
-    return waves * (tile + 400.0);
+    const double tiles = ceil(M / IGEMM_BLOCK_M) * ceil((double)d.oc / bn);
+    if (tiles >= sms)
+        return 1.0 / bn;           // enough parallelism: widest first
+    return 1.0 + 1.0 / tiles;      // small problems: most tiles first
 }
 }  // namespace
 

@@ -60,6 +60,8 @@ struct IgemmParams {
     // rows mode (a_mode 3): stride-1 conv over the padded-linear pixel index m' = oh * PW + ow',
     // PW = OW + FW - 1; a tile = 128 consecutive m' of one image, its input rows resident in smem
     uint32_t PW, tiles_per_img, rows_rh;
+    uint32_t cluster;  // CTAs per thread-block cluster sharing each filter tile by TMA multicast (1, 2, 4)
+    uint32_t pair;     // 1: the 2 CTAs of a cluster form a cta_group::2 MMA pair (256 x BN tile, B split)
     uint32_t flip;     // mode == CONVOLUTION
     uint32_t has_bias, has_z, nonline;
     RequantParams rq;
@@ -91,6 +93,17 @@ __device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) 
 }
 __device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout) {
     return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout << 29);
+}
+template <int KIND>
+__device__ __forceinline__ void mma_issue_2sm(
+        uint32_t taddr, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi, uint32_t idesc,
+        uint32_t accumulate) {
+    const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | a_lo;
+    const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | b_lo;
+    if constexpr (KIND == KIND_S8)
+        mma_i8_2sm(taddr, adesc, bdesc, idesc, accumulate);
+    else
+        mma_f16_2sm(taddr, adesc, bdesc, idesc, accumulate);
 }
 template <int KIND>
 __device__ __forceinline__ void mma_issue(
@@ -183,7 +196,9 @@ __device__ __forceinline__ void requant_row32(
     }
 }
 
-template <int KIND, int BN, int OUT32>
+// PAIR = 1 instantiations contain cta_group::2 instructions and must be launched as clusters of 2
+// (the driver rejects them otherwise), hence a template parameter rather than a runtime flag.
+template <int KIND, int BN, int OUT32, int PAIR>
 __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         igemm_kernel(const __grid_constant__ IgemmParams p) {
     using T = Traits<KIND, OUT32>;
@@ -214,7 +229,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     const uint32_t plane_bytes = rows ? p.rows_rh * p.PW * 128u   // rows: one 64-channel block of the slab
                                       : p.stem_fh * p.stem_nj * 16; // stem: one pixel parity, all filter rows
     const uint32_t a_bytes = stem ? 2 * plane_bytes : rows ? p.num_kc * plane_bytes : IGEMM_BLOCK_M * p.kb_bytes;
-    const uint32_t stage_bytes = (stem || rows) ? a_bytes : a_bytes + BN * p.kb_bytes;
+    // CTA pair: each CTA stages only its half of the filter tile's rows
+    constexpr bool pair = PAIR != 0;
+    const uint32_t b_rows = pair ? BN / 2 : BN;
+    const uint32_t stage_bytes = (stem || rows) ? a_bytes : a_bytes + b_rows * p.kb_bytes;
     const uint32_t bres_bytes = stem ? p.stem_fh * BN * 128u : rows ? p.num_taps * p.num_kc * BN * 128u : 0u;
     const uint32_t sZ = smem_base + OFF_SZ;
     const uint32_t sBres = sZ + (p.has_z ? NZ * T::ZBUF_BYTES : SLABS_BYTES);  // resident filter
@@ -228,7 +246,14 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     const long long dbg_t0 = clock64();
 #endif
     const uint32_t num_kb = p.num_taps * p.num_kc;
-    const uint32_t total_tiles = p.m_tiles * p.n_tiles;
+    // Tile schedule: a cluster of C CTAs walks "cluster tiles" = C consecutive M tiles x one N tile, so
+    // that all its CTAs need the same filter tile at the same time (each loads 1/C of it and
+    // multicasts).  C == 1 (always in stem / rows mode) degenerates to tile = blockIdx.x + i * gridDim.x.
+    const uint32_t C = p.cluster;
+    const uint32_t crank = C > 1 ? cluster_ctarank() : 0;
+    const uint32_t cl_id = blockIdx.x / C, cl_num = gridDim.x / C;
+    const uint32_t total_ct = ((p.m_tiles + C - 1) / C) * p.n_tiles;
+    const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1);
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&p.tmA);
@@ -240,11 +265,13 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     if (warp == 1 && lane == 0) {
         for (uint32_t i = 0; i < p.stages; ++i) {
             mbar_init(bar_full + 8 * i, 1);
-            mbar_init(bar_empty + 8 * i, 1);
+            // multicast clusters: one MMA commit per CTA; pair: one (multicast) commit of the leader
+            mbar_init(bar_empty + 8 * i, pair ? 1 : C);
         }
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            mbar_init(bar_tempty + 8 * i, 4 * T::GROUPS);  // one arrive per epilogue warp
+            // one arrive per epilogue warp (pair: of both CTAs, on the leader's barrier)
+            mbar_init(bar_tempty + 8 * i, (pair ? 2 : 1) * 4 * T::GROUPS);
         }
         for (uint32_t i = 0; i < NZ; ++i) {
             mbar_init(bar_zfull + 8 * i, 1);
@@ -254,11 +281,18 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         fence_mbar_init();
     }
     if (warp == 2) {
-        tmem_alloc(smem_base + OFF_TMEM, TMEM_COLS);
-        tmem_relinquish();
+        if (pair) {
+            tmem_alloc_2sm(smem_base + OFF_TMEM, TMEM_COLS);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(smem_base + OFF_TMEM, TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
     __syncthreads();
+    if (C > 1)
+        cluster_sync_all();  // peers multicast into this CTA's stages and arrive on its barriers
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
 
@@ -272,7 +306,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 tma_load_3d(sBres + fh * BN * 128u, &p.tmB, bar_bres, 0, static_cast<int32_t>(fh), 0);
         }
         uint32_t stage = 0, phase = 0;
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+            const uint32_t tile = ct;  // C == 1 in this mode
             const uint32_t seg = tile % p.nseg, row3 = tile / p.nseg;  // row3 = img * OH + oh
             const uint32_t img = row3 / p.OH, oh = row3 % p.OH;
             const int32_t j0 = static_cast<int32_t>(seg * IGEMM_BLOCK_M) - p.stem_pad_lo2;
@@ -295,7 +330,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         // ============================ MMA issuer, stem mode ============================
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         TIMED_WAIT(6, bar_bres, 0);
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
             TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
             TIMED_WAIT(2, bar_full + 8 * stage, phase);
             tc_fence_after();
@@ -339,7 +374,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                             static_cast<int32_t>(kc * p.kb_elems), static_cast<int32_t>(tap), 0);
         }
         uint32_t stage = 0, phase = 0;
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+            const uint32_t tile = ct;  // C == 1 in this mode
             const uint32_t img = tile / p.tiles_per_img, t = tile % p.tiles_per_img;
             const uint32_t r0 = (t * IGEMM_BLOCK_M) / p.PW;  // first (padded) input row of the slab
             TIMED_WAIT(0, bar_empty + 8 * stage, phase ^ 1);
@@ -364,7 +400,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         // A descriptor (128-byte rows, SWIZZLE_128B keyed on absolute smem address bits)
         uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
         TIMED_WAIT(6, bar_bres, 0);
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+            const uint32_t tile = ct;  // C == 1 in this mode
             const uint32_t t = tile % p.tiles_per_img;
             const uint32_t off0 = (t * IGEMM_BLOCK_M) % p.PW;
             TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -413,8 +450,11 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     } else if (warp == 0) {
         // ============================ TMA producer (A, B) ============================
         uint32_t stage = 0, phase = 0;
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const uint32_t m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+            // a phantom tile (M tiles not a multiple of C) re-loads the last valid tile: every CTA of the
+            // cluster must run the same k-loop because the filter slices are exchanged in lock step
+            const uint32_t m_raw = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
+            const uint32_t m_blk = m_raw < p.m_tiles ? m_raw : p.m_tiles - 1;
             const int32_t m0 = static_cast<int32_t>(m_blk * IGEMM_BLOCK_M);
             const int32_t n0 = static_cast<int32_t>(n_blk * BN);
             const uint32_t img = static_cast<uint32_t>(m0) / p.OHW;
@@ -432,6 +472,24 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         const uint32_t sa = sStage + stage * stage_bytes;
                         const uint32_t sb = sa + a_bytes;
                         const int32_t c0 = static_cast<int32_t>(kc * p.kb_elems);
+                        if (pair) {
+                            // both CTAs' loads complete on the LEADER's barrier, which expects both stages
+                            const uint32_t lfull = mapa(full, 0);
+                            if (crank == 0)
+                                mbar_arrive_expect_tx(full, 2 * stage_bytes);
+                            if (p.a_mode == 0) {
+                                tma_load_2d_2sm(sa, &p.tmA, lfull, c0, m0);
+                            } else {
+                                tma_load_im2col_4d_2sm(
+                                        sa, &p.tmA, lfull, c0, base_w, base_h, static_cast<int32_t>(img),
+                                        static_cast<uint16_t>(fw * p.dil_w),
+                                        static_cast<uint16_t>(fh * p.dil_h));
+                            }
+                            tma_load_3d_2sm(
+                                    sb, &p.tmB, lfull, c0, static_cast<int32_t>(btap),
+                                    n0 + static_cast<int32_t>(crank * b_rows));
+                        }
+                        if (!pair) {
                         mbar_arrive_expect_tx(full, stage_bytes);
                         if (p.a_mode == 0) {
                             tma_load_2d(sa, &p.tmA, full, c0, m0);
@@ -441,7 +499,16 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                     static_cast<uint16_t>(fw * p.dil_w),
                                     static_cast<uint16_t>(fh * p.dil_h));
                         }
-                        tma_load_3d(sb, &p.tmB, full, c0, static_cast<int32_t>(btap), n0);
+                        if (C == 1) {
+                            tma_load_3d(sb, &p.tmB, full, c0, static_cast<int32_t>(btap), n0);
+                        } else {
+                            // this CTA's 1/C of the filter tile's rows, delivered to every CTA of the cluster
+                            const uint32_t rows_c = BN / C;
+                            tma_load_3d_mc(
+                                    sb + crank * rows_c * p.kb_bytes, &p.tmB, full, c0,
+                                    static_cast<int32_t>(btap), n0 + static_cast<int32_t>(crank * rows_c), cmask);
+                        }
+                        }
                     }
                     __syncwarp();
                     if (++stage == p.stages) {
@@ -462,7 +529,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         // UMMA layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B; SBO = 8 rows
         const uint32_t layout = p.kb_bytes == 128 ? 2u : (p.kb_bytes == 64 ? 4u : 6u);
         const uint32_t ab_hi = desc_hi(8 * p.kb_bytes, layout);
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        // pair: M = 256 in the instruction descriptor, only the leader CTA issues
+        constexpr uint32_t IDESC_PAIR = (IDESC & ~(0x1Fu << 24)) | ((256u >> 4) << 24);
+        const uint32_t ct_end = (pair && crank != 0) ? 0 : total_ct;
+        for (uint32_t ct = cl_id; ct < ct_end; ct += cl_num) {
             TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
             tc_fence_after();
             const uint32_t taddr = tmem_base + acc * BN;
@@ -473,11 +543,23 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     const uint32_t sa = sStage + stage * stage_bytes;
                     const uint32_t sb = sa + a_bytes;
                     const uint32_t a_lo = desc_lo(sa, 16), b_lo = desc_lo(sb, 16);
-                    for (uint32_t k = 0; k < mma_per_kb; ++k)
-                        mma_issue<KIND>(taddr, a_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC, (kb | k) != 0);
-                    mma_commit(bar_empty + 8 * stage);
-                    if (kb == num_kb - 1)
-                        mma_commit(bar_tfull + 8 * acc);
+                    if (pair) {
+                        for (uint32_t k = 0; k < mma_per_kb; ++k)
+                            mma_issue_2sm<KIND>(
+                                    taddr, a_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC_PAIR, (kb | k) != 0);
+                        mma_commit_2sm_mc(bar_empty + 8 * stage, 3);  // frees the stage in both CTAs
+                        if (kb == num_kb - 1)
+                            mma_commit_2sm_mc(bar_tfull + 8 * acc, 3);  // both CTAs' epilogues
+                    } else {
+                        for (uint32_t k = 0; k < mma_per_kb; ++k)
+                            mma_issue<KIND>(taddr, a_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC, (kb | k) != 0);
+                        if (C == 1)
+                            mma_commit(bar_empty + 8 * stage);
+                        else
+                            mma_commit_mc(bar_empty + 8 * stage, cmask);  // frees the stage in every CTA
+                        if (kb == num_kb - 1)
+                            mma_commit(bar_tfull + 8 * acc);
+                    }
                 }
                 __syncwarp();
                 if (++stage == p.stages) {
@@ -493,8 +575,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         // ============================ z prefetch (TMA) ============================
         if (p.has_z) {
             uint32_t cnt = 0;
-            for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-                const uint32_t m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+                const uint32_t m_blk = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
+                if (m_blk >= p.m_tiles)
+                    continue;  // phantom tile
                 const int32_t m0 = static_cast<int32_t>(m_blk * IGEMM_BLOCK_M);
                 for (uint32_t c = 0; c < NUM_CHUNKS; ++c) {
                     const uint32_t col0 = n_blk * BN + c * T::EPI_N;
@@ -533,12 +617,33 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         uint8_t* slab_gen = smem_gen + OFF_SD + e * T::NSLAB * T::SLAB_BYTES;
         const uint8_t* sZ_gen = smem_gen + OFF_SZ;
         // RELU: x <= 0 ? 0 : x;  IDENTITY: the same select against -inf (a no-op) -- branch-free
+        // TMEM hand-back: to the MMA warp of this CTA, or (pair) of the leader CTA
+        const bool remote_tempty = pair && crank != 0;
+        auto arrive_tempty = [&](uint32_t bar) {
+            if (remote_tempty)
+                mbar_arrive_cluster(mapa(bar, 0));
+            else
+                mbar_arrive(bar);
+        };
         const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
         const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
         const bool fast8 = KIND == KIND_S8 && !generic_act && p.rq.fast_div == 2;
         uint32_t acc = 0, acc_phase = 0, cnt = 0, db = 0;
-        for (uint32_t tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-            const uint32_t m_blk = tile / p.n_tiles, n_blk = tile % p.n_tiles;
+        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+            const uint32_t m_blk = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
+            if (m_blk >= p.m_tiles) {
+                // phantom tile: consume the accumulator and hand it straight back
+                TIMED_WAIT(3, bar_tfull + 8 * acc, acc_phase);
+                tc_fence_after();
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0)
+                    arrive_tempty(bar_tempty + 8 * acc);
+                acc ^= 1;
+                if (acc == 0)
+                    acc_phase ^= 1;
+                continue;
+            }
             const int32_t m0 = static_cast<int32_t>(m_blk * IGEMM_BLOCK_M);
             const uint32_t n0 = n_blk * BN;
             // bias slice of this tile -> the warp's private smem (fp32 for float kinds, int32 for int8)
@@ -575,7 +680,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0)
-                    mbar_arrive(bar_tempty + 8 * acc);
+                    arrive_tempty(bar_tempty + 8 * acc);
             }
 #pragma unroll 1
             for (uint32_t c = 0; c < nchunks; ++c, ++cnt) {
@@ -614,7 +719,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0)
-                            mbar_arrive(bar_tempty + 8 * acc);
+                            arrive_tempty(bar_tempty + 8 * acc);
                     }
                     const uint32_t* bcol = sbias + c * T::EPI_N + h * 32;
                     constexpr uint32_t COLS_PER_16B = 16 / T::OUT_ES;
@@ -813,9 +918,14 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 #endif
     tc_fence_before();
     __syncthreads();
+    if (C > 1)
+        cluster_sync_all();  // no CTA may exit while a peer can still signal its barriers
     if (warp == 2) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, TMEM_COLS);
+        if (pair)
+            tmem_dealloc_2sm(tmem_base, TMEM_COLS);
+        else
+            tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
@@ -896,21 +1006,59 @@ __global__ void selftest_fastq_kernel(const float* scales, int nscales, unsigned
         atomicAdd(bad, local);
 }
 
-template <int KIND, int BN, int OUT32>
-cudaError_t launch_variant(const IgemmParams& p, uint32_t grid, uint32_t smem, cudaStream_t stream) {
-    auto kern = igemm_kernel<KIND, BN, OUT32>;
+// `grid` == 0: one CTA per SM (clusters: as many whole clusters as the device keeps co-resident, asked
+// from the occupancy API once per kernel variant / cluster size -- GPC boundaries strand a few SMs for
+// clusters of 4), capped by the number of tiles.
+template <int KIND, int BN, int OUT32, int PAIR>
+cudaError_t launch_variant(
+        const IgemmParams& p, uint32_t grid, uint64_t total_tiles, uint32_t smem, cudaStream_t stream) {
+    auto kern = igemm_kernel<KIND, BN, OUT32, PAIR>;
     static bool attr_set[64] = {false};
+    static int max_clusters[64][5] = {{0}};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+    if (dev < 0 || dev >= 64)
+        return cudaErrorInvalidDevice;
+    if (!attr_set[dev]) {
         cudaError_t e = cudaFuncSetAttribute(
                 kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(MAX_DYN_SMEM));
         if (e != cudaSuccess)
             return e;
         attr_set[dev] = true;
     }
-    kern<<<grid, Traits<KIND, OUT32>::THREADS, smem, stream>>>(p);
-    return cudaGetLastError();
+    const uint32_t C = p.cluster;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.blockDim = dim3(Traits<KIND, OUT32>::THREADS, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = C;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = C > 1 ? 1 : 0;
+    if (grid == 0) {
+        grid = static_cast<uint32_t>(device_sm_count());
+        if (C > 1) {
+            if (max_clusters[dev][C] == 0) {
+                cfg.gridDim = dim3(grid / C * C, 1, 1);
+                int n = 0;
+                cudaError_t e = cudaOccupancyMaxActiveClusters(&n, kern, &cfg);
+                if (e != cudaSuccess)
+                    return e;
+                max_clusters[dev][C] = n > 0 ? n : 1;
+            }
+            const uint32_t fit = static_cast<uint32_t>(max_clusters[dev][C]) * C;
+            grid = (grid < fit ? grid : fit) / C * C;
+        }
+    }
+    const uint64_t cluster_tiles = (total_tiles + C - 1) / C;
+    if (grid / C > cluster_tiles)
+        grid = static_cast<uint32_t>(cluster_tiles) * C;
+    cfg.gridDim = dim3(grid, 1, 1);
+    return cudaLaunchKernelEx(&cfg, kern, p);
 }
 
 // geometry actually fed to the kernel (differs from the descriptor when the conv is W-folded)
@@ -985,6 +1133,23 @@ RowsGeom rows_geometry(const b200cb_desc& d, uint32_t in_es, uint32_t block_n) {
     r.bres = d.fh * d.fw * r.num_kc * block_n * 128;
     r.ok = true;
     return r;
+}
+
+// CTA-pair heuristic: a single CTA's 128 x BN MMA is bound by shared-memory bandwidth (operand reads
+// plus TMA writes: 192 B/clk at BN = 256, 256 B/clk at BN = 128, against 128 B/clk); the pair halves
+// the filter-side traffic.  It pays once the k-loop is long enough for the main loop, not the epilogue
+// or HBM, to bound the tile.
+uint32_t pick_pair(const b200cb_desc& d, uint32_t block_n, uint32_t m_tiles) {
+    const uint32_t in_es = d.src_dtype == B200CB_DT_QS8 ? 1 : 2;
+    const uint64_t k_bytes = (uint64_t)d.fh * d.fw * d.ic * in_es;
+    (void)block_n;
+    if (m_tiles < 148)
+        return 0;
+    // measured crossover (tools/sweep_resnet.py): long k-loops always; 1 KiB k-loops only for wide
+    // 16-bit tiles without the z stream; shorter ones are epilogue / HBM bound and lose to the pairing
+    if (k_bytes >= 2048)
+        return 1;
+    return (in_es == 2 && k_bytes >= 1024 && !d.has_z && d.oc >= 256) ? 1u : 0u;
 }
 
 uint32_t pick_kb_bytes(uint32_t ic_bytes) {
@@ -1144,9 +1309,28 @@ int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
     // rows mode: the filter and >= 2 input slabs must fit next to the epilogue buffers
     const RowsGeom rg = rows_geometry(dd, in_es, block_n);
     const bool rows = !stem && !g.folded && rg.ok && fixed0 + rg.bres + 2 * rg.a_stage <= MAX_DYN_SMEM;
+    // generic modes: CTA pair (cta_group::2, 256 x BN tile, filter rows split between the two CTAs) or
+    // a thread-block cluster sharing each filter tile by TMA multicast
+    uint32_t cluster = 1, pair = 0;
+    if (!stem && !rows) {
+        const uint32_t m_tiles = (uint32_t)((M + IGEMM_BLOCK_M - 1) / IGEMM_BLOCK_M);
+        pair = pick_pair(d, block_n, m_tiles);
+        if (const char* e = getenv("B200CB_PAIR"))  // experiment knobs (tools/)
+            pair = atoi(e) != 0;
+        if (m_tiles < 4)
+            pair = 0;
+        cluster = pair ? 2 : 1;
+        if (const char* e = getenv("B200CB_CLUSTER"))
+            if (!pair)
+                cluster = (uint32_t)atoi(e);
+        if (cluster != 1 && cluster != 2 && cluster != 4)
+            cluster = 1;
+        while (!pair && cluster > 1 && (m_tiles < 2 * cluster || (block_n / cluster) % 8 != 0))
+            cluster /= 2;
+    }
     const uint32_t stage_b = stem   ? 2 * d.fh * STEM_NJ * 16
                              : rows ? rg.a_stage
-                                    : (IGEMM_BLOCK_M + block_n) * kb_bytes;
+                                    : (IGEMM_BLOCK_M + (pair ? block_n / 2 : block_n)) * kb_bytes;
     const uint32_t fixed = fixed0 + (stem ? d.fh * block_n * 128 : rows ? rg.bres : 0);
     uint32_t stages = (MAX_DYN_SMEM - fixed) / stage_b;
     if (rows && stages > 3)
@@ -1172,6 +1356,8 @@ int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
     plan->reserved[3] = 0;  // 1: `filter` passed to launch is already packed (weight preprocess)
     plan->reserved[4] = g.folded ? 1 : 0;
     plan->reserved[5] = kb_bytes;
+    plan->reserved[6] = cluster;
+    plan->reserved[7] = pair;
     // folded stem: the re-packed filter lives in the workspace unless it was preprocessed
     const uint32_t fwp = stem ? g.fw_packed : g.fw;
     plan->workspace_bytes =
@@ -1322,7 +1508,8 @@ int igemm_launch(
         uint32_t box_stem[3] = {g.fw_packed * g.ic, 1, BN};
         uint64_t dims[3] = {g.ic, (uint64_t)d.fh * g.fw, d.oc};
         uint64_t strides[2] = {(uint64_t)g.ic * in_es, (uint64_t)d.fh * g.fw * g.ic * in_es};
-        uint32_t box[3] = {kb_elems, 1, BN};
+        const uint32_t C = (stem || rows) ? 1u : (plan.reserved[6] ? plan.reserved[6] : 1u);
+        uint32_t box[3] = {kb_elems, 1, BN / C};  // clusters: each CTA loads (and multicasts) BN / C rows
         cr = stem ? encode_tiled(
                             &p.tmB, in_dt, 3, flt, dims_stem, strides_stem, box_stem, nullptr,
                             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)
@@ -1392,6 +1579,8 @@ int igemm_launch(
     }
     p.stages = plan.stages;
     p.a_mode = a_mode;
+    p.cluster = (stem || rows) ? 1u : (plan.reserved[6] ? plan.reserved[6] : 1u);
+    p.pair = (stem || rows) ? 0u : plan.reserved[7];
     p.flip = d.mode == B200CB_MODE_CONVOLUTION;
     p.has_bias = d.bias_mode != B200CB_BIAS_NONE;
     p.has_z = d.has_z;
@@ -1402,27 +1591,36 @@ int igemm_launch(
         p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 16));
 #endif
 
-    const uint64_t total = (uint64_t)p.m_tiles * p.n_tiles;
-    uint32_t grid = plan.grid ? plan.grid : (uint32_t)device_sm_count();
-    if (grid > total)
-        grid = (uint32_t)total;
+    // the cap on the grid counts M tiles only per N tile: cluster tiles = ceil(m_tiles / C) * n_tiles
+    const uint64_t total = (uint64_t)((p.m_tiles + p.cluster - 1) / p.cluster) * p.cluster * p.n_tiles;
+    const uint32_t grid = plan.grid / p.cluster * p.cluster;
 
     cudaError_t e = cudaErrorInvalidValue;
-#define B200CB_DISPATCH(KIND_, OUT_)                                                          \
+#define B200CB_DISPATCH(KIND_, OUT_, PAIR_)                                                        \
     switch (BN) {                                                                             \
-        case 64: e = launch_variant<KIND_, 64, OUT_>(p, grid, plan.smem_bytes, stream); break;   \
-        case 128: e = launch_variant<KIND_, 128, OUT_>(p, grid, plan.smem_bytes, stream); break; \
-        case 256: e = launch_variant<KIND_, 256, OUT_>(p, grid, plan.smem_bytes, stream); break; \
+        case 64: e = launch_variant<KIND_, 64, OUT_, PAIR_>(p, grid, total, plan.smem_bytes, stream); break;   \
+        case 128: e = launch_variant<KIND_, 128, OUT_, PAIR_>(p, grid, total, plan.smem_bytes, stream); break; \
+        case 256: e = launch_variant<KIND_, 256, OUT_, PAIR_>(p, grid, total, plan.smem_bytes, stream); break; \
         default: break;                                                                       \
     }
-    if (kind == KIND_BF16) {
-        B200CB_DISPATCH(KIND_BF16, 0)
+    if (p.pair) {
+        if (kind == KIND_BF16) {
+            B200CB_DISPATCH(KIND_BF16, 0, 1)
+        } else if (kind == KIND_F16) {
+            B200CB_DISPATCH(KIND_F16, 0, 1)
+        } else if (!out32) {
+            B200CB_DISPATCH(KIND_S8, 0, 1)
+        } else {
+            B200CB_DISPATCH(KIND_S8, 1, 1)
+        }
+    } else if (kind == KIND_BF16) {
+        B200CB_DISPATCH(KIND_BF16, 0, 0)
     } else if (kind == KIND_F16) {
-        B200CB_DISPATCH(KIND_F16, 0)
+        B200CB_DISPATCH(KIND_F16, 0, 0)
     } else if (!out32) {
-        B200CB_DISPATCH(KIND_S8, 0)
+        B200CB_DISPATCH(KIND_S8, 0, 0)
     } else {
-        B200CB_DISPATCH(KIND_S8, 1)
+        B200CB_DISPATCH(KIND_S8, 1, 0)
     }
 #undef B200CB_DISPATCH
     if (e != cudaSuccess) {

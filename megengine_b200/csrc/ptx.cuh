@@ -27,6 +27,27 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- thread-block clusters
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+// shared::cluster address of the same smem offset in CTA `rank` of the cluster
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+    return r;
+}
+// arrive on an mbarrier of another CTA of the cluster (address from mapa)
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n"
+                 "barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
@@ -103,6 +124,44 @@ __device__ __forceinline__ void tma_load_im2col_4d(
             "h"(off_w), "h"(off_h)
             : "memory");
 }
+// multicast variant: the box lands at the same smem offset of every CTA in `mask`, and each
+// destination CTA's mbarrier (same offset) receives the complete_tx
+__device__ __forceinline__ void tma_load_3d_mc(
+        uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1, int32_t c2, uint16_t mask) {
+    asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            ".multicast::cluster [%0], [%1, {%3, %4, %5}], [%2], %6;" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "h"(mask)
+            : "memory");
+}
+// CTA-pair (cta_group::2) loads: the data lands in the executing CTA's smem, the complete_tx goes to
+// `bar`, a shared::cluster address that may name the PEER CTA's mbarrier (the MMA leader's).
+__device__ __forceinline__ void tma_load_2d_2sm(
+        uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1) {
+    asm volatile(
+            "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1)
+            : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_2sm(
+        uint32_t dst, const void* tmap, uint32_t bar, int32_t c0, int32_t c1, int32_t c2) {
+    asm volatile(
+            "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+            : "memory");
+}
+__device__ __forceinline__ void tma_load_im2col_4d_2sm(
+        uint32_t dst, const void* tmap, uint32_t bar, int32_t c, int32_t w, int32_t h, int32_t n,
+        uint16_t off_w, uint16_t off_h) {
+    asm volatile(
+            "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.im2col.mbarrier::complete_tx::bytes"
+            " [%0], [%1, {%3, %4, %5, %6}], [%2], {%7, %8};" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c), "r"(w), "r"(h), "r"(n),
+            "h"(off_w), "h"(off_h)
+            : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const void* tmap, uint32_t src, int32_t c0, int32_t c1) {
     asm volatile(
             "cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%2, %3}], [%1];" ::"l"(
@@ -143,6 +202,19 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                  : "memory");
 }
+// CTA-pair allocation: executed by one warp of EACH CTA of the pair
+__device__ __forceinline__ void tmem_alloc_2sm(uint32_t smem_dst, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst),
+                 "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish_2sm() {
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc_2sm(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
 __device__ __forceinline__ void tc_fence_before() {
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
 }
@@ -173,10 +245,50 @@ __device__ __forceinline__ void mma_i8(
             "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
             : "memory");
 }
+// CTA-pair MMAs (issued by the leader CTA only): M = 256 rows, 128 from each CTA's A tile, B rows
+// [0, N/2) from the leader's smem and [N/2, N) from the peer's; each CTA's TMEM gets its 128 rows
+__device__ __forceinline__ void mma_f16_2sm(
+        uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(taddr),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+__device__ __forceinline__ void mma_i8_2sm(
+        uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "setp.ne.b32 p, %4, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n"
+            "}\n" ::"r"(taddr),
+            "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+}
+// pair commit: arrives on the barrier at this offset in every CTA of `mask`
+__device__ __forceinline__ void mma_commit_2sm_mc(uint32_t bar, uint16_t mask) {
+    asm volatile(
+            "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                    bar),
+            "h"(mask)
+            : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile(
             "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+            : "memory");
+}
+// same, arriving on the barrier at this offset in every CTA of `mask` (thread-block cluster)
+__device__ __forceinline__ void mma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile(
+            "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                    bar),
+            "h"(mask)
             : "memory");
 }
 // 32 lanes x 32 columns of 32-bit: thread i of the warp receives columns [c, c+32) of TMEM lane
