@@ -174,6 +174,9 @@ int b200cb_plan_num_launches(const b200cb_plan* plan) {
     // W-folded stem without weight preprocess: filter re-pack + conv
     if (plan->kernel == KERNEL_IGEMM && plan->reserved[4] && !plan->reserved[3])
         return 2;
+    // NCHW4: src re-tile + filter re-tile + conv
+    if (plan->kernel == KERNEL_IGEMM && plan->desc.format == B200CB_FORMAT_NCHW4)
+        return 3;
     return 1;
 }
 

@@ -50,6 +50,11 @@ int dwconv_launch(
         const b200cb_plan& plan, const void* src, const void* filter, const void* bias,
         const void* z, void* dst, cudaStream_t stream);
 
+// NCHW4 pre-pass (relayout.cu): (B, C/4, P, 4) int8 -> (B, P, Cpad) int8, zero-padded channels
+int relayout_c4_to_channels_last(
+        const void* in, void* out, uint32_t B, uint32_t C, uint32_t Cpad, uint32_t P,
+        uint64_t in_batch_elems, cudaStream_t stream);
+
 int device_sm_count();
 
 inline uint32_t dtype_size(uint32_t dt) {

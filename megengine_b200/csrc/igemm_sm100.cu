@@ -63,7 +63,10 @@ struct IgemmParams {
     uint32_t cluster;  // CTAs per thread-block cluster sharing each filter tile by TMA multicast (1, 2, 4)
     uint32_t pair;     // 1: the 2 CTAs of a cluster form a cta_group::2 MMA pair (256 x BN tile, B split)
     uint32_t flip;     // mode == CONVOLUTION
-    uint32_t has_bias, has_z, nonline;
+    uint32_t has_bias, has_z, nonline;  // has_z: z arrives through the TMA ring (NHWC)
+    // NCHW4 destination (N, OC/4, OH, OW, 4): dst and z are accessed in place by the epilogue
+    uint32_t nchw4, z_direct;
+    const void* z;
     RequantParams rq;
     long long* dbg;   // -DB200CB_DEBUG_TIMING builds only: 148 x 3 roles x 9 counters
 };
@@ -196,6 +199,47 @@ __device__ __forceinline__ void requant_row32(
     }
 }
 
+// NCHW4 epilogue for one thread's 32 accumulator columns: the thread owns one output pixel, its 32
+// channels are 8 int8x4 words that live in 8 consecutive (N, OC/4) planes `plane_words` apart, so a
+// warp's 32 pixels make every store (and z load) a coalesced 128-byte line.  `nwords` = planes that
+// exist (OC tail / rows beyond M: 0).  Same arithmetic as requant_row32; any activation.
+template <bool HAS_Z>
+__device__ __forceinline__ void requant_row32_nchw4(
+        const uint32_t (&r)[32], const uint32_t* bcol, const uint32_t* zw, uint32_t* dw,
+        size_t plane_words, uint32_t nwords, uint32_t nl, bool fast, const RequantParams& rq) {
+    uint32_t zv[8];
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j)
+        zv[j] = (HAS_Z && j < nwords) ? __ldg(zw + j * plane_words) : 0u;
+#pragma unroll
+    for (uint32_t j = 0; j < 8; ++j) {
+        const uint4 bv = *reinterpret_cast<const uint4*>(bcol + j * 4);
+        const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
+        const uint32_t zx = zv[j] ^ 0x80808080u;
+        uint32_t ub[4];
+#pragma unroll
+        for (uint32_t b = 0; b < 4; ++b) {
+            const int32_t sfb = static_cast<int32_t>(r[j * 4 + b] + bb[b]);
+            if (fast) {
+                float x = __fmul_rn(__int2float_rn(sfb), rq.s_bias);
+                if constexpr (HAS_Z) {
+                    const float zf =
+                            __uint_as_float(__byte_perm(zx, 0x4B000000u, 0x7540u | b)) - 8388736.f;
+                    x = __fadd_rn(x, __fmul_rn(zf, rq.s_z));
+                }
+                if (nl == B200CB_NL_RELU)
+                    x = fmaxf(x, 0.f);
+                ub[b] = round_sat_s8_signed(div_by_scale_noguard(x, rq));
+            } else {
+                const int32_t zq = static_cast<int32_t>(static_cast<int8_t>((zv[j] >> (8 * b)) & 0xff));
+                ub[b] = static_cast<uint32_t>(requant_s8(sfb, HAS_Z ? zq : 0, nl, rq));
+            }
+        }
+        if (j < nwords)
+            dw[j * plane_words] = pack_low_bytes(ub[0], ub[1], ub[2], ub[3]);
+    }
+}
+
 // PAIR = 1 instantiations contain cta_group::2 instructions and must be launched as clusters of 2
 // (the driver rejects them otherwise), hence a template parameter rather than a runtime flag.
 template <int KIND, int BN, int OUT32, int PAIR>
@@ -258,7 +302,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&p.tmA);
         prefetch_tensormap(&p.tmB);
-        prefetch_tensormap(&p.tmD);
+        if (!p.nchw4)
+            prefetch_tensormap(&p.tmD);
         if (p.has_z)
             prefetch_tensormap(&p.tmZ);
     }
@@ -738,7 +783,21 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                             *reinterpret_cast<uint4*>(drow + off * 16) = ov;
                         }
                     } else if constexpr (KIND == KIND_S8) {
-                      if (fast8) {
+                      if (p.nchw4) {
+                        const uint32_t m = static_cast<uint32_t>(m0) + row;
+                        const uint32_t img = m / p.OHW, pix = m - img * p.OHW;
+                        const uint32_t col = col0 + h * 32;
+                        uint32_t nwords = 0;
+                        if (m < p.M && col < p.OC)
+                            nwords = (p.OC - col) / 4 < 8 ? (p.OC - col) / 4 : 8;
+                        const size_t w0 = (static_cast<size_t>(img) * (p.OC / 4) + col / 4) * p.OHW + pix;
+                        uint32_t* dw = static_cast<uint32_t*>(p.dst) + w0;
+                        const uint32_t* zw = static_cast<const uint32_t*>(p.z) + w0;
+                        if (p.z_direct)
+                            requant_row32_nchw4<true>(r, bcol, zw, dw, p.OHW, nwords, p.nonline, fast8, p.rq);
+                        else
+                            requant_row32_nchw4<false>(r, bcol, zw, dw, p.OHW, nwords, p.nonline, fast8, p.rq);
+                      } else if (fast8) {
                         if (p.has_z) {
                             if (p.nonline == B200CB_NL_RELU)
                                 requant_row32<true, true>(r, bcol, zrow, drow, h, lane, p.rq);
@@ -849,6 +908,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         }
                     }
                 }
+                if (p.nchw4)
+                    continue;  // written in place above, no slab / TMA store
                 if (rows) {
                     // rows mode: the slab's 32 consecutive m' span several output rows and skip the
                     // PW - OW padding columns, which a TMA box cannot express (negative store
@@ -1072,7 +1133,20 @@ struct Geometry {
 };
 constexpr uint32_t STEM_NJ = 136;  // 128 output pixels + up to 4 tap pairs - 1, rounded up to 8
 
-Geometry make_geometry(const b200cb_desc& d, uint32_t in_es) {
+// The NCHW4 cells run on an NHWC / KRSC copy of src / filter in the workspace (relayout.cu), with the
+// channels zero-padded to a TMA-legal multiple of 16: this is the descriptor of that equivalent conv.
+b200cb_desc nchw4_equivalent(const b200cb_desc& d) {
+    b200cb_desc e = d;
+    e.format = B200CB_FORMAT_NHWC;
+    e.ic = (d.ic + 15) / 16 * 16;
+    e.src_batch_stride = 0;
+    return e;
+}
+size_t align256(size_t v) {
+    return (v + 255) & ~static_cast<size_t>(255);
+}
+
+Geometry make_geometry(const b200cb_desc& d, uint32_t in_es, bool allow_fold = true) {
     Geometry g;
     g.ic = d.ic, g.iw = d.iw, g.fw = d.fw, g.stride_w = d.stride_w;
     g.pad_w_lo = (int32_t)d.pad_w;
@@ -1081,7 +1155,7 @@ Geometry make_geometry(const b200cb_desc& d, uint32_t in_es) {
     g.fw_packed = d.fw;
     g.folded = false;
     g.stem = false;
-    if (d.stride_w == 2 && d.dilate_w == 1 && d.iw % 2 == 0 && d.ic * in_es <= 16 &&
+    if (allow_fold && d.stride_w == 2 && d.dilate_w == 1 && d.iw % 2 == 0 && d.ic * in_es <= 16 &&
         d.mode == B200CB_MODE_CROSS_CORRELATION && d.src_batch_stride == 0) {
         // window of output ow covers pixels [2*ow - pad, 2*ow - pad + FW); extend it to an even start
         // and an even length: pixel pairs [ow - pad_lo2, ow - pad_lo2 + FW2)
@@ -1216,9 +1290,21 @@ int igemm_selftest(int which, cudaStream_t stream, uint64_t* mismatches) {
 }
 
 // --------------------------------------------------------------------------- host side
-int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
-    if (d.format != B200CB_FORMAT_NHWC)
+int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
+    const bool nchw4 = d0.format == B200CB_FORMAT_NCHW4;
+    if (d0.format != B200CB_FORMAT_NHWC && !nchw4)
         return B200CB_UNSUPPORTED_FORMAT;
+    if (nchw4) {
+        // QuantizedS8 only (the reference's NCHW4 algos are int8: implicit_gemm_int8_nchw4_*.cpp)
+        if (d0.src_dtype != B200CB_DT_QS8 || d0.dst_dtype != B200CB_DT_QS8)
+            return B200CB_UNSUPPORTED_DTYPE;
+        if (d0.ic % 4 != 0 || d0.oc % 4 != 0)
+            return B200CB_UNSUPPORTED_ALIGNMENT;
+        const uint64_t simg = (uint64_t)d0.ih * d0.iw * d0.ic;
+        if (d0.src_batch_stride != 0 && (d0.src_batch_stride < simg || d0.src_batch_stride % 4 != 0))
+            return B200CB_UNSUPPORTED_ALIGNMENT;
+    }
+    const b200cb_desc d = nchw4 ? nchw4_equivalent(d0) : d0;
     if (d.sparse != B200CB_SPARSE_DENSE || d.group != 1)
         return B200CB_UNSUPPORTED_PARAM;
     int kind;
@@ -1268,7 +1354,7 @@ int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
     const uint32_t in_es = kind == KIND_S8 ? 1 : 2;
     const uint32_t out_es = out32 ? 4 : in_es;
     // TMA needs 16-byte aligned global strides
-    if ((d.ic * in_es) % 16 != 0 || (d.oc * out_es) % 16 != 0)
+    if ((d.ic * in_es) % 16 != 0 || (!nchw4 && (d.oc * out_es) % 16 != 0))
         return B200CB_UNSUPPORTED_ALIGNMENT;
     if (d.n == 0 || d.oh == 0 || d.ow == 0 || d.fh == 0 || d.fw == 0)
         return B200CB_UNSUPPORTED_SHAPE;
@@ -1300,15 +1386,19 @@ int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
     b200cb_desc dd = d;
     if (d.src_batch_stride == src_img)
         dd.src_batch_stride = 0;
-    const Geometry g = make_geometry(dd, in_es);
+    // NCHW4 runs the generic modes only (no W-fold / stem / rows: their filter packing and output
+    // paths are NHWC-specific); its z is read in place by the epilogue, not through the TMA ring
+    const Geometry g = make_geometry(dd, in_es, !nchw4);
     if (g.folded && (g.pad_w_hi - (int32_t)(g.fw - 1) < -128 || g.pad_w_lo > 127))
         return B200CB_UNSUPPORTED_PARAM;
     const bool stem = g.stem && block_n == 64;
     const uint32_t kb_bytes = pick_kb_bytes(g.ic * in_es);
-    const uint32_t fixed0 = fixed_smem(out32 ? 1 : 2, block_n, d.has_z, (out32 || in_es == 2) ? 128 : 64);
+    const uint32_t fixed0 =
+            fixed_smem(out32 ? 1 : 2, block_n, d.has_z && !nchw4, (out32 || in_es == 2) ? 128 : 64);
     // rows mode: the filter and >= 2 input slabs must fit next to the epilogue buffers
     const RowsGeom rg = rows_geometry(dd, in_es, block_n);
-    const bool rows = !stem && !g.folded && rg.ok && fixed0 + rg.bres + 2 * rg.a_stage <= MAX_DYN_SMEM;
+    const bool rows = !nchw4 && !stem && !g.folded && rg.ok &&
+                      fixed0 + rg.bres + 2 * rg.a_stage <= MAX_DYN_SMEM;
     // generic modes: CTA pair (cta_group::2, 256 x BN tile, filter rows split between the two CTAs) or
     // a thread-block cluster sharing each filter tile by TMA multicast
     uint32_t cluster = 1, pair = 0;
@@ -1362,7 +1452,10 @@ int igemm_query(const b200cb_desc& d, uint32_t block_n, b200cb_plan* plan) {
     const uint32_t fwp = stem ? g.fw_packed : g.fw;
     plan->workspace_bytes =
             g.folded ? (((uint64_t)d.oc * d.fh * fwp * g.ic * in_es + 255) & ~255ull) : 0;
-    plan->desc = d;
+    if (nchw4)  // NHWC copy of src + KRSC copy of the filter, channels padded to d.ic
+        plan->workspace_bytes = align256((size_t)d.n * d.ih * d.iw * d.ic) +
+                                align256((size_t)d.oc * d.fh * d.fw * d.ic);
+    plan->desc = d0;
     return B200CB_OK;
 }
 
@@ -1405,7 +1498,8 @@ int igemm_launch(
         const b200cb_plan& plan, const void* src, const void* filter, const void* bias,
         const void* z, void* dst, void* workspace, size_t /*workspace_bytes*/,
         cudaStream_t stream) {
-    const b200cb_desc& d = plan.desc;
+    const bool nchw4 = plan.desc.format == B200CB_FORMAT_NCHW4;
+    const b200cb_desc d = nchw4 ? nchw4_equivalent(plan.desc) : plan.desc;
     const int kind = static_cast<int>(plan.reserved[0]);
     const bool out32 = plan.reserved[1] != 0;
     const uint32_t in_es = kind == KIND_S8 ? 1 : 2;
@@ -1419,12 +1513,28 @@ int igemm_launch(
 
     if (!src || !filter || !dst || (d.bias_mode != B200CB_BIAS_NONE && !bias) || (d.has_z && !z))
         return B200CB_ERR_NULL;
+    if (nchw4) {
+        // pre-pass: src (N, C/4, H, W, 4) -> NHWC, filter (OC, IC/4, FH, FW, 4) -> KRSC, in the workspace
+        const b200cb_desc& o = plan.desc;
+        if (!workspace)
+            return B200CB_ERR_WORKSPACE;
+        uint8_t* ws_src = static_cast<uint8_t*>(workspace);
+        uint8_t* ws_flt = ws_src + align256((size_t)d.n * d.ih * d.iw * d.ic);
+        int rc = relayout_c4_to_channels_last(
+                src, ws_src, o.n, o.ic, d.ic, o.ih * o.iw, o.src_batch_stride, stream);
+        if (rc == B200CB_OK)
+            rc = relayout_c4_to_channels_last(filter, ws_flt, o.oc, o.ic, d.ic, o.fh * o.fw, 0, stream);
+        if (rc != B200CB_OK)
+            return rc;
+        src = ws_src;
+        filter = ws_flt;
+    }
 
     b200cb_desc dd = d;
     const uint64_t src_img = (uint64_t)d.ih * d.iw * d.ic;
     if (d.src_batch_stride == src_img)
         dd.src_batch_stride = 0;
-    const Geometry g = make_geometry(dd, in_es);
+    const Geometry g = make_geometry(dd, in_es, !nchw4);
     const uint32_t kb_bytes = pick_kb_bytes(g.ic * in_es);
     const uint32_t kb_elems = kb_bytes / in_es;
     const CUtensorMapSwizzle in_swz = kb_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -1523,7 +1633,7 @@ int igemm_launch(
             return B200CB_ERR_DRIVER;
         }
     }
-    {
+    if (!nchw4) {
         const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
         // stem tiles are row segments: dst / z as (OC, OW, N*OH) so that a tile's tail is clipped
         uint64_t dims[3] = {d.oc, (stem || rows) ? (uint64_t)d.ow : M, (uint64_t)d.n * d.oh};
@@ -1583,7 +1693,10 @@ int igemm_launch(
     p.pair = (stem || rows) ? 0u : plan.reserved[7];
     p.flip = d.mode == B200CB_MODE_CONVOLUTION;
     p.has_bias = d.bias_mode != B200CB_BIAS_NONE;
-    p.has_z = d.has_z;
+    p.has_z = d.has_z && !nchw4;
+    p.nchw4 = nchw4;
+    p.z_direct = d.has_z && nchw4;
+    p.z = z;
     p.nonline = d.nonline_mode;
     p.rq = make_requant(d);
 #ifdef B200CB_DEBUG_TIMING

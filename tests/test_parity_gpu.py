@@ -84,6 +84,52 @@ def test_int8_epilogue_matrix(nl, has_z):
     _check(d, {"int_range": 127, "bias_range": 5000}, seed=77 + nl)
 
 
+NCHW4_CASES = [
+    # name, n, ic, h, w, oc, f, stride, pad, nonline, has_z     (dnn/test/cuda/conv_bias_int8.cpp:26-121)
+    ("1x1", 2, 64, 14, 14, 128, 1, 1, 0, C.NL_RELU, False),
+    ("3x3_z", 3, 32, 9, 11, 64, 3, 1, 1, C.NL_RELU, True),
+    ("5x5_s2", 2, 16, 17, 17, 32, 5, 2, 2, C.NL_IDENTITY, False),
+    ("7x7_ic4_stem", 2, 4, 30, 30, 64, 7, 2, 3, C.NL_RELU, False),
+    ("oc_tail_36_z_hswish", 2, 24, 8, 8, 36, 3, 1, 1, C.NL_H_SWISH, True),
+    ("identity_z", 1, 128, 7, 7, 256, 1, 1, 0, C.NL_IDENTITY, True),
+    ("resnet_l3_c2_pairable", 2, 256, 14, 14, 256, 3, 1, 1, C.NL_RELU, False),
+]
+
+
+@pytest.mark.parametrize("case", NCHW4_CASES, ids=[c[0] for c in NCHW4_CASES])
+def test_nchw4_int8_bit_exact(case):
+    """QuantizedS8 NCHW4 (BASELINE config 3): src / filter re-tiled by the pre-pass, dst and z accessed
+    in place by the epilogue -- 0 mismatching bytes against the oracle, saturation included."""
+    _name, n, ic, h, w, oc, f, s, pd, nl, has_z = case
+    d = K.make_desc("qs8", n, ic, h, w, oc, f, stride=s, pad=pd, fmt=C.FORMAT_NCHW4, nonline=nl, has_z=has_z,
+                    scales=(0.37, 0.71, None, 1.9, 23.0))
+    plan, info = _check(d, {"int_range": 127, "bias_range": 5000}, seed=31 + ic)
+    assert info["mismatch"] == 0
+
+
+def test_nchw4_equals_nhwc_full_size():
+    """N = 64 ResNet-50 l2 3x3 (pair tiles): the NCHW4 run equals the NHWC run of the same logical
+    tensors, element for element (layout independence at a size the oracle does not reach)."""
+    import torch
+    from . import _gpu as G
+    n, ic, hw, oc = 64, 128, 28, 128
+    dn = K.make_desc("qs8", n, ic, hw, hw, oc, 3, pad=1, nonline=C.NL_RELU, has_z=True,
+                     scales=(0.05, 0.02, None, 0.07, 0.11))
+    d4 = K.make_desc("qs8", n, ic, hw, hw, oc, 3, pad=1, fmt=C.FORMAT_NCHW4, nonline=C.NL_RELU, has_z=True,
+                     scales=(0.05, 0.02, None, 0.07, 0.11))
+    rng = np.random.default_rng(9)
+    src = rng.integers(-127, 128, (n, hw, hw, ic), dtype=np.int8)
+    flt = rng.integers(-127, 128, (oc, 3, 3, ic), dtype=np.int8)
+    z = rng.integers(-127, 128, (n, hw, hw, oc), dtype=np.int8)
+    bias = rng.integers(-5000, 5001, oc, dtype=np.int32)
+    got_n, _ = G.run_gpu(dn, src.reshape(-1), flt.reshape(-1), bias, z.reshape(-1))
+    to4 = lambda a: a.reshape(a.shape[0], a.shape[1], a.shape[2], a.shape[3] // 4, 4).transpose(0, 3, 1, 2, 4)
+    got_4, _ = G.run_gpu(d4, to4(src).reshape(-1), to4(flt).reshape(-1), bias, to4(z).reshape(-1))
+    back = got_4.reshape(n, oc // 4, hw, hw, 4).transpose(0, 2, 3, 1, 4).reshape(-1)
+    assert np.array_equal(back, got_n)
+    assert len(np.unique(got_n)) > 50
+
+
 def test_batch_stride_noncontiguous_src():
     """AlgoBase must accept a non-contiguous batch stride (dnn/src/cuda/conv_bias/algo.h:32-37)."""
     import torch
