@@ -1,0 +1,252 @@
+// TEST INFRASTRUCTURE -- drop-in check of megdnn::b200::ConvBiasForwardImpl (megengine_b200/host/).
+//
+// Drives the B200 operator exactly as the reference's Checker<ConvBiasForward> drives a backend
+// (dnn/test/common/checker.h, dnn/test/cuda/conv_bias.cpp:83-124, conv_bias_int8.cpp:798-835): the
+// reference's own naive operator (Handle::make(comp, 2), dnn/src/naive/conv_bias/opr_impl.cpp:211-292)
+// computes the expected dst on the host from the same TensorNDs, param and dtypes; the B200 operator
+// runs from device copies through the inherited public interface -- deduce_layout,
+// get_all_algorithms_info_safe, execution_policy (every algorithm, as fastrun does),
+// get_workspace_in_bytes, exec -- and the results are compared: QuantizedS8 bit for bit, BFloat16 /
+// Float16 with the reference test's own eps (2e-2 / 2e-2, metric dnn/test/common/utils.h:189-193).
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "conv_bias_b200.h"
+#include "megcore.h"
+#include "megdnn/dtype.h"
+#include "megdnn/handle.h"
+#include "megdnn/oprs.h"
+
+using namespace megdnn;
+
+namespace {
+
+#define CUDA_OK(x)                                                                  \
+    do {                                                                            \
+        cudaError_t e__ = (x);                                                      \
+        if (e__ != cudaSuccess) {                                                   \
+            fprintf(stderr, "CUDA %s at %d: %s\n", #x, __LINE__, cudaGetErrorString(e__)); \
+            exit(3);                                                                \
+        }                                                                           \
+    } while (0)
+
+struct Case {
+    const char* name;
+    param::ConvBias::Format format;
+    DTypeEnum kind;
+    size_t n, ic, h, w, oc, f, stride, pad, group;
+    param::ConvBias::NonlineMode nl;
+    bool has_z;
+};
+
+DType mk(DTypeEnum k, float scale) {
+    switch (k) {
+        case DTypeEnum::QuantizedS8: return dtype::QuantizedS8(scale);
+        case DTypeEnum::BFloat16: return dtype::BFloat16();
+        case DTypeEnum::Float16: return dtype::Float16();
+        default: return dtype::Float32();
+    }
+}
+
+void fill(std::vector<uint8_t>& buf, const DType& dt, size_t elems, std::mt19937& rng, float fscale) {
+    buf.resize(elems * dt.size());
+    if (dt.enumv() == DTypeEnum::QuantizedS8) {
+        std::uniform_int_distribution<int> u(-127, 127);
+        for (size_t i = 0; i < elems; ++i)
+            reinterpret_cast<int8_t*>(buf.data())[i] = static_cast<int8_t>(u(rng));
+    } else if (dt.enumv() == DTypeEnum::QuantizedS32) {
+        std::uniform_int_distribution<int> u(-5000, 5000);
+        for (size_t i = 0; i < elems; ++i)
+            reinterpret_cast<int32_t*>(buf.data())[i] = u(rng);
+    } else {
+        std::normal_distribution<float> g(0.f, fscale);
+        for (size_t i = 0; i < elems; ++i) {
+            float v = g(rng);
+            if (dt.enumv() == DTypeEnum::BFloat16)
+                reinterpret_cast<dt_bfloat16*>(buf.data())[i] = dt_bfloat16(v);
+            else
+                reinterpret_cast<dt_float16*>(buf.data())[i] = dt_float16(v);
+        }
+    }
+}
+
+float to_f32(const uint8_t* p, const DType& dt, size_t i) {
+    switch (dt.enumv()) {
+        case DTypeEnum::QuantizedS8: return reinterpret_cast<const int8_t*>(p)[i];
+        case DTypeEnum::BFloat16: return static_cast<float>(reinterpret_cast<const dt_bfloat16*>(p)[i]);
+        case DTypeEnum::Float16: return static_cast<float>(reinterpret_cast<const dt_float16*>(p)[i]);
+        default: return reinterpret_cast<const float*>(p)[i];
+    }
+}
+
+struct DevBuf {
+    void* p = nullptr;
+    explicit DevBuf(size_t bytes) { CUDA_OK(cudaMalloc(&p, bytes ? bytes : 16)); }
+    ~DevBuf() { cudaFree(p); }
+};
+
+bool run_case(Handle* host, cudaStream_t stream, const Case& c) {
+    std::mt19937 rng(1234 + c.ic * 7 + c.oc);
+    const bool q = c.kind == DTypeEnum::QuantizedS8;
+    const float s_src = 0.37f, s_flt = 0.71f, s_z = 1.9f, s_dst = 23.0f;
+    DType sd = mk(c.kind, s_src), fd = mk(c.kind, s_flt), dd = mk(c.kind, s_dst), zd = mk(c.kind, s_z);
+    DType bd = q ? DType(dtype::QuantizedS32(s_src * s_flt)) : sd;
+    const size_t oh = (c.h + 2 * c.pad - c.f) / c.stride + 1, ow = (c.w + 2 * c.pad - c.f) / c.stride + 1;
+    TensorLayout lsrc, lflt, lbias, ldst;
+    const bool grp = c.group > 1;
+    const size_t icpg = c.ic / c.group, ocpg = c.oc / c.group;
+    if (c.format == param::ConvBias::Format::NHWC) {
+        lsrc = TensorLayout({c.n, c.h, c.w, c.ic}, sd);
+        lflt = grp ? TensorLayout({c.group, ocpg, c.f, c.f, icpg}, fd) : TensorLayout({c.oc, c.f, c.f, c.ic}, fd);
+        lbias = TensorLayout({1, 1, 1, c.oc}, bd);
+    } else {  // NCHW4
+        lsrc = TensorLayout({c.n, c.ic / 4, c.h, c.w, 4}, sd);
+        lflt = TensorLayout({c.oc, c.ic / 4, c.f, c.f, 4}, fd);
+        lbias = TensorLayout({1, c.oc / 4, 1, 1, 4}, bd);
+    }
+    auto set_param = [&](ConvBiasForward* opr) {
+        auto& p = opr->param();
+        p.format = c.format;
+        p.nonlineMode = c.nl;
+        p.sparse = grp ? param::ConvBias::Sparse::GROUP : param::ConvBias::Sparse::DENSE;
+        p.pad_h = p.pad_w = c.pad;
+        p.stride_h = p.stride_w = c.stride;
+        p.compute_mode = q ? param::ConvBias::ComputeMode::DEFAULT : param::ConvBias::ComputeMode::FLOAT32;
+    };
+    auto ref = host->create_operator<ConvBiasForward>();
+    auto dut = b200::create_conv_bias_forward(host, stream);
+    set_param(ref.get());
+    set_param(dut.get());
+    // shape deduction must agree between the reference operator and ours (same inherited code path)
+    ldst.dtype = dd;
+    TensorLayout lz_absent(zd);
+    dut->deduce_layout(lsrc, lflt, lbias, lz_absent, ldst);
+    TensorLayout lz = c.has_z ? TensorLayout(TensorShape(ldst), zd) : lz_absent;
+    if (ldst.total_nr_elems() != c.n * oh * ow * c.oc) {
+        printf("FAIL %-28s deduce_layout -> %s\n", c.name, ldst.to_string().c_str());
+        return false;
+    }
+    std::vector<uint8_t> hsrc, hflt, hbias, hz, href(ldst.span().dist_byte()), hgot(ldst.span().dist_byte());
+    fill(hsrc, sd, lsrc.total_nr_elems(), rng, 1.f);
+    fill(hflt, fd, lflt.total_nr_elems(), rng, std::sqrt(2.f / (icpg * c.f * c.f)));
+    fill(hbias, bd, lbias.total_nr_elems(), rng, 0.3f);
+    if (c.has_z)
+        fill(hz, zd, lz.total_nr_elems(), rng, 1.f);
+    static char dummy[64];
+    // expected: the reference's naive operator on the host
+    {
+        size_t ws = ref->get_workspace_in_bytes(lsrc, lflt, lbias, lz, ldst, nullptr);
+        std::vector<dt_byte> wbuf(ws + 64);
+        ref->exec(
+                TensorND(hsrc.data(), lsrc), TensorND(hflt.data(), lflt), TensorND(hbias.data(), lbias),
+                TensorND(c.has_z ? (void*)hz.data() : (void*)dummy, lz), TensorND(href.data(), ldst), nullptr,
+                Workspace(wbuf.data(), ws));
+    }
+    DevBuf dsrc(hsrc.size()), dflt(hflt.size()), dbias(hbias.size()), dz(hz.size()), ddst(hgot.size());
+    CUDA_OK(cudaMemcpyAsync(dsrc.p, hsrc.data(), hsrc.size(), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(dflt.p, hflt.data(), hflt.size(), cudaMemcpyHostToDevice, stream));
+    CUDA_OK(cudaMemcpyAsync(dbias.p, hbias.data(), hbias.size(), cudaMemcpyHostToDevice, stream));
+    if (c.has_z)
+        CUDA_OK(cudaMemcpyAsync(dz.p, hz.data(), hz.size(), cudaMemcpyHostToDevice, stream));
+    // fastrun protocol: every algorithm the operator reports, forced through execution_policy()
+    auto infos = dut->get_all_algorithms_info_safe(lsrc, lflt, lbias, lz, ldst);
+    auto heur = dut->get_algorithm_info_heuristic(lsrc, lflt, lbias, lz, ldst);
+    bool all_ok = true;
+    std::string tried;
+    for (auto& info : infos) {
+        dut->execution_policy().algo = info.desc;
+        size_t ws = dut->get_workspace_in_bytes(lsrc, lflt, lbias, lz, ldst, nullptr);
+        DevBuf dws(ws);
+        CUDA_OK(cudaMemsetAsync(ddst.p, 0x55, hgot.size(), stream));
+        dut->exec(
+                TensorND(dsrc.p, lsrc), TensorND(dflt.p, lflt), TensorND(dbias.p, lbias),
+                TensorND(c.has_z ? dz.p : nullptr, lz), TensorND(ddst.p, ldst), nullptr, Workspace((dt_byte*)dws.p, ws));
+        CUDA_OK(cudaMemcpyAsync(hgot.data(), ddst.p, hgot.size(), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        size_t bad = 0;
+        double max_err = 0;
+        const size_t ne = ldst.total_nr_elems();
+        for (size_t i = 0; i < ne; ++i) {
+            if (q) {
+                bad += hgot[i] != href[i];
+            } else {
+                float a = to_f32(hgot.data(), dd, i), b = to_f32(href.data(), dd, i);
+                double e = std::fabs(a - b) / std::fmax(std::fmax(std::fabs(a), std::fabs(b)), 1.0);
+                if (!(e <= 2e-2))  // dnn/test/cuda/conv_bias.cpp:102-124,234-265
+                    ++bad;
+                max_err = std::fmax(max_err, e);
+            }
+        }
+        tried += std::string(" ") + info.desc.name + (info.desc == heur.desc ? "*" : "") +
+                 (bad ? "[BAD]" : "[ok]");
+        if (bad) {
+            all_ok = false;
+            printf("     %s: %zu / %zu elements differ (max rel err %.3g)\n", info.desc.name.c_str(), bad, ne, max_err);
+        }
+    }
+    printf("%s %-28s algos:%s\n", all_ok ? "PASS" : "FAIL", c.name, tried.c_str());
+    return all_ok;
+}
+
+}  // namespace
+
+int main() {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        fprintf(stderr, "dropin_driver: no CUDA device\n");
+        return 2;
+    }
+    cudaStream_t stream;
+    CUDA_OK(cudaStreamCreate(&stream));
+    megcoreDeviceHandle_t dev;
+    megcoreComputingHandle_t comp;
+    megcoreCreateDeviceHandle(&dev, megcorePlatformCPU);
+    megcoreCreateComputingHandle(&comp, dev);
+    auto host = Handle::make(comp, 2);  // naive: the oracle
+    using F = param::ConvBias::Format;
+    using NL = param::ConvBias::NonlineMode;
+    const Case cases[] = {
+            {"nhwc_qs8_3x3_z_relu", F::NHWC, DTypeEnum::QuantizedS8, 2, 64, 14, 14, 128, 3, 1, 1, 1, NL::RELU, true},
+            {"nhwc_qs8_1x1_hswish", F::NHWC, DTypeEnum::QuantizedS8, 3, 32, 9, 9, 64, 1, 1, 0, 1, NL::H_SWISH, false},
+            {"nhwc_qs8_7x7s2_stem", F::NHWC, DTypeEnum::QuantizedS8, 2, 16, 30, 30, 64, 7, 2, 3, 1, NL::RELU, false},
+            {"nchw4_qs8_3x3_z_relu", F::NCHW4, DTypeEnum::QuantizedS8, 2, 32, 9, 11, 64, 3, 1, 1, 1, NL::RELU, true},
+            {"nchw4_qs8_ic4_5x5s2", F::NCHW4, DTypeEnum::QuantizedS8, 2, 4, 17, 17, 32, 5, 2, 2, 1, NL::IDENTITY, false},
+            {"nhwc_bf16_3x3_z_relu", F::NHWC, DTypeEnum::BFloat16, 2, 64, 14, 14, 256, 3, 1, 1, 1, NL::RELU, true},
+            {"nhwc_f16_1x1s2_identity", F::NHWC, DTypeEnum::Float16, 2, 64, 14, 14, 128, 1, 2, 0, 1, NL::IDENTITY, false},
+            {"nhwc_bf16_depthwise3x3", F::NHWC, DTypeEnum::BFloat16, 2, 32, 14, 14, 32, 3, 1, 1, 32, NL::RELU, false},
+            {"nhwc_qs8_depthwise3x3s2", F::NHWC, DTypeEnum::QuantizedS8, 2, 32, 15, 15, 32, 3, 2, 1, 32, NL::RELU, false},
+    };
+    int failed = 0;
+    for (auto& c : cases) {
+        try {
+            failed += !run_case(host.get(), stream, c);
+        } catch (const std::exception& e) {
+            printf("FAIL %-28s exception: %s\n", c.name, e.what());
+            ++failed;
+        }
+    }
+    // error behaviour: an unsupported cell must throw through megdnn's error handler, not crash
+    {
+        auto dut = b200::create_conv_bias_forward(host.get(), stream);
+        dut->param().format = F::NCHW;
+        TensorLayout s({2, 8, 10, 10}, dtype::Float32()), f({8, 8, 3, 3}, dtype::Float32());
+        TensorLayout b({1, 8, 1, 1}, dtype::Float32()), z{DType(dtype::Float32())}, d({2, 8, 8, 8}, dtype::Float32());
+        bool threw = false;
+        try {
+            dut->get_all_algorithms_info_safe(s, f, b, z, d);
+        } catch (const std::exception&) {
+            threw = true;
+        }
+        printf("%s %-28s\n", threw ? "PASS" : "FAIL", "unsupported_cell_throws");
+        failed += !threw;
+    }
+    printf("dropin_driver: %d failed\n", failed);
+    return failed ? 1 : 0;
+}
