@@ -14,8 +14,10 @@
 //   -> element (c, fh, fw) at c*FH*FW + fh*FW + fw   (dnn/src/common/convolution.cpp:33-94).
 #include <stdio.h>
 #include <string.h>
+#include <type_traits>
 #include "common.h"
 #include "epilogue.cuh"
+#include "ptx.cuh"
 
 namespace b200cb {
 
@@ -311,6 +313,515 @@ __global__ void __launch_bounds__(256) dwconv_nhwc_kernel(const DwParams p) {
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3x3 depthwise, 16-bit floats: the bandwidth kernels (MobileNetV2 / ShuffleNetV2).
+//
+//   thread   = one channel PAIR (a 32-bit word of the NHWC row) x TW adjacent output columns x a
+//              vertical span of output rows;
+//   warp     = consecutive channel pairs: every load / store instruction touches whole 128-byte lines;
+//   window   = the three input rows of the current output row live UNPACKED (fp32 pairs) in registers
+//              and slide down: each output row fetches only its new input row(s), an input element is
+//              unpacked once per span;
+//   math     = packed FFMA2 (two channels per instruction), the pair's 3x3 weights in registers;
+//   epilogue = bias (accumulator init) + z + activation fused, one pass over HBM.
+// Two front ends feed the same window code:
+//   dw3x3_tma_kernel  (C % 8 == 0)  input tiles (rows x cols x 64 channels, halo and zero padding
+//                     included) are staged in shared memory by TMA, 3 tiles in flight per SM, so
+//                     memory-level parallelism does not depend on registers or occupancy;
+//   dw3x3_kernel      (any even C)  rows are read straight from global memory (ld.global.nc).
+struct Dw3Common {
+    const void* filter;
+    const void* bias;
+    const uint32_t* z;
+    uint32_t* dst;
+    uint32_t N, C, IH, IW, OH, OW, CP;
+    int32_t pad_h, pad_w;
+    uint64_t z_bwords, dst_bwords;  // batch strides in 32-bit words
+    uint32_t flip, has_bias, has_z, nonline;
+};
+
+template <int KIND>
+__device__ __forceinline__ float2 unpack2(uint32_t w) {
+    if constexpr (KIND == B200CB_DT_BF16)
+        return make_float2(bf16lo(w), bf16hi(w));
+    else
+        return make_float2(f16lo(w), f16hi(w));
+}
+template <int KIND>
+__device__ __forceinline__ float elem_f32(const void* p, size_t idx) {
+    if constexpr (KIND == B200CB_DT_BF16)
+        return __uint_as_float(static_cast<uint32_t>(reinterpret_cast<const unsigned short*>(p)[idx]) << 16);
+    else
+        return __half2float(reinterpret_cast<const __half*>(p)[idx]);
+}
+template <int KIND>
+__device__ __forceinline__ void load_weights(const Dw3Common& p, uint32_t c, float2 (&w)[9], float2& bias) {
+#pragma unroll
+    for (int tap = 0; tap < 9; ++tap) {
+        const int ft = p.flip ? 8 - tap : tap;
+        w[tap] = make_float2(elem_f32<KIND>(p.filter, (size_t)c * 9 + ft), elem_f32<KIND>(p.filter, (size_t)(c + 1) * 9 + ft));
+    }
+    bias = p.has_bias ? make_float2(elem_f32<KIND>(p.bias, c), elem_f32<KIND>(p.bias, c + 1)) : make_float2(0.f, 0.f);
+}
+
+// Output rows [oh0, oh1) x columns [ow0, ow0 + TW) of image n for channel pair cp.  `ld(r, raw)` fetches
+// the IN packed words of input row r, r counted from the top tap row of output row oh0.
+template <int KIND, int S, int TW, class Loader>
+__device__ __forceinline__ void dw3_slide(
+        const Dw3Common& p, const Loader& ld, uint32_t n, uint32_t cp, uint32_t oh0, uint32_t oh1,
+        uint32_t ow0, const float2 (&w)[9], float2 bias, bool store_ok) {
+    constexpr int IN = (TW - 1) * S + 3;
+    constexpr int NEW = S;  // new input rows per output row
+    const uint32_t* zp = p.z + n * p.z_bwords + cp;
+    uint32_t* dst = p.dst + n * p.dst_bwords + cp;
+    const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
+    const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
+    float2 buf[3][IN];
+    uint32_t raw[NEW][IN];
+    {
+        uint32_t r0[IN];
+        ld(0, r0);
+#pragma unroll
+        for (int j = 0; j < IN; ++j)
+            buf[0][j] = unpack2<KIND>(r0[j]);
+        if constexpr (S == 1) {
+            ld(1, r0);
+#pragma unroll
+            for (int j = 0; j < IN; ++j)
+                buf[1][j] = unpack2<KIND>(r0[j]);
+        }
+    }
+    auto fetch = [&](uint32_t oh) {
+        const int32_t r = static_cast<int32_t>(oh - oh0) * S + 3 - NEW;
+#pragma unroll
+        for (int k = 0; k < NEW; ++k)
+            ld(r + k, raw[k]);
+    };
+    fetch(oh0);
+    // one output row; T / M / B = which buffer holds the top / middle / bottom input row
+    auto step = [&](uint32_t oh, auto TT, auto MM, auto BB) {
+        constexpr int T = decltype(TT)::value, M = decltype(MM)::value, B = decltype(BB)::value;
+#pragma unroll
+        for (int j = 0; j < IN; ++j) {
+            if constexpr (S == 1) {
+                buf[B][j] = unpack2<KIND>(raw[0][j]);
+            } else {
+                buf[M][j] = unpack2<KIND>(raw[0][j]);
+                buf[B][j] = unpack2<KIND>(raw[1][j]);
+            }
+        }
+        uint32_t zraw[TW];
+        const size_t orow = (static_cast<size_t>(oh) * p.OW + ow0) * p.CP;
+        if (p.has_z) {
+#pragma unroll
+            for (int t2 = 0; t2 < TW; ++t2)
+                zraw[t2] = (store_ok && ow0 + t2 < p.OW) ? __ldg(zp + orow + static_cast<size_t>(t2) * p.CP) : 0u;
+        }
+        if (oh + 1 < oh1)
+            fetch(oh + 1);  // next row's loads fly while this row is computed
+#pragma unroll
+        for (int t2 = 0; t2 < TW; ++t2) {
+            float2 acc = bias;
+#pragma unroll
+            for (int fw = 0; fw < 3; ++fw) {
+                acc = __ffma2_rn(buf[T][t2 * S + fw], w[fw], acc);
+                acc = __ffma2_rn(buf[M][t2 * S + fw], w[3 + fw], acc);
+                acc = __ffma2_rn(buf[B][t2 * S + fw], w[6 + fw], acc);
+            }
+            if (p.has_z) {
+                const float2 zf = unpack2<KIND>(zraw[t2]);
+                acc.x += zf.x, acc.y += zf.y;
+            }
+            if (generic_act) {
+                acc.x = act_generic(acc.x, p.nonline), acc.y = act_generic(acc.y, p.nonline);
+            } else {
+                acc.x = acc.x <= act_lo ? act_lo : acc.x;
+                acc.y = acc.y <= act_lo ? act_lo : acc.y;
+            }
+            if (store_ok && ow0 + t2 < p.OW)
+                dst[orow + static_cast<size_t>(t2) * p.CP] =
+                        KIND == B200CB_DT_BF16 ? pack_bf16x2(acc.x, acc.y) : pack_f16x2(acc.x, acc.y);
+        }
+    };
+    using I0 = std::integral_constant<int, 0>;
+    using I1 = std::integral_constant<int, 1>;
+    using I2 = std::integral_constant<int, 2>;
+    uint32_t oh = oh0;
+    while (true) {
+        step(oh, I0{}, I1{}, I2{});
+        if (++oh >= oh1) break;
+        if constexpr (S == 1) {
+            step(oh, I1{}, I2{}, I0{});
+            if (++oh >= oh1) break;
+            step(oh, I2{}, I0{}, I1{});
+        } else {
+            step(oh, I2{}, I0{}, I1{});
+            if (++oh >= oh1) break;
+            step(oh, I1{}, I2{}, I0{});
+        }
+        if (++oh >= oh1) break;
+    }
+}
+
+// ---------------------------------------------------------------- front end 1: rows from global memory
+struct Dw3Params {
+    Dw3Common c;
+    const uint32_t* src;
+    uint32_t strips, spans, RH;
+    uint64_t total_items;
+    uint64_t src_bwords;
+};
+
+template <int KIND, int S, int TW>
+__global__ void __launch_bounds__(256, 2) dw3x3_kernel(const Dw3Params q) {
+    constexpr int IN = (TW - 1) * S + 3;
+    const Dw3Common& p = q.c;
+    const uint64_t item = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (item >= q.total_items)
+        return;
+    const uint32_t cp = static_cast<uint32_t>(item % p.CP);
+    uint64_t t = item / p.CP;
+    const uint32_t strip = static_cast<uint32_t>(t % q.strips);
+    t /= q.strips;
+    const uint32_t span = static_cast<uint32_t>(t % q.spans);
+    const uint32_t n = static_cast<uint32_t>(t / q.spans);
+    const uint32_t ow0 = strip * TW, oh0 = span * q.RH;
+    const uint32_t oh1 = oh0 + q.RH < p.OH ? oh0 + q.RH : p.OH;
+    float2 w[9], bias;
+    load_weights<KIND>(p, cp * 2, w, bias);
+    const uint32_t* src = q.src + n * q.src_bwords + cp;
+    const int32_t iw0 = static_cast<int32_t>(ow0) * S - p.pad_w;
+    const int32_t ih0 = static_cast<int32_t>(oh0) * S - p.pad_h;
+    uint32_t colmask = 0;
+#pragma unroll
+    for (int j = 0; j < IN; ++j)
+        colmask |= (static_cast<uint32_t>(iw0 + j) < p.IW ? 1u : 0u) << j;
+    auto ld = [&](int32_t r, uint32_t (&raw)[IN]) {
+        const int32_t ih = ih0 + r;
+        const bool rv = static_cast<uint32_t>(ih) < p.IH;
+        const uint32_t* row = src + (static_cast<int64_t>(ih) * p.IW + iw0) * static_cast<int64_t>(p.CP);
+#pragma unroll
+        for (int j = 0; j < IN; ++j)
+            raw[j] = (rv && ((colmask >> j) & 1)) ? __ldg(row + static_cast<size_t>(j) * p.CP) : 0u;
+    };
+    dw3_slide<KIND, S, TW>(p, ld, n, cp, oh0, oh1, ow0, w, bias, true);
+}
+
+// ---------------------------------------------------------------- front end 2: TMA-staged input tiles
+// Persistent CTAs walk the tiles with the channel block as the FASTEST tile index and a grid that is a
+// multiple of the channel-block count: a CTA keeps one channel block for its whole life (weights are
+// loaded once) and the channel blocks of one spatial tile run at the same time on neighbouring SMs, so
+// every DRAM line of the NHWC rows is consumed while it is still in L2.  Warp 15 is the TMA producer
+// (ring of `stages` tiles, full / empty mbarriers); each compute warp owns one unit = (column strip x
+// row span) of the tile.  The tile is [IHT][IWT][CB] in shared memory: a warp reading one pixel's
+// channel pairs hits consecutive banks, and all tile offsets are immediates or one register.
+struct Dw3TmaParams {
+    Dw3Common c;
+    CUtensorMap tmS;       // src (C, IW, IH, N), box (CB, IWT, IHT, 1), zero fill = conv padding
+    uint32_t TH, TWT;      // output rows / columns per tile
+    uint32_t IHT, IWT;     // input rows / columns per tile
+    uint32_t tiles_h, tiles_w, cblks;
+    uint32_t spatial_tiles;      // N * tiles_h * tiles_w
+    uint32_t RS, strips, units;  // rows per unit, column strips per tile, units per tile (<= 15)
+    uint32_t stage_bytes, tile_bytes, stages;  // ring stride (128-byte aligned) / bytes one TMA box delivers
+};
+constexpr uint32_t DW3_COMPUTE_WARPS = 15;  // + 1 producer warp = 16 warps: 128 registers per thread
+
+template <int KIND, int S, int TW, int CPB>
+__global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
+        dw3x3_tma_kernel(const __grid_constant__ Dw3TmaParams q) {
+    constexpr int IN = (TW - 1) * S + 3;
+    constexpr uint32_t PIX = CPB * 4;  // bytes per pixel in the tile
+    constexpr uint32_t CB = CPB * 2;
+    using namespace ptx;
+    const Dw3Common& p = q.c;
+    extern __shared__ __align__(128) uint8_t dsm[];
+    const uint32_t sbase = smem_u32(dsm);
+    const uint32_t bar_full = sbase, bar_empty = sbase + 64;  // [8] each
+    const uint32_t stage0 = sbase + 128;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&q.tmS);
+        for (uint32_t i = 0; i < q.stages; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, DW3_COMPUTE_WARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    // gridDim.x is a multiple of cblks: this CTA's channel block never changes
+    const uint32_t cblk = blockIdx.x % q.cblks;
+    const uint32_t sp0 = blockIdx.x / q.cblks, sp_step = gridDim.x / q.cblks;
+    if (warp == DW3_COMPUTE_WARPS) {
+        uint32_t st = 0, ph = 0;
+        for (uint32_t sp = sp0; sp < q.spatial_tiles; sp += sp_step) {
+            const uint32_t tw = sp % q.tiles_w, r = sp / q.tiles_w;
+            const uint32_t th = r % q.tiles_h, n = r / q.tiles_h;
+            mbar_wait(bar_empty + 8 * st, ph ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_full + 8 * st, q.tile_bytes);
+                tma_load_4d(
+                        stage0 + st * q.stage_bytes, &q.tmS, bar_full + 8 * st,
+                        static_cast<int32_t>(cblk * CB), static_cast<int32_t>(tw * q.TWT) * S - p.pad_w,
+                        static_cast<int32_t>(th * q.TH) * S - p.pad_h, static_cast<int32_t>(n));
+            }
+            __syncwarp();
+            if (++st == q.stages) {
+                st = 0;
+                ph ^= 1;
+            }
+        }
+        return;
+    }
+    // ---- compute warps: lane = channel pair (and, when CPB == 16, one of two adjacent units)
+    const uint32_t cpl = lane % CPB, sub = lane / CPB;
+    constexpr uint32_t SUBS = 32 / CPB;
+    const uint32_t c = cblk * CB + cpl * 2;
+    const bool ch_ok = c < p.C;
+    float2 w[9], bias;
+    load_weights<KIND>(p, ch_ok ? c : 0, w, bias);
+    const uint32_t u = warp * SUBS + sub;          // this thread's unit in every tile
+    const bool has_unit = u < q.units;
+    const uint32_t strip = u % q.strips, span = u / q.strips;
+    const uint32_t srow = q.IWT * PIX;                                  // bytes per tile row
+    const uint32_t unit_off = (span * q.RS * S * q.IWT + strip * TW * S) * PIX + cpl * 4;
+    const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
+    const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
+    const uint32_t cstride = p.CP;                 // words between adjacent output pixels
+    const uint32_t rstride = p.OW * p.CP;          // words between output rows
+    uint32_t st = 0, ph = 0;
+    for (uint32_t sp = sp0; sp < q.spatial_tiles; sp += sp_step) {
+        const uint32_t tw = sp % q.tiles_w, r = sp / q.tiles_w;
+        const uint32_t th = r % q.tiles_h, n = r / q.tiles_h;
+        mbar_wait(bar_full + 8 * st, ph);
+        const uint32_t oh0 = th * q.TH + span * q.RS;
+        uint32_t oh1 = oh0 + q.RS;
+        if (oh1 > (th + 1) * q.TH)
+            oh1 = (th + 1) * q.TH;
+        if (oh1 > p.OH)
+            oh1 = p.OH;
+        const uint32_t ow0 = tw * q.TWT + strip * TW;
+        if (has_unit && oh0 < oh1 && ow0 < p.OW) {
+            // next tile row to read (generic pointer into the staged tile; offsets fold into the LDS)
+            const uint8_t* a = dsm + 128 + st * q.stage_bytes + unit_off;
+            uint32_t cmask = 0;                                    // columns this thread stores
+#pragma unroll
+            for (int t2 = 0; t2 < TW; ++t2)
+                cmask |= (ch_ok && ow0 + t2 < p.OW ? 1u : 0u) << t2;
+            uint32_t* drow = p.dst + n * p.dst_bwords + (static_cast<size_t>(oh0) * p.OW + ow0) * p.CP + c / 2;
+            const uint32_t* zrow = p.z + n * p.z_bwords + (static_cast<size_t>(oh0) * p.OW + ow0) * p.CP + c / 2;
+            float2 buf[3][IN];
+            auto lds_row = [&](float2 (&dstrow)[IN]) {
+                uint32_t raw[IN];
+#pragma unroll
+                for (int j = 0; j < IN; ++j)
+                    raw[j] = *reinterpret_cast<const uint32_t*>(a + j * PIX);
+#pragma unroll
+                for (int j = 0; j < IN; ++j)
+                    dstrow[j] = unpack2<KIND>(raw[j]);
+                a += srow;
+            };
+            lds_row(buf[0]);
+            if constexpr (S == 1)
+                lds_row(buf[1]);
+            auto step = [&](auto TT, auto MM, auto BB) {
+                constexpr int T = decltype(TT)::value, M = decltype(MM)::value, B = decltype(BB)::value;
+                if constexpr (S == 2)
+                    lds_row(buf[M]);
+                lds_row(buf[B]);
+                float2 acc[TW];
+#pragma unroll
+                for (int t2 = 0; t2 < TW; ++t2) {
+                    acc[t2] = bias;
+#pragma unroll
+                    for (int fw = 0; fw < 3; ++fw) {
+                        acc[t2] = __ffma2_rn(buf[T][t2 * S + fw], w[fw], acc[t2]);
+                        acc[t2] = __ffma2_rn(buf[M][t2 * S + fw], w[3 + fw], acc[t2]);
+                        acc[t2] = __ffma2_rn(buf[B][t2 * S + fw], w[6 + fw], acc[t2]);
+                    }
+                }
+                if (p.has_z) {
+#pragma unroll
+                    for (int t2 = 0; t2 < TW; ++t2)
+                        if ((cmask >> t2) & 1) {
+                            const float2 zf = unpack2<KIND>(__ldg(zrow + t2 * cstride));
+                            acc[t2].x += zf.x, acc[t2].y += zf.y;
+                        }
+                    zrow += rstride;
+                }
+                if (generic_act) {
+#pragma unroll
+                    for (int t2 = 0; t2 < TW; ++t2)
+                        acc[t2].x = act_generic(acc[t2].x, p.nonline), acc[t2].y = act_generic(acc[t2].y, p.nonline);
+                } else {
+#pragma unroll
+                    for (int t2 = 0; t2 < TW; ++t2)
+                        acc[t2].x = fmaxf(acc[t2].x, act_lo), acc[t2].y = fmaxf(acc[t2].y, act_lo);
+                }
+#pragma unroll
+                for (int t2 = 0; t2 < TW; ++t2)
+                    if ((cmask >> t2) & 1)
+                        drow[t2 * cstride] = KIND == B200CB_DT_BF16 ? pack_bf16x2(acc[t2].x, acc[t2].y)
+                                                                    : pack_f16x2(acc[t2].x, acc[t2].y);
+                drow += rstride;
+            };
+            using I0 = std::integral_constant<int, 0>;
+            using I1 = std::integral_constant<int, 1>;
+            using I2 = std::integral_constant<int, 2>;
+            uint32_t rows = oh1 - oh0;
+            while (true) {
+                step(I0{}, I1{}, I2{});
+                if (--rows == 0) break;
+                if constexpr (S == 1) {
+                    step(I1{}, I2{}, I0{});
+                    if (--rows == 0) break;
+                    step(I2{}, I0{}, I1{});
+                } else {
+                    step(I2{}, I0{}, I1{});
+                    if (--rows == 0) break;
+                    step(I1{}, I2{}, I0{});
+                }
+                if (--rows == 0) break;
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(bar_empty + 8 * st);
+        if (++st == q.stages) {
+            st = 0;
+            ph ^= 1;
+        }
+    }
+}
+
+bool dw3_applicable(const b200cb_desc& d) {
+    return (d.src_dtype == B200CB_DT_BF16 || d.src_dtype == B200CB_DT_F16) && d.fh == 3 && d.fw == 3 &&
+           d.stride_h == d.stride_w && (d.stride_h == 1 || d.stride_h == 2) && d.dilate_h == 1 &&
+           d.dilate_w == 1 && d.ic % 2 == 0 && d.src_batch_stride % 2 == 0 && d.dst_batch_stride % 2 == 0 &&
+           d.z_batch_stride % 2 == 0;
+}
+bool dw3_tma_applicable(const b200cb_desc& d) {
+    return dw3_applicable(d) && d.ic % 8 == 0 && (d.src_batch_stride * 2) % 16 == 0 && d.pad_h <= 8 && d.pad_w <= 8;
+}
+
+template <int KIND>
+cudaError_t launch_dw3(const b200cb_desc& d, Dw3Params& p, cudaStream_t stream) {
+    const uint32_t tw = d.stride_h == 1 ? 4 : 2;
+    p.strips = (d.ow + tw - 1) / tw;
+    // vertical span: long enough to amortise the 2 halo rows, short enough to fill the machine
+    uint32_t rh = 16;
+    auto items = [&](uint32_t r) { return (uint64_t)p.c.CP * p.strips * ((d.oh + r - 1) / r) * d.n; };
+    while (rh > 4 && items(rh) < 148ull * 2048)
+        rh /= 2;
+    p.RH = rh;
+    p.spans = (d.oh + rh - 1) / rh;
+    p.total_items = items(rh);
+    const uint64_t blocks = (p.total_items + 255) / 256;
+    if (blocks > 0x7fffffffull)
+        return cudaErrorInvalidValue;
+    if (d.stride_h == 1)
+        dw3x3_kernel<KIND, 1, 4><<<(uint32_t)blocks, 256, 0, stream>>>(p);
+    else
+        dw3x3_kernel<KIND, 2, 2><<<(uint32_t)blocks, 256, 0, stream>>>(p);
+    return cudaGetLastError();
+}
+
+template <int KIND, int S, int TW, int CPB>
+cudaError_t launch_dw3_tma_variant(const Dw3TmaParams& q, uint32_t grid, uint32_t smem, cudaStream_t stream) {
+    auto kern = dw3x3_tma_kernel<KIND, S, TW, CPB>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM);
+        if (e != cudaSuccess)
+            return e;
+        attr_set[dev] = true;
+    }
+    kern<<<grid, (DW3_COMPUTE_WARPS + 1) * 32, smem, stream>>>(q);
+    return cudaGetLastError();
+}
+
+// tile geometry + tensor map of the TMA front end
+template <int KIND>
+int launch_dw3_tma(const b200cb_desc& d, const Dw3Common& c, const void* src, cudaStream_t stream) {
+    Dw3TmaParams q;
+    memset(&q, 0, sizeof(q));
+    q.c = c;
+    const uint32_t S = d.stride_h, TW = S == 1 ? 4 : 2;
+    const uint32_t CB = d.ic > 32 ? 64 : 32, CPB = CB / 2, SUBS = 32 / CPB;
+    // column strips per tile: 7 (28 / 14 output columns) divides the MobileNet widths; small images
+    // take their whole width.  One unit per compute warp (x SUBS): spans = floor(15 * SUBS / strips).
+    const uint32_t strips_full = (d.ow + TW - 1) / TW;
+    q.strips = strips_full <= 8 ? strips_full : 7;
+    q.TWT = q.strips * TW;
+    q.IWT = (q.TWT - 1) * S + 3;
+    uint32_t spans = DW3_COMPUTE_WARPS * SUBS / q.strips;
+    if (spans < 1)
+        spans = 1;
+    if (spans > d.oh)
+        spans = d.oh;
+    // rows per unit: as many as a ~64 KiB stage holds (3 stages in flight), at most the image
+    const uint32_t budget = 64 * 1024;
+    uint32_t rs = (d.oh + spans - 1) / spans;
+    while (rs > 1 && ((spans * rs - 1) * S + 3) * q.IWT * CB * 2 > budget)
+        --rs;
+    q.RS = rs;
+    q.TH = spans * rs;
+    q.units = q.strips * spans;
+    q.IHT = (q.TH - 1) * S + 3;
+    if (q.IHT > 256 || q.IWT > 256 || q.units > DW3_COMPUTE_WARPS * SUBS)
+        return B200CB_UNSUPPORTED_SHAPE;
+    q.tiles_h = (d.oh + q.TH - 1) / q.TH;
+    q.tiles_w = (d.ow + q.TWT - 1) / q.TWT;
+    q.cblks = (d.ic + CB - 1) / CB;
+    const uint64_t spatial = (uint64_t)d.n * q.tiles_h * q.tiles_w;
+    if (spatial > 0x7fffffffull)
+        return B200CB_UNSUPPORTED_SHAPE;
+    q.spatial_tiles = (uint32_t)spatial;
+    q.tile_bytes = q.IHT * q.IWT * CB * 2;
+    q.stage_bytes = (q.tile_bytes + 127) & ~127u;
+    q.stages = (MAX_DYN_SMEM - 128) / q.stage_bytes;
+    if (q.stages > 4)
+        q.stages = 4;
+    if (q.stages < 2)
+        return B200CB_UNSUPPORTED_SHAPE;
+    const uint64_t src_b = d.src_batch_stride ? d.src_batch_stride : (uint64_t)d.ih * d.iw * d.ic;
+    uint64_t dims[4] = {d.ic, d.iw, d.ih, d.n};
+    uint64_t strides[3] = {(uint64_t)d.ic * 2, (uint64_t)d.iw * d.ic * 2, src_b * 2};
+    uint32_t box[4] = {CB, q.IWT, q.IHT, 1};
+    CUresult cr = encode_tiled(
+            &q.tmS, KIND == B200CB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+            src, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    if (cr != CUDA_SUCCESS) {
+        char buf[64];
+        snprintf(buf, sizeof(buf), "CUresult %d (depthwise src map)", (int)cr);
+        set_last_error("cuTensorMapEncodeTiled", buf);
+        return B200CB_ERR_DRIVER;
+    }
+    // persistent grid: a multiple of the channel-block count, at most one CTA per SM
+    const uint32_t sms = (uint32_t)device_sm_count();
+    if (q.cblks > sms)
+        return B200CB_UNSUPPORTED_SHAPE;
+    uint64_t per = sms / q.cblks;
+    if (per > spatial)
+        per = spatial;
+    const uint32_t grid = (uint32_t)per * q.cblks;
+    const uint32_t smem = 128 + q.stages * q.stage_bytes;
+    cudaError_t e;
+    if (S == 1)
+        e = CPB == 32 ? launch_dw3_tma_variant<KIND, 1, 4, 32>(q, grid, smem, stream)
+                      : launch_dw3_tma_variant<KIND, 1, 4, 16>(q, grid, smem, stream);
+    else
+        e = CPB == 32 ? launch_dw3_tma_variant<KIND, 2, 2, 32>(q, grid, smem, stream)
+                      : launch_dw3_tma_variant<KIND, 2, 2, 16>(q, grid, smem, stream);
+    if (e != cudaSuccess) {
+        set_last_error("dw3x3 tma launch", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    return B200CB_OK;
+}
+
 template <int KIND, int F, int S, int TW>
 cudaError_t launch_dw(const DwParams& p, dim3 grid, size_t smem, cudaStream_t stream) {
     auto kern = dwconv_nhwc_kernel<KIND, F, S, TW>;
@@ -373,15 +884,18 @@ int dwconv_query(const b200cb_desc& d, b200cb_plan* plan) {
     if (dt == B200CB_DT_QS8 && d.nonline_mode == B200CB_NL_SIGMOID)
         return B200CB_UNSUPPORTED_PARAM;
     const uint32_t vec = dw_vec(dt);
-    if (d.ic % vec != 0)
-        return B200CB_UNSUPPORTED_ALIGNMENT;
     const uint32_t es = dtype_size(dt);
-    if ((d.src_batch_stride * es) % 16 || (d.dst_batch_stride * es) % 16 || (d.z_batch_stride * es) % 16)
-        return B200CB_UNSUPPORTED_ALIGNMENT;
+    // the 3x3 16-bit bandwidth kernel works on channel pairs; everything else on 16-byte vectors
+    if (!dw3_applicable(d)) {
+        if (d.ic % vec != 0)
+            return B200CB_UNSUPPORTED_ALIGNMENT;
+        if ((d.src_batch_stride * es) % 16 || (d.dst_batch_stride * es) % 16 || (d.z_batch_stride * es) % 16)
+            return B200CB_UNSUPPORTED_ALIGNMENT;
+    }
     if (d.fh * d.fw > 1024)
         return B200CB_UNSUPPORTED_SHAPE;
 
-    const uint32_t cv = d.ic / vec;
+    const uint32_t cv = d.ic / vec ? d.ic / vec : 1;
     uint32_t cvb = 1;
     for (uint32_t c = 1; c <= 32 && c <= cv; ++c)
         if (cv % c == 0)
@@ -409,6 +923,38 @@ int dwconv_launch(
     const b200cb_desc& d = plan.desc;
     if (!src || !filter || !dst || (d.bias_mode != B200CB_BIAS_NONE && !bias) || (d.has_z && !z))
         return B200CB_ERR_NULL;
+    if (dw3_applicable(d)) {
+        Dw3Common c;
+        memset(&c, 0, sizeof(c));
+        c.filter = filter, c.bias = bias;
+        c.z = static_cast<const uint32_t*>(z), c.dst = static_cast<uint32_t*>(dst);
+        c.N = d.n, c.C = d.ic, c.IH = d.ih, c.IW = d.iw, c.OH = d.oh, c.OW = d.ow, c.CP = d.ic / 2;
+        c.pad_h = d.pad_h, c.pad_w = d.pad_w;
+        c.dst_bwords = (d.dst_batch_stride ? d.dst_batch_stride : (uint64_t)d.oh * d.ow * d.oc) / 2;
+        c.z_bwords = (d.z_batch_stride ? d.z_batch_stride : (uint64_t)d.oh * d.ow * d.oc) / 2;
+        c.flip = d.mode == B200CB_MODE_CONVOLUTION;
+        c.has_bias = d.bias_mode != B200CB_BIAS_NONE;
+        c.has_z = d.has_z;
+        c.nonline = d.nonline_mode;
+        if (dw3_tma_applicable(d) && plan.reserved[2] != 2) {  // reserved[2] == 2: force the register front end
+            int rc = d.src_dtype == B200CB_DT_BF16 ? launch_dw3_tma<B200CB_DT_BF16>(d, c, src, stream)
+                                                   : launch_dw3_tma<B200CB_DT_F16>(d, c, src, stream);
+            if (rc != B200CB_UNSUPPORTED_SHAPE)
+                return rc;
+        }
+        Dw3Params q;
+        memset(&q, 0, sizeof(q));
+        q.c = c;
+        q.src = static_cast<const uint32_t*>(src);
+        q.src_bwords = (d.src_batch_stride ? d.src_batch_stride : (uint64_t)d.ih * d.iw * d.ic) / 2;
+        cudaError_t e3 = d.src_dtype == B200CB_DT_BF16 ? launch_dw3<B200CB_DT_BF16>(d, q, stream)
+                                                      : launch_dw3<B200CB_DT_F16>(d, q, stream);
+        if (e3 != cudaSuccess) {
+            set_last_error("dw3x3 launch", cudaGetErrorString(e3));
+            return B200CB_ERR_CUDA;
+        }
+        return B200CB_OK;
+    }
     const bool spec = dw_specialised(d);
     const uint32_t vec = dw_vec(d.src_dtype);
     const uint32_t tw = dw_tw(d.src_dtype, spec);
