@@ -340,6 +340,12 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         cluster_sync_all();  // peers multicast into this CTA's stages and arrive on its barriers
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot_gen;
+    // Programmatic dependent launch: everything above (barrier init, TMEM allocation, descriptor
+    // prefetch) overlapped the tail of the previous kernel in the stream; no global memory is read or
+    // written before its completion is observed here.  The next kernel may start its own prologue as
+    // soon as this grid's CTAs retire.
+    pdl_launch_dependents();
+    pdl_wait();
 
     if (warp == 0 && stem) {
         // ============================ TMA producer, stem mode ============================
@@ -1093,13 +1099,16 @@ cudaError_t launch_variant(
     cfg.blockDim = dim3(Traits<KIND, OUT32>::THREADS, 1, 1);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
-    attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = C;
-    attr[0].val.clusterDim.y = 1;
-    attr[0].val.clusterDim.z = 1;
+    cudaLaunchAttribute attr[2];
+    static const bool use_pdl = getenv("B200CB_NO_PDL") == nullptr;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+    attr[1].id = cudaLaunchAttributeClusterDimension;
+    attr[1].val.clusterDim.x = C;
+    attr[1].val.clusterDim.y = 1;
+    attr[1].val.clusterDim.z = 1;
     cfg.attrs = attr;
-    cfg.numAttrs = C > 1 ? 1 : 0;
+    cfg.numAttrs = C > 1 ? 2 : 1;
     if (grid == 0) {
         grid = static_cast<uint32_t>(device_sm_count());
         if (C > 1) {

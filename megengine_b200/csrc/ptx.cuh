@@ -48,6 +48,16 @@ __device__ __forceinline__ void cluster_sync_all() {
                  "barrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// wait: blocks until the preceding kernel of the stream has completed and its writes are visible;
+// launch_dependents: lets the next kernel's CTAs be scheduled as this grid's CTAs retire.
+__device__ __forceinline__ void pdl_wait() {
+    asm volatile("griddepcontrol.wait;" ::: "memory");
+}
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
