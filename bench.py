@@ -188,7 +188,7 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------ GPU arm
-def build_layers(kind, batch, device):
+def build_layers(kind, batch, device, conv1_pixel_bytes=8):
     """private tensors + plan for each of the 53 layer instances."""
     import torch
     import megengine_b200 as mb
@@ -203,7 +203,9 @@ def build_layers(kind, batch, device):
         _nm, ic, h, w, oc, f, s, p, has_z, _cnt = layers[name]
         ic_real = ic
         if ic < 8:
-            ic = 16 if kind == "qs8" else 8   # conv1: IC 3 zero-padded (gopt PaddingChannelPass); flops count IC=3
+            # conv1: IC 3 zero-padded (gopt PaddingChannelPass) to an 8- or 16-byte pixel -- bf16 IC 4 / 8,
+            # int8 IC 8 / 16 (SURVEY 8d config 2 runs both); flops and algorithmic bytes count IC = 3
+            ic = conv1_pixel_bytes // (1 if kind == "qs8" else 2)
         oh, ow = K.conv_out(h, f, s, p), K.conv_out(w, f, s, p)
         g.manual_seed(1000 + idx)
         opr = handle.create_operator()
@@ -293,6 +295,8 @@ def main():
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "qs8"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--conv1-pixel-bytes", type=int, default=8, choices=[8, 16],
+                    help="channel padding of the 3-channel network input: 8 bytes (bf16 IC=4 / int8 IC=8) or 16")
     ap.add_argument("--layer-report", default="", help="write the per-layer roofline table (JSON) here")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
@@ -315,7 +319,7 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(device))
     peaks = load_peaks()
 
-    handle, layers = build_layers(args.dtype, args.batch, device)
+    handle, layers = build_layers(args.dtype, args.batch, device, args.conv1_pixel_bytes)
     flops_step = sum(L["flops"] for L in layers)
     bytes_step = sum(L["bytes"] for L in layers)
     launches_step = sum(L["launches"] for L in layers)
@@ -447,7 +451,8 @@ def main():
             "data": "synthetic",
             "config": {"workload": "resnet50_v1.5_53_convbias_layers_%s_nhwc" % args.dtype,
                        "batch_per_gpu": args.batch, "global_batch": args.batch * world, "format": "NHWC",
-                       "epilogue": "bias+relu, +z on 16 layers", "sharding": "batch, no collective in timed path",
+                       "epilogue": "bias+relu, +z on 16 layers",
+                       "conv1_input": "IC 3 zero-padded to %d-byte pixels" % args.conv1_pixel_bytes, "sharding": "batch, no collective in timed path",
                        "l2": "inputs larger than L2: every layer owns private tensors, %.1f GB touched per step"
                              % (bytes_step / 1e9)},
             "tflops": tf,

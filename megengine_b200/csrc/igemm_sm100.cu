@@ -57,6 +57,9 @@ struct IgemmParams {
     uint32_t stem_nj;           // pixel pairs per staged input row
     uint32_t stem_fh, stem_fw2; // filter rows, tap pairs per row
     int32_t stem_pad_lo2;       // pixel pairs of left padding
+    // stem4: a pixel PAIR is one 16-byte unit (IC * es == 8, e.g. bf16 IC = 4): a single plane, K step =
+    // two consecutive pairs (LBO = 16 B), filter rows of 64 bytes (SWIZZLE_64B)
+    uint32_t stem4;
     // rows mode (a_mode 3): stride-1 conv over the padded-linear pixel index m' = oh * PW + ow',
     // PW = OW + FW - 1; a tile = 128 consecutive m' of one image, its input rows resident in smem
     uint32_t PW, tiles_per_img, rows_rh;
@@ -272,12 +275,15 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     const bool rows = p.a_mode == 3;
     const uint32_t plane_bytes = rows ? p.rows_rh * p.PW * 128u   // rows: one 64-channel block of the slab
                                       : p.stem_fh * p.stem_nj * 16; // stem: one pixel parity, all filter rows
-    const uint32_t a_bytes = stem ? 2 * plane_bytes : rows ? p.num_kc * plane_bytes : IGEMM_BLOCK_M * p.kb_bytes;
+    const uint32_t a_bytes = stem ? (p.stem4 ? plane_bytes : 2 * plane_bytes)
+                             : rows ? p.num_kc * plane_bytes
+                                    : IGEMM_BLOCK_M * p.kb_bytes;
+    const uint32_t stem_rb = p.stem4 ? 64u : 128u;  // bytes of one packed filter row
     // CTA pair: each CTA stages only its half of the filter tile's rows
     constexpr bool pair = PAIR != 0;
     const uint32_t b_rows = pair ? BN / 2 : BN;
     const uint32_t stage_bytes = (stem || rows) ? a_bytes : a_bytes + b_rows * p.kb_bytes;
-    const uint32_t bres_bytes = stem ? p.stem_fh * BN * 128u : rows ? p.num_taps * p.num_kc * BN * 128u : 0u;
+    const uint32_t bres_bytes = stem ? p.stem_fh * BN * stem_rb : rows ? p.num_taps * p.num_kc * BN * 128u : 0u;
     const uint32_t sZ = smem_base + OFF_SZ;
     const uint32_t sBres = sZ + (p.has_z ? NZ * T::ZBUF_BYTES : SLABS_BYTES);  // resident filter
     const uint32_t sStage = sBres + bres_bytes;
@@ -352,9 +358,9 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         // the whole (packed) filter once, then per tile the FH input rows it needs, de-interleaved
         // into even / odd pixel planes: [parity][fh][pixel pair][16 bytes], no swizzle
         if (elect_one()) {
-            mbar_arrive_expect_tx(bar_bres, p.stem_fh * BN * 128u);
+            mbar_arrive_expect_tx(bar_bres, bres_bytes);
             for (uint32_t fh = 0; fh < p.stem_fh; ++fh)
-                tma_load_3d(sBres + fh * BN * 128u, &p.tmB, bar_bres, 0, static_cast<int32_t>(fh), 0);
+                tma_load_3d(sBres + fh * BN * stem_rb, &p.tmB, bar_bres, 0, static_cast<int32_t>(fh), 0);
         }
         uint32_t stage = 0, phase = 0;
         for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
@@ -369,7 +375,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 const uint32_t sa = sStage + stage * stage_bytes;
                 mbar_arrive_expect_tx(full, stage_bytes);
                 tma_load_4d(sa, &p.tmA, full, 0, j0, ih0, static_cast<int32_t>(img));
-                tma_load_4d(sa + plane_bytes, &p.tmA2, full, 0, j0, ih0, static_cast<int32_t>(img));
+                if (!p.stem4)
+                    tma_load_4d(sa + plane_bytes, &p.tmA2, full, 0, j0, ih0, static_cast<int32_t>(img));
             }
             __syncwarp();
             if (++stage == p.stages) {
@@ -390,17 +397,21 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 const uint32_t sa = sStage + stage * stage_bytes;
                 // A: rows = output pixels (16 bytes apart), K = [even pixel 8ch | odd pixel 8ch]:
                 // no swizzle, LBO = parity-plane distance, SBO = 128 B; one entry (16 B) per tap pair
-                const uint32_t a_hi = desc_hi(128, 0), b_hi = desc_hi(1024, 2);
-                uint32_t a_lo = desc_lo(sa, plane_bytes);
+                // stem4: K = [pair j | pair j + 1], the two halves 16 bytes apart, one K step per two pairs
+                const uint32_t a_hi = desc_hi(128, 0);
+                const uint32_t b_hi = p.stem4 ? desc_hi(512, 4) : desc_hi(1024, 2);
+                uint32_t a_lo = desc_lo(sa, p.stem4 ? 16u : plane_bytes);
                 uint32_t b_lo = desc_lo(sBres, 16);
+                const uint32_t ksteps = p.stem4 ? (p.stem_fw2 + 1) / 2 : p.stem_fw2;
+                const uint32_t a_step = p.stem4 ? 2u : 1u;
                 uint32_t first = 0;
                 for (uint32_t fh = 0; fh < p.stem_fh; ++fh) {
-                    for (uint32_t t2 = 0; t2 < p.stem_fw2; ++t2) {
-                        mma_issue<KIND>(taddr, a_lo + t2, a_hi, b_lo + 2 * t2, b_hi, IDESC, first);
+                    for (uint32_t t2 = 0; t2 < ksteps; ++t2) {
+                        mma_issue<KIND>(taddr, a_lo + t2 * a_step, a_hi, b_lo + 2 * t2, b_hi, IDESC, first);
                         first = 1;
                     }
-                    a_lo += p.stem_nj;        // next filter row: stem_nj entries further
-                    b_lo += BN * 128u / 16u;  // next 128-byte K row block of the resident filter
+                    a_lo += p.stem_nj;            // next filter row: stem_nj entries further
+                    b_lo += BN * stem_rb / 16u;   // next K row block of the resident filter
                 }
                 mma_commit(bar_empty + 8 * stage);
                 mma_commit(bar_tfull + 8 * acc);
@@ -1139,6 +1150,7 @@ struct Geometry {
     uint32_t fw_packed;   // tap pairs stored per filter row in the packed filter
     bool folded;
     bool stem;            // a_mode 2: resident filter + one input-row slab per tile
+    bool stem4;           // ... with a pixel pair per 16-byte unit (IC * es == 8)
 };
 constexpr uint32_t STEM_NJ = 136;  // 128 output pixels + up to 4 tap pairs - 1, rounded up to 8
 
@@ -1164,6 +1176,7 @@ Geometry make_geometry(const b200cb_desc& d, uint32_t in_es, bool allow_fold = t
     g.fw_packed = d.fw;
     g.folded = false;
     g.stem = false;
+    g.stem4 = false;
     if (allow_fold && d.stride_w == 2 && d.dilate_w == 1 && d.iw % 2 == 0 && d.ic * in_es <= 16 &&
         d.mode == B200CB_MODE_CROSS_CORRELATION && d.src_batch_stride == 0) {
         // window of output ow covers pixels [2*ow - pad, 2*ow - pad + FW); extend it to an even start
@@ -1181,9 +1194,10 @@ Geometry make_geometry(const b200cb_desc& d, uint32_t in_es, bool allow_fold = t
         g.folded = true;
         // stem mode: every tap pair of a filter row in one 128-byte K row (4 pairs), the whole
         // filter resident in shared memory (<= 64 output channels, <= 8 filter rows)
-        if (d.ic * in_es == 16 && fw2 <= 4 && d.fh <= 8 && d.oc <= 64 && d.stride_h == 2 &&
-            d.dilate_h == 1 && pad_lo2 <= 64) {
+        if ((d.ic * in_es == 16 || d.ic * in_es == 8) && fw2 <= 4 && d.fh <= 8 && d.oc <= 64 &&
+            d.stride_h == 2 && d.dilate_h == 1 && pad_lo2 <= 64) {
             g.stem = true;
+            g.stem4 = d.ic * in_es == 8;
             g.fw_packed = 4;
         }
     }
@@ -1363,7 +1377,8 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     const uint32_t in_es = kind == KIND_S8 ? 1 : 2;
     const uint32_t out_es = out32 ? 4 : in_es;
     // TMA needs 16-byte aligned global strides
-    if ((d.ic * in_es) % 16 != 0 || (!nchw4 && (d.oc * out_es) % 16 != 0))
+    // (8-byte pixels are legal when the W-fold turns a pixel pair into one 16-byte unit: checked below)
+    if (((d.ic * in_es) % 16 != 0 && d.ic * in_es != 8) || (!nchw4 && (d.oc * out_es) % 16 != 0))
         return B200CB_UNSUPPORTED_ALIGNMENT;
     if (d.n == 0 || d.oh == 0 || d.ow == 0 || d.fh == 0 || d.fw == 0)
         return B200CB_UNSUPPORTED_SHAPE;
@@ -1398,6 +1413,8 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     // NCHW4 runs the generic modes only (no W-fold / stem / rows: their filter packing and output
     // paths are NHWC-specific); its z is read in place by the epilogue, not through the TMA ring
     const Geometry g = make_geometry(dd, in_es, !nchw4);
+    if ((g.ic * in_es) % 16 != 0)
+        return B200CB_UNSUPPORTED_ALIGNMENT;
     if (g.folded && (g.pad_w_hi - (int32_t)(g.fw - 1) < -128 || g.pad_w_lo > 127))
         return B200CB_UNSUPPORTED_PARAM;
     const bool stem = g.stem && block_n == 64;
@@ -1427,10 +1444,11 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         while (!pair && cluster > 1 && (m_tiles < 2 * cluster || (block_n / cluster) % 8 != 0))
             cluster /= 2;
     }
-    const uint32_t stage_b = stem   ? 2 * d.fh * STEM_NJ * 16
+    const uint32_t stem_rb = g.stem4 ? 64u : 128u;
+    const uint32_t stage_b = stem   ? (g.stem4 ? 1 : 2) * d.fh * STEM_NJ * 16
                              : rows ? rg.a_stage
                                     : (IGEMM_BLOCK_M + (pair ? block_n / 2 : block_n)) * kb_bytes;
-    const uint32_t fixed = fixed0 + (stem ? d.fh * block_n * 128 : rows ? rg.bres : 0);
+    const uint32_t fixed = fixed0 + (stem ? d.fh * block_n * stem_rb : rows ? rg.bres : 0);
     uint32_t stages = (MAX_DYN_SMEM - fixed) / stage_b;
     if (rows && stages > 3)
         stages = 3;
@@ -1583,14 +1601,16 @@ int igemm_launch(
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     } else if (stem) {
         // even / odd input pixels as two (C, W/2, H, N) tensors whose W stride is one pixel pair
-        uint64_t dims[4] = {d.ic, d.iw / 2, d.ih, d.n};
+        // (stem4: one tensor whose innermost 16 bytes are the pixel pair itself)
+        const uint32_t unit = g.stem4 ? 2 * d.ic : d.ic;
+        uint64_t dims[4] = {unit, d.iw / 2, d.ih, d.n};
         uint64_t strides[3] = {
                 2ull * d.ic * in_es, (uint64_t)d.iw * d.ic * in_es, src_bstride * in_es};
-        uint32_t box[4] = {d.ic, STEM_NJ, d.fh, 1};
+        uint32_t box[4] = {unit, STEM_NJ, d.fh, 1};
         cr = encode_tiled(
                 &p.tmA, in_dt, 4, src, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
-        if (cr == CUDA_SUCCESS)
+        if (cr == CUDA_SUCCESS && !g.stem4)
             cr = encode_tiled(
                     &p.tmA2, in_dt, 4, static_cast<const uint8_t*>(src) + d.ic * in_es, dims, strides,
                     box, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
@@ -1623,7 +1643,8 @@ int igemm_launch(
     {
         // packed stem filter: (4 tap pairs x 2*IC = 128 bytes, FH, OC), one 128-byte K row per filter row
         uint64_t dims_stem[3] = {(uint64_t)g.fw_packed * g.ic, d.fh, d.oc};
-        uint64_t strides_stem[2] = {128, (uint64_t)d.fh * 128};
+        const uint64_t rb = (uint64_t)g.fw_packed * g.ic * in_es;  // 128, or 64 for stem4
+        uint64_t strides_stem[2] = {rb, (uint64_t)d.fh * rb};
         uint32_t box_stem[3] = {g.fw_packed * g.ic, 1, BN};
         uint64_t dims[3] = {g.ic, (uint64_t)d.fh * g.fw, d.oc};
         uint64_t strides[2] = {(uint64_t)g.ic * in_es, (uint64_t)d.fh * g.fw * g.ic * in_es};
@@ -1631,7 +1652,8 @@ int igemm_launch(
         uint32_t box[3] = {kb_elems, 1, BN / C};  // clusters: each CTA loads (and multicasts) BN / C rows
         cr = stem ? encode_tiled(
                             &p.tmB, in_dt, 3, flt, dims_stem, strides_stem, box_stem, nullptr,
-                            CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B)
+                            rb == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B)
                   : encode_tiled(
                 &p.tmB, in_dt, 3, flt, dims, strides, box, nullptr, in_swz,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
@@ -1688,6 +1710,7 @@ int igemm_launch(
     p.stem_fh = d.fh;
     p.stem_fw2 = g.fw;
     p.stem_pad_lo2 = g.pad_w_lo;
+    p.stem4 = (stem && g.stem4) ? 1 : 0;
     if (stem)
         p.m_tiles = d.n * d.oh * p.nseg;
     if (rows) {

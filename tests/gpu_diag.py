@@ -62,6 +62,13 @@ def stage_cases(stage):
                 ("stem_c3_bf16_wide_ow150", md("bf16", 1, 8, 20, 300, 64, 3, stride=2, pad=1, nonline=1), {}),
                 ("stem_c3_bf16_oc32_z", md("bf16", 2, 8, 18, 18, 32, 3, stride=2, pad=1, nonline=1, has_z=True), {}),
                 ("stem_c7_f16_ic8_hswish", md("f16", 1, 8, 34, 34, 64, 7, stride=2, pad=3, nonline=3), {}),
+                # stem4: 8-byte pixels (bf16 / fp16 IC = 4, int8 IC = 8), a pixel pair per 16-byte unit
+                ("stem4_c7_bf16_ic4", md("bf16", 2, 4, 30, 30, 64, 7, stride=2, pad=3, nonline=1), {}),
+                ("stem4_c7_bf16_ic4_wide_z", md("bf16", 1, 4, 12, 300, 64, 7, stride=2, pad=3, nonline=1, has_z=True), {}),
+                ("stem4_c3_f16_ic4_p1_oc32", md("f16", 2, 4, 18, 18, 32, 3, stride=2, pad=1, nonline=1), {}),
+                ("stem4_c5_bf16_ic4_p2", md("bf16", 2, 4, 20, 20, 64, 5, stride=2, pad=2), {}),
+                ("stem4_c3_bf16_ic4_p0", md("bf16", 3, 4, 18, 22, 64, 3, stride=2, pad=0, nonline=3), {}),
+                ("fold4_c7_bf16_ic4_oc128", md("bf16", 2, 4, 30, 30, 128, 7, stride=2, pad=3, nonline=1), {}),
                 # rows mode (resident input rows + resident filter)
                 ("rows_c3_bf16_56", md("bf16", 2, 64, 56, 56, 64, 3, pad=1, nonline=1), {}),
                 ("rows_c3_bf16_7x7_n3", md("bf16", 3, 64, 7, 7, 64, 3, pad=1, nonline=1), {}),
@@ -82,6 +89,9 @@ def stage_cases(stage):
                 ("q_pw_qs32", md("qs8", 2, 64, 14, 14, 64, 1, dst_kind="qs32"), {}),
                 ("q_c3_stress", md("qs8", 2, 256, 14, 14, 256, 3, pad=1, nonline=1, has_z=True,
                                    scales=(0.013, 0.021, None, 0.05, 0.9)), {"int_range": 127, "bias_range": 5000}),
+                ("q_stem4_c7_ic8", md("qs8", 2, 8, 30, 30, 64, 7, stride=2, pad=3, nonline=1, scales=sc),
+                 {"int_range": 127}),
+                ("q_stem4_c3_ic8_z", md("qs8", 2, 8, 18, 18, 64, 3, stride=2, pad=1, nonline=1, has_z=True, scales=sc), {}),
                 ("q_fold_c7_ic16", md("qs8", 2, 16, 30, 30, 64, 7, stride=2, pad=3, nonline=1, scales=sc),
                  {"int_range": 127}),
                 ("q_c3_ic32_sw32", md("qs8", 2, 32, 14, 14, 64, 3, pad=1, nonline=1, has_z=True, scales=sc), {}),
