@@ -251,6 +251,9 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     using T = Traits<KIND, OUT32>;
     constexpr uint32_t TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
     constexpr uint32_t NUM_CHUNKS = BN / T::EPI_N;
+    // BN == 64: a tile is ONE epilogue chunk -- instead of idling the second epilogue group, whole tiles
+    // alternate between the groups (group g drains accumulator buffer g)
+    constexpr bool TILE_SPLIT = NUM_CHUNKS == 1 && T::GROUPS == 2;
     constexpr uint32_t IDESC =
             (KIND == KIND_S8) ? umma_idesc(2, 1, 128, BN)
                               : umma_idesc(1, KIND == KIND_BF16 ? 1 : 0, 128, BN);
@@ -321,8 +324,9 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         }
         for (uint32_t i = 0; i < 2; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
-            // one arrive per epilogue warp (pair: of both CTAs, on the leader's barrier)
-            mbar_init(bar_tempty + 8 * i, (pair ? 2 : 1) * 4 * T::GROUPS);
+            // one arrive per epilogue warp that reads the accumulator (pair: of both CTAs, on the leader's
+            // barrier); single-chunk tiles alternate between the two groups, so only one group arrives
+            mbar_init(bar_tempty + 8 * i, (pair ? 2 : 1) * 4 * (TILE_SPLIT ? 1 : T::GROUPS));
         }
         for (uint32_t i = 0; i < NZ; ++i) {
             mbar_init(bar_zfull + 8 * i, 1);
@@ -690,9 +694,18 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
         const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
         const bool fast8 = KIND == KIND_S8 && !generic_act && p.rq.fast_div == 2;
-        uint32_t acc = 0, acc_phase = 0, cnt = 0, db = 0;
+        uint32_t acc = 0, acc_phase = 0, cnt = 0, db = 0, cur_nblk = 0xffffffffu;
         for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
             const uint32_t m_blk = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
+            if (TILE_SPLIT && acc != group) {
+                // the other group's tile (it has one z chunk unless it is a phantom tile)
+                if (m_blk < p.m_tiles)
+                    ++cnt;
+                acc ^= 1;
+                if (acc == 0)
+                    acc_phase ^= 1;
+                continue;
+            }
             if (m_blk >= p.m_tiles) {
                 // phantom tile: consume the accumulator and hand it straight back
                 TIMED_WAIT(3, bar_tfull + 8 * acc, acc_phase);
@@ -708,8 +721,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             }
             const int32_t m0 = static_cast<int32_t>(m_blk * IGEMM_BLOCK_M);
             const uint32_t n0 = n_blk * BN;
-            // bias slice of this tile -> the warp's private smem (fp32 for float kinds, int32 for int8)
+            // bias slice of this tile -> the warp's private smem (fp32 for float kinds, int32 for int8);
+            // only when the N tile changes (never again for single-N-tile layers)
             __syncwarp();
+            if (n_blk != cur_nblk)
             for (uint32_t i = lane; i < BN; i += 32) {
                 uint32_t v = 0;
                 if (p.has_bias && n0 + i < p.OC) {
@@ -726,6 +741,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 }
                 sbias[i] = v;
             }
+            cur_nblk = n_blk;
             __syncwarp();
             uint32_t nchunks = 0;
 #pragma unroll
@@ -734,7 +750,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     nchunks = c + 1;
             // last chunk this warp's group owns (decides when TMEM can be handed back)
             int32_t last_c = -1;
-            for (uint32_t c = group; c < nchunks; c += T::GROUPS)
+            for (uint32_t c = TILE_SPLIT ? 0 : group; c < nchunks; c += TILE_SPLIT ? 1 : T::GROUPS)
                 last_c = static_cast<int32_t>(c);
             TIMED_WAIT(3, bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
@@ -746,7 +762,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             }
 #pragma unroll 1
             for (uint32_t c = 0; c < nchunks; ++c, ++cnt) {
-                if (T::GROUPS > 1 && (c % T::GROUPS) != group)
+                if (!TILE_SPLIT && T::GROUPS > 1 && (c % T::GROUPS) != group)
                     continue;
                 const uint32_t col0 = n0 + c * T::EPI_N;
                 const uint32_t zb = cnt % NZ, zphase = (cnt / NZ) & 1;
