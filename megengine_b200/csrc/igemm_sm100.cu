@@ -133,8 +133,10 @@ struct Traits {
     static constexpr int THREADS = 128 + 128 * GROUPS;
     static constexpr int SLAB_BYTES = 32 * ROW_BYTES;   // one warp's staging slab (32 rows)
     // slabs per warp: double buffered where 32 KiB allow it (int8), single for 8 warps x 4 KiB
-    static constexpr int NSLAB = (4 * GROUPS * 2 * SLAB_BYTES <= 32768) ? 2 : 1;
-    static_assert(4 * GROUPS * NSLAB * SLAB_BYTES == 32768, "slab area is 32 KiB");
+    // double buffered where 32 KiB allow it (int8, int32), and for BN == 64 tiles, whose short epilogue
+    // would otherwise wait for the previous TMA store to drain its only slab (64 KiB there)
+    __host__ __device__ static constexpr int nslab(int bn) { return (bn == 64 || 4 * GROUPS * 2 * SLAB_BYTES <= 32768) ? 2 : 1; }
+    __host__ __device__ static constexpr int slabs_bytes(int bn) { return 4 * GROUPS * nslab(bn) * SLAB_BYTES; }
     static constexpr int ZBUF_BYTES = 128 * ROW_BYTES;  // one z chunk
 };
 
@@ -149,7 +151,10 @@ constexpr uint32_t OFF_TMEM = 352;
 constexpr uint32_t OFF_BRES = 360;     // stem: resident filter barrier
 constexpr uint32_t NZ = 4;             // z ring depth (2 epilogue groups busy + 2 chunks in flight)
 constexpr uint32_t OFF_BIAS = 1024;    // (4 * GROUPS) warps x BN x 4 bytes, rounded up to 1 KiB
-constexpr uint32_t SLABS_BYTES = 32768;  // (4 * GROUPS) warps x 2 slabs x SLAB_BYTES == 32 KiB always
+// host mirror of Traits::slabs_bytes
+__host__ __device__ constexpr uint32_t slabs_bytes(uint32_t groups, uint32_t bn, uint32_t row_bytes) {
+    return 4 * groups * ((bn == 64 || 4 * groups * 2 * 32 * row_bytes <= 32768) ? 2u : 1u) * 32 * row_bytes;
+}
 __host__ __device__ constexpr uint32_t off_sd(uint32_t groups, uint32_t bn) {
     return OFF_BIAS + ((4 * groups * bn * 4 + 1023u) & ~1023u);
 }
@@ -288,7 +293,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     const uint32_t stage_bytes = (stem || rows) ? a_bytes : a_bytes + b_rows * p.kb_bytes;
     const uint32_t bres_bytes = stem ? p.stem_fh * BN * stem_rb : rows ? p.num_taps * p.num_kc * BN * 128u : 0u;
     const uint32_t sZ = smem_base + OFF_SZ;
-    const uint32_t sBres = sZ + (p.has_z ? NZ * T::ZBUF_BYTES : SLABS_BYTES);  // resident filter
+    constexpr uint32_t NSLAB = T::nslab(BN);
+    const uint32_t sBres = sZ + (p.has_z ? NZ * T::ZBUF_BYTES : T::slabs_bytes(BN));  // resident filter
     const uint32_t sStage = sBres + bres_bytes;
     const uint32_t bar_bres = smem_base + OFF_BRES;
 
@@ -679,8 +685,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         const uint32_t group = e >> 2;
         const uint32_t row = quad * 32 + lane;            // row of the tile == TMEM lane
         uint32_t* sbias = reinterpret_cast<uint32_t*>(smem_gen + OFF_BIAS) + e * BN;
-        const uint32_t slab_u32 = smem_base + OFF_SD + e * T::NSLAB * T::SLAB_BYTES;
-        uint8_t* slab_gen = smem_gen + OFF_SD + e * T::NSLAB * T::SLAB_BYTES;
+        const uint32_t slab_u32 = smem_base + OFF_SD + e * NSLAB * T::SLAB_BYTES;
+        uint8_t* slab_gen = smem_gen + OFF_SD + e * NSLAB * T::SLAB_BYTES;
         const uint8_t* sZ_gen = smem_gen + OFF_SZ;
         // RELU: x <= 0 ? 0 : x;  IDENTITY: the same select against -inf (a no-op) -- branch-free
         // TMEM hand-back: to the MMA warp of this CTA, or (pair) of the leader CTA
@@ -772,7 +778,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 #endif
                 if (!p.has_z) {
                     if (lane == 0)
-                        tma_store_wait_read<T::NSLAB - 1>();
+                        tma_store_wait_read<NSLAB - 1>();
                     __syncwarp();
                 }
 #ifdef B200CB_DEBUG_TIMING
@@ -970,7 +976,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                     dst_img + (static_cast<size_t>(oh * p.OW + owp) * p.OC + col) * T::OUT_ES) = v;
                     }
                     __syncwarp();
-                    db ^= (T::NSLAB - 1);
+                    db ^= (NSLAB - 1);
                     continue;
                 }
                 fence_proxy_async_smem();
@@ -992,7 +998,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         mbar_arrive(bar_zempty + 8 * zb);
                     }
                 }
-                db ^= (T::NSLAB - 1);
+                db ^= (NSLAB - 1);
             }
             acc ^= 1;
             if (acc == 0)
@@ -1270,7 +1276,7 @@ uint32_t pick_kb_bytes(uint32_t ic_bytes) {
 }
 
 uint32_t fixed_smem(uint32_t groups, uint32_t bn, bool has_z, uint32_t row_bytes) {
-    return off_sd(groups, bn) + (has_z ? NZ * 128 * row_bytes : SLABS_BYTES);
+    return off_sd(groups, bn) + (has_z ? NZ * 128 * row_bytes : slabs_bytes(groups, bn, row_bytes));
 }
 
 }  // namespace
