@@ -68,6 +68,7 @@ struct IgemmParams {
     uint32_t flip;     // mode == CONVOLUTION
     uint32_t has_bias, has_z, nonline;  // has_z: z arrives through the TMA ring (NHWC)
     // NCHW4 destination (N, OC/4, OH, OW, 4): dst and z are accessed in place by the epilogue
+    uint32_t nz;  // z ring depth
     uint32_t nchw4, z_direct;
     const void* z;
     RequantParams rq;
@@ -145,11 +146,14 @@ constexpr uint32_t OFF_FULL = 0;       // [16] x 8
 constexpr uint32_t OFF_EMPTY = 128;    // [16] x 8
 constexpr uint32_t OFF_TFULL = 256;    // [2]
 constexpr uint32_t OFF_TEMPTY = 272;   // [2]
-constexpr uint32_t OFF_ZFULL = 288;    // [4]
-constexpr uint32_t OFF_ZEMPTY = 320;   // [4]
-constexpr uint32_t OFF_TMEM = 352;
-constexpr uint32_t OFF_BRES = 360;     // stem: resident filter barrier
-constexpr uint32_t NZ = 4;             // z ring depth (2 epilogue groups busy + 2 chunks in flight)
+constexpr uint32_t OFF_ZFULL = 288;    // [8]
+constexpr uint32_t OFF_ZEMPTY = 352;   // [8]
+constexpr uint32_t OFF_TMEM = 416;
+constexpr uint32_t OFF_BRES = 424;     // stem: resident filter barrier
+// z ring depth: 4 (2 epilogue groups busy + 2 chunks in flight) up to 8 -- short-k layers are bound by
+// the z / dst streams, so their spare shared memory holds z chunks (a tile or more ahead) rather than
+// more A/B stages
+constexpr uint32_t NZ_MIN = 4, NZ_MAX = 8;
 constexpr uint32_t OFF_BIAS = 1024;    // (4 * GROUPS) warps x BN x 4 bytes, rounded up to 1 KiB
 // host mirror of Traits::slabs_bytes
 __host__ __device__ constexpr uint32_t slabs_bytes(uint32_t groups, uint32_t bn, uint32_t row_bytes) {
@@ -294,7 +298,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     const uint32_t bres_bytes = stem ? p.stem_fh * BN * stem_rb : rows ? p.num_taps * p.num_kc * BN * 128u : 0u;
     const uint32_t sZ = smem_base + OFF_SZ;
     constexpr uint32_t NSLAB = T::nslab(BN);
-    const uint32_t sBres = sZ + (p.has_z ? NZ * T::ZBUF_BYTES : T::slabs_bytes(BN));  // resident filter
+    const uint32_t nz = p.nz;
+    const uint32_t sBres = sZ + (p.has_z ? nz * T::ZBUF_BYTES : T::slabs_bytes(BN));  // resident filter
     const uint32_t sStage = sBres + bres_bytes;
     const uint32_t bar_bres = smem_base + OFF_BRES;
 
@@ -334,7 +339,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             // barrier); single-chunk tiles alternate between the two groups, so only one group arrives
             mbar_init(bar_tempty + 8 * i, (pair ? 2 : 1) * 4 * (TILE_SPLIT ? 1 : T::GROUPS));
         }
-        for (uint32_t i = 0; i < NZ; ++i) {
+        for (uint32_t i = 0; i < nz; ++i) {
             mbar_init(bar_zfull + 8 * i, 1);
             mbar_init(bar_zempty + 8 * i, 4);               // the 4 warps of the consuming group
         }
@@ -646,7 +651,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     } else if (warp == 2) {
         // ============================ z prefetch (TMA) ============================
         if (p.has_z) {
-            uint32_t cnt = 0;
+            uint32_t zb = 0, zphase = 0;
             for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
                 const uint32_t m_blk = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
                 if (m_blk >= p.m_tiles)
@@ -656,7 +661,6 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     const uint32_t col0 = n_blk * BN + c * T::EPI_N;
                     if (col0 >= p.OC)
                         break;
-                    const uint32_t zb = cnt % NZ, zphase = (cnt / NZ) & 1;
                     TIMED_WAIT(5, bar_zempty + 8 * zb, zphase ^ 1);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(bar_zfull + 8 * zb, IGEMM_BLOCK_M * T::ROW_BYTES);
@@ -672,7 +676,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                     static_cast<int32_t>(col0), m0);
                     }
                     __syncwarp();
-                    ++cnt;
+                    if (++zb == nz) {
+                        zb = 0;
+                        zphase ^= 1;
+                    }
                 }
             }
         }
@@ -700,13 +707,20 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
         const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
         const bool fast8 = KIND == KIND_S8 && !generic_act && p.rq.fast_div == 2;
-        uint32_t acc = 0, acc_phase = 0, cnt = 0, db = 0, cur_nblk = 0xffffffffu;
+        uint32_t acc = 0, acc_phase = 0, db = 0, cur_nblk = 0xffffffffu;
+        uint32_t zb = 0, zphase = 0;  // z ring position, advanced once per chunk of every valid tile
+        auto z_advance = [&]() {
+            if (++zb == nz) {
+                zb = 0;
+                zphase ^= 1;
+            }
+        };
         for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
             const uint32_t m_blk = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
             if (TILE_SPLIT && acc != group) {
                 // the other group's tile (it has one z chunk unless it is a phantom tile)
                 if (m_blk < p.m_tiles)
-                    ++cnt;
+                    z_advance();
                 acc ^= 1;
                 if (acc == 0)
                     acc_phase ^= 1;
@@ -767,11 +781,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     arrive_tempty(bar_tempty + 8 * acc);
             }
 #pragma unroll 1
-            for (uint32_t c = 0; c < nchunks; ++c, ++cnt) {
+            for (uint32_t c = 0; c < nchunks; ++c, z_advance()) {
                 if (!TILE_SPLIT && T::GROUPS > 1 && (c % T::GROUPS) != group)
                     continue;
                 const uint32_t col0 = n0 + c * T::EPI_N;
-                const uint32_t zb = cnt % NZ, zphase = (cnt / NZ) & 1;
                 // slab db must have been drained by the TMA store issued NSLAB chunks ago
 #ifdef B200CB_DEBUG_TIMING
                 const long long tsw__ = clock64();
@@ -1275,8 +1288,8 @@ uint32_t pick_kb_bytes(uint32_t ic_bytes) {
     return ic_bytes > 64 ? 128u : (ic_bytes > 32 ? 64u : 32u);
 }
 
-uint32_t fixed_smem(uint32_t groups, uint32_t bn, bool has_z, uint32_t row_bytes) {
-    return off_sd(groups, bn) + (has_z ? NZ * 128 * row_bytes : slabs_bytes(groups, bn, row_bytes));
+uint32_t fixed_smem(uint32_t groups, uint32_t bn, bool has_z, uint32_t row_bytes, uint32_t nz = NZ_MIN) {
+    return off_sd(groups, bn) + (has_z ? nz * 128 * row_bytes : slabs_bytes(groups, bn, row_bytes));
 }
 
 }  // namespace
@@ -1478,13 +1491,32 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         stages = IGEMM_MAX_STAGES;
     if (stages < 2)
         return B200CB_UNSUPPORTED_SHAPE;
+    // z ring depth: layers with a short k-loop are bound by the z / dst streams; give them z chunks
+    // (prefetched a tile or more ahead) instead of a third A/B stage
+    uint32_t nz = NZ_MIN, smem_total = fixed + stages * stage_b;
+    if (d.has_z && !nchw4 && !stem && !rows) {
+        const uint32_t zbuf = 128 * ((out32 || in_es == 2) ? 128 : 64);
+        const uint32_t num_kb = d.fh * d.fw * ((g.ic * in_es + kb_bytes - 1) / kb_bytes);
+        const uint32_t keep = num_kb >= 4 ? 3u : 2u;  // stages the main loop keeps (measured: l3.c3 wants 3)
+        if (stages > keep) {
+            const uint32_t spare = MAX_DYN_SMEM - fixed - keep * stage_b;
+            uint32_t extra = spare / zbuf;
+            if (extra > NZ_MAX - NZ_MIN)
+                extra = NZ_MAX - NZ_MIN;
+            nz = NZ_MIN + extra;
+            stages = (MAX_DYN_SMEM - fixed - extra * zbuf) / stage_b;
+            if (stages > IGEMM_MAX_STAGES)
+                stages = IGEMM_MAX_STAGES;
+            smem_total = fixed + extra * zbuf + stages * stage_b;
+        }
+    }
 
     plan->magic = PLAN_MAGIC;
     plan->kernel = KERNEL_IGEMM;
     plan->block_n = block_n;
     plan->stages = stages;
     plan->grid = 0;  // resolved at launch from the device's SM count
-    plan->smem_bytes = fixed + stages * stage_b;
+    plan->smem_bytes = smem_total;
     const bool pointwise = d.fh == 1 && d.fw == 1 && d.stride_h == 1 && d.stride_w == 1 &&
                            d.pad_h == 0 && d.pad_w == 0 && dd.src_batch_stride == 0;
     plan->a_mode = stem ? 2 : rows ? 3 : (pointwise ? 0 : 1);
@@ -1494,7 +1526,7 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     plan->reserved[1] = out32 ? 1 : 0;
     plan->reserved[3] = 0;  // 1: `filter` passed to launch is already packed (weight preprocess)
     plan->reserved[4] = g.folded ? 1 : 0;
-    plan->reserved[5] = kb_bytes;
+    plan->reserved[5] = kb_bytes | (nz << 16);
     plan->reserved[6] = cluster;
     plan->reserved[7] = pair;
     // folded stem: the re-packed filter lives in the workspace unless it was preprocessed
@@ -1751,6 +1783,7 @@ int igemm_launch(
     p.nchw4 = nchw4;
     p.z_direct = d.has_z && nchw4;
     p.z = z;
+    p.nz = (plan.reserved[5] >> 16) ? (plan.reserved[5] >> 16) : NZ_MIN;
     p.nonline = d.nonline_mode;
     p.rq = make_requant(d);
 #ifdef B200CB_DEBUG_TIMING
