@@ -188,7 +188,7 @@ def run_reference_arm(args):
 
 
 # ------------------------------------------------------------------------------ GPU arm
-def build_layers(kind, batch, device, conv1_pixel_bytes=8):
+def build_layers(kind, batch, device, conv1_pixel_bytes=8, fmt="nhwc"):
     """private tensors + plan for each of the 53 layer instances."""
     import torch
     import megengine_b200 as mb
@@ -211,6 +211,8 @@ def build_layers(kind, batch, device, conv1_pixel_bytes=8):
         opr = handle.create_operator()
         P = opr.param
         P.format, P.pad_h, P.pad_w, P.stride_h, P.stride_w = mb.Param.Format.NHWC, p, p, s, s
+        if fmt == "nchw4":
+            P.format = mb.Param.Format.NCHW4
         P.nonlineMode = mb.Param.NonlineMode.IDENTITY if name.endswith(".ds") else mb.Param.NonlineMode.RELU
         if kind == "qs8":
             sdt, fdt = mb.dtype.QuantizedS8(0.05), mb.dtype.QuantizedS8(0.02)
@@ -232,6 +234,12 @@ def build_layers(kind, batch, device, conv1_pixel_bytes=8):
             src[..., ic_real:] = 0
             flt[..., ic_real:] = 0
         dst = torch.empty((batch, oh, ow, oc), dtype=tdt, device=device)
+        if fmt == "nchw4":
+            # QuantizedS8 NCHW4 (BASELINE config 3): the same logical tensors as (N, C/4, H, W, 4)
+            to4 = lambda t: t.reshape(t.shape[0], t.shape[1], t.shape[2], t.shape[3] // 4, 4).permute(0, 3, 1, 2, 4).contiguous()
+            src, flt, dst = to4(src), to4(flt), to4(dst)
+            z = to4(z) if has_z else None
+            bias = bias.reshape(1, oc // 4, 1, 1, 4)
         S, F, B, D = mb.make_tensor(src, sdt), mb.make_tensor(flt, fdt), mb.make_tensor(bias, bdt), mb.make_tensor(dst, ddt)
         Z = mb.make_tensor(z, zdt) if has_z else mb.empty_like_dtype(zdt)
         plan = opr.get_plan(S.layout, F.layout, B.layout, Z.layout, D.layout)
@@ -294,6 +302,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--dtype", default="bf16", choices=["bf16", "f16", "qs8"])
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--format", default="nhwc", choices=["nhwc", "nchw4"], help="nchw4: QuantizedS8 only")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--conv1-pixel-bytes", type=int, default=8, choices=[8, 16],
                     help="channel padding of the 3-channel network input: 8 bytes (bf16 IC=4 / int8 IC=8) or 16")
@@ -319,7 +328,9 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device(device))
     peaks = load_peaks()
 
-    handle, layers = build_layers(args.dtype, args.batch, device, args.conv1_pixel_bytes)
+    if args.format == "nchw4" and args.dtype != "qs8":
+        raise SystemExit("bench.py: --format nchw4 is the QuantizedS8 configuration (use --dtype qs8)")
+    handle, layers = build_layers(args.dtype, args.batch, device, args.conv1_pixel_bytes, args.format)
     flops_step = sum(L["flops"] for L in layers)
     bytes_step = sum(L["bytes"] for L in layers)
     launches_step = sum(L["launches"] for L in layers)
@@ -449,8 +460,8 @@ def main():
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": {"bf16": "bf16", "f16": "f16", "qs8": "s8"}[args.dtype],
             "data": "synthetic",
-            "config": {"workload": "resnet50_v1.5_53_convbias_layers_%s_nhwc" % args.dtype,
-                       "batch_per_gpu": args.batch, "global_batch": args.batch * world, "format": "NHWC",
+            "config": {"workload": "resnet50_v1.5_53_convbias_layers_%s_%s" % (args.dtype, args.format),
+                       "batch_per_gpu": args.batch, "global_batch": args.batch * world, "format": args.format.upper(),
                        "epilogue": "bias+relu, +z on 16 layers",
                        "conv1_input": "IC 3 zero-padded to %d-byte pixels" % args.conv1_pixel_bytes, "sharding": "batch, no collective in timed path",
                        "l2": "inputs larger than L2: every layer owns private tensors, %.1f GB touched per step"

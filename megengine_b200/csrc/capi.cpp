@@ -171,12 +171,12 @@ int b200cb_launch(
 int b200cb_plan_num_launches(const b200cb_plan* plan) {
     if (!plan || plan->magic != PLAN_MAGIC)
         return 0;
+    // NCHW4: src re-tile + filter re-tile (+ stem filter re-pack) + conv
+    if (plan->kernel == KERNEL_IGEMM && plan->desc.format == B200CB_FORMAT_NCHW4)
+        return plan->reserved[4] ? 4 : 3;
     // W-folded stem without weight preprocess: filter re-pack + conv
     if (plan->kernel == KERNEL_IGEMM && plan->reserved[4] && !plan->reserved[3])
         return 2;
-    // NCHW4: src re-tile + filter re-tile + conv
-    if (plan->kernel == KERNEL_IGEMM && plan->desc.format == B200CB_FORMAT_NCHW4)
-        return 3;
     return 1;
 }
 
@@ -192,8 +192,8 @@ int b200cb_preprocess_filter(const b200cb_plan* plan, const void* filter, void* 
         return B200CB_ERR_NULL;
     if (plan->magic != PLAN_MAGIC)
         return B200CB_ERR_BAD_PLAN;
-    if (plan->kernel != KERNEL_IGEMM || !plan->reserved[4])
-        return B200CB_OK;  // nothing to pack
+    if (plan->kernel != KERNEL_IGEMM || !plan->reserved[4] || plan->desc.format == B200CB_FORMAT_NCHW4)
+        return B200CB_OK;  // nothing to pack (NCHW4 filters are re-tiled per exec)
     if (!filter || !packed)
         return B200CB_ERR_NULL;
     return igemm_pack_filter(*plan, filter, packed, static_cast<cudaStream_t>(stream));
@@ -204,7 +204,7 @@ int b200cb_plan_use_preprocessed_filter(b200cb_plan* plan) {
         return B200CB_ERR_NULL;
     if (plan->magic != PLAN_MAGIC)
         return B200CB_ERR_BAD_PLAN;
-    if (plan->kernel == KERNEL_IGEMM && plan->reserved[4]) {
+    if (plan->kernel == KERNEL_IGEMM && plan->reserved[4] && plan->desc.format != B200CB_FORMAT_NCHW4) {
         plan->reserved[3] = 1;
         plan->workspace_bytes = 0;
     }

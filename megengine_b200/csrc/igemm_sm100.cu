@@ -215,10 +215,11 @@ __device__ __forceinline__ void requant_row32(
 // channels are 8 int8x4 words that live in 8 consecutive (N, OC/4) planes `plane_words` apart, so a
 // warp's 32 pixels make every store (and z load) a coalesced 128-byte line.  `nwords` = planes that
 // exist (OC tail / rows beyond M: 0).  Same arithmetic as requant_row32; any activation.
-template <bool HAS_Z>
+// MODE: 0 = generic sequence (any activation / scale), 1 = fast IDENTITY, 2 = fast RELU
+template <bool HAS_Z, int MODE>
 __device__ __forceinline__ void requant_row32_nchw4(
         const uint32_t (&r)[32], const uint32_t* bcol, const uint32_t* zw, uint32_t* dw,
-        size_t plane_words, uint32_t nwords, uint32_t nl, bool fast, const RequantParams& rq) {
+        size_t plane_words, uint32_t nwords, uint32_t nl, const RequantParams& rq) {
     uint32_t zv[8];
 #pragma unroll
     for (uint32_t j = 0; j < 8; ++j)
@@ -232,16 +233,19 @@ __device__ __forceinline__ void requant_row32_nchw4(
 #pragma unroll
         for (uint32_t b = 0; b < 4; ++b) {
             const int32_t sfb = static_cast<int32_t>(r[j * 4 + b] + bb[b]);
-            if (fast) {
+            if constexpr (MODE != 0) {
                 float x = __fmul_rn(__int2float_rn(sfb), rq.s_bias);
                 if constexpr (HAS_Z) {
                     const float zf =
                             __uint_as_float(__byte_perm(zx, 0x4B000000u, 0x7540u | b)) - 8388736.f;
                     x = __fadd_rn(x, __fmul_rn(zf, rq.s_z));
                 }
-                if (nl == B200CB_NL_RELU)
+                if constexpr (MODE == 2) {
                     x = fmaxf(x, 0.f);
-                ub[b] = round_sat_s8_signed(div_by_scale_noguard(x, rq));
+                    ub[b] = round_sat_s8_nonneg(div_by_scale_noguard(x, rq));
+                } else {
+                    ub[b] = round_sat_s8_signed(div_by_scale_noguard(x, rq));
+                }
             } else {
                 const int32_t zq = static_cast<int32_t>(static_cast<int8_t>((zv[j] >> (8 * b)) & 0xff));
                 ub[b] = static_cast<uint32_t>(requant_s8(sfb, HAS_Z ? zq : 0, nl, rq));
@@ -836,19 +840,40 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         }
                     } else if constexpr (KIND == KIND_S8) {
                       if (p.nchw4) {
-                        const uint32_t m = static_cast<uint32_t>(m0) + row;
-                        const uint32_t img = m / p.OHW, pix = m - img * p.OHW;
+                        // this thread's output pixel (stem tiles are 128-pixel segments of one output row)
+                        uint32_t img, pix;
+                        bool px_ok;
+                        if (stem) {
+                            const uint32_t row3 = m_blk / p.nseg, ow = (m_blk % p.nseg) * IGEMM_BLOCK_M + row;
+                            img = row3 / p.OH;
+                            pix = (row3 % p.OH) * p.OW + ow;
+                            px_ok = ow < p.OW;
+                        } else {
+                            const uint32_t m = static_cast<uint32_t>(m0) + row;
+                            img = m / p.OHW;
+                            pix = m - img * p.OHW;
+                            px_ok = m < p.M;
+                        }
                         const uint32_t col = col0 + h * 32;
                         uint32_t nwords = 0;
-                        if (m < p.M && col < p.OC)
+                        if (px_ok && col < p.OC)
                             nwords = (p.OC - col) / 4 < 8 ? (p.OC - col) / 4 : 8;
                         const size_t w0 = (static_cast<size_t>(img) * (p.OC / 4) + col / 4) * p.OHW + pix;
                         uint32_t* dw = static_cast<uint32_t*>(p.dst) + w0;
                         const uint32_t* zw = static_cast<const uint32_t*>(p.z) + w0;
-                        if (p.z_direct)
-                            requant_row32_nchw4<true>(r, bcol, zw, dw, p.OHW, nwords, p.nonline, fast8, p.rq);
-                        else
-                            requant_row32_nchw4<false>(r, bcol, zw, dw, p.OHW, nwords, p.nonline, fast8, p.rq);
+                        const uint32_t mode = !fast8 ? 0u : (p.nonline == B200CB_NL_RELU ? 2u : 1u);
+#define B200CB_NCHW4_CASE(Z_, M_)                                                                          \
+    requant_row32_nchw4<Z_, M_>(r, bcol, zw, dw, p.OHW, nwords, p.nonline, p.rq)
+                        if (p.z_direct) {
+                            if (mode == 2) B200CB_NCHW4_CASE(true, 2);
+                            else if (mode == 1) B200CB_NCHW4_CASE(true, 1);
+                            else B200CB_NCHW4_CASE(true, 0);
+                        } else {
+                            if (mode == 2) B200CB_NCHW4_CASE(false, 2);
+                            else if (mode == 1) B200CB_NCHW4_CASE(false, 1);
+                            else B200CB_NCHW4_CASE(false, 0);
+                        }
+#undef B200CB_NCHW4_CASE
                       } else if (fast8) {
                         if (p.has_z) {
                             if (p.nonline == B200CB_NL_RELU)
@@ -1191,11 +1216,14 @@ constexpr uint32_t STEM_NJ = 136;  // 128 output pixels + up to 4 tap pairs - 1,
 
 // The NCHW4 cells run on an NHWC / KRSC copy of src / filter in the workspace (relayout.cu), with the
 // channels zero-padded to a TMA-legal multiple of 16: this is the descriptor of that equivalent conv.
+// Network stems (IC <= 8, stride 2, even width) pad to 8-byte pixels instead and take the stem path.
 b200cb_desc nchw4_equivalent(const b200cb_desc& d) {
     b200cb_desc e = d;
     e.format = B200CB_FORMAT_NHWC;
-    e.ic = (d.ic + 15) / 16 * 16;
     e.src_batch_stride = 0;
+    const bool stem_like = d.ic <= 8 && d.stride_w == 2 && d.stride_h == 2 && d.dilate_w == 1 &&
+                           d.dilate_h == 1 && d.iw % 2 == 0 && d.mode == B200CB_MODE_CROSS_CORRELATION;
+    e.ic = stem_like ? 8 : (d.ic + 15) / 16 * 16;
     return e;
 }
 size_t align256(size_t v) {
@@ -1447,7 +1475,7 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         dd.src_batch_stride = 0;
     // NCHW4 runs the generic modes only (no W-fold / stem / rows: their filter packing and output
     // paths are NHWC-specific); its z is read in place by the epilogue, not through the TMA ring
-    const Geometry g = make_geometry(dd, in_es, !nchw4);
+    const Geometry g = make_geometry(dd, in_es, !nchw4 || dd.ic == 8);
     if ((g.ic * in_es) % 16 != 0)
         return B200CB_UNSUPPORTED_ALIGNMENT;
     if (g.folded && (g.pad_w_hi - (int32_t)(g.fw - 1) < -128 || g.pad_w_lo > 127))
@@ -1533,15 +1561,16 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     const uint32_t fwp = stem ? g.fw_packed : g.fw;
     plan->workspace_bytes =
             g.folded ? (((uint64_t)d.oc * d.fh * fwp * g.ic * in_es + 255) & ~255ull) : 0;
-    if (nchw4)  // NHWC copy of src + KRSC copy of the filter, channels padded to d.ic
+    if (nchw4)  // NHWC copy of src + KRSC copy of the filter (channels padded to d.ic) [+ packed stem filter]
         plan->workspace_bytes = align256((size_t)d.n * d.ih * d.iw * d.ic) +
-                                align256((size_t)d.oc * d.fh * d.fw * d.ic);
+                                align256((size_t)d.oc * d.fh * d.fw * d.ic) + plan->workspace_bytes;
     plan->desc = d0;
     return B200CB_OK;
 }
 
 size_t igemm_packed_filter_bytes(const b200cb_plan& plan) {
-    if (!plan.reserved[4])
+    // (NCHW4 filters are re-tiled and packed on every exec: no weight-preprocess form)
+    if (!plan.reserved[4] || plan.desc.format == B200CB_FORMAT_NCHW4)
         return 0;
     const b200cb_desc& d = plan.desc;
     const uint32_t in_es = plan.reserved[0] == KIND_S8 ? 1 : 2;
@@ -1553,7 +1582,9 @@ size_t igemm_packed_filter_bytes(const b200cb_plan& plan) {
 int igemm_pack_filter(const b200cb_plan& plan, const void* filter, void* packed, cudaStream_t stream) {
     if (!plan.reserved[4])
         return B200CB_OK;
-    const b200cb_desc& d = plan.desc;
+    // `filter` is KRSC (for NCHW4 plans: the re-tiled workspace copy)
+    const b200cb_desc d =
+            plan.desc.format == B200CB_FORMAT_NCHW4 ? nchw4_equivalent(plan.desc) : plan.desc;
     const uint32_t in_es = plan.reserved[0] == KIND_S8 ? 1 : 2;
     const Geometry g = make_geometry(d, in_es);
     const uint32_t fwp = plan.a_mode == 2 ? g.fw_packed : g.fw;
@@ -1615,7 +1646,7 @@ int igemm_launch(
     const uint64_t src_img = (uint64_t)d.ih * d.iw * d.ic;
     if (d.src_batch_stride == src_img)
         dd.src_batch_stride = 0;
-    const Geometry g = make_geometry(dd, in_es, !nchw4);
+    const Geometry g = make_geometry(dd, in_es, !nchw4 || dd.ic == 8);
     const uint32_t kb_bytes = pick_kb_bytes(g.ic * in_es);
     const uint32_t kb_elems = kb_bytes / in_es;
     const CUtensorMapSwizzle in_swz = kb_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -1625,10 +1656,15 @@ int igemm_launch(
     if (g.folded && !plan.reserved[3]) {
         if (!workspace)
             return B200CB_ERR_WORKSPACE;
-        int rc = igemm_pack_filter(plan, filter, workspace, stream);
+        // packed stem filter: the workspace, after the NCHW4 copies if any
+        void* ws_pack = workspace;
+        if (nchw4)
+            ws_pack = static_cast<uint8_t*>(workspace) + align256((size_t)d.n * d.ih * d.iw * d.ic) +
+                      align256((size_t)d.oc * d.fh * d.fw * d.ic);
+        int rc = igemm_pack_filter(plan, filter, ws_pack, stream);
         if (rc != B200CB_OK)
             return rc;
-        flt = workspace;
+        flt = ws_pack;
     }
 
     IgemmParams p;

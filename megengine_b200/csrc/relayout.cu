@@ -37,6 +37,27 @@ __global__ void __launch_bounds__(256) transpose_words_kernel(
     }
 }
 
+// Few channel groups (network stems: C4pad <= 8): one thread per pixel gathers its words from the C4
+// planes (each plane read is coalesced across the warp) and writes them as one contiguous run.
+template <int C4PAD>
+__global__ void __launch_bounds__(256) gather_words_kernel(
+        const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t C4, uint32_t P,
+        uint64_t in_batch_words) {
+    const uint32_t b = blockIdx.y;
+    const uint32_t p = blockIdx.x * 256 + threadIdx.x;
+    if (p >= P)
+        return;
+    const uint32_t* src = in + static_cast<size_t>(b) * in_batch_words + p;
+    uint32_t w[C4PAD];
+#pragma unroll
+    for (int c = 0; c < C4PAD; ++c)
+        w[c] = c < (int)C4 ? __ldg(src + static_cast<size_t>(c) * P) : 0u;
+    uint32_t* dst = out + (static_cast<size_t>(b) * P + p) * C4PAD;
+#pragma unroll
+    for (int c = 0; c < C4PAD; ++c)
+        dst[c] = w[c];
+}
+
 }  // namespace
 
 // (B, C/4, P, 4) int8 -> (B, P, Cpad) int8; `in_batch_elems` = elements between consecutive b (0 = dense)
@@ -47,6 +68,21 @@ int relayout_c4_to_channels_last(
         return B200CB_UNSUPPORTED_SHAPE;
     const uint32_t C4 = C / 4, C4pad = Cpad / 4;
     const uint64_t bw = in_batch_elems ? in_batch_elems / 4 : static_cast<uint64_t>(C4) * P;
+    if ((C4pad == 2 || C4pad == 4) && B <= 65535) {
+        dim3 g((P + 255) / 256, B, 1);
+        if (C4pad == 2)
+            gather_words_kernel<2><<<g, 256, 0, stream>>>(
+                    static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), C4, P, bw);
+        else
+            gather_words_kernel<4><<<g, 256, 0, stream>>>(
+                    static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), C4, P, bw);
+        cudaError_t e = cudaGetLastError();
+        if (e != cudaSuccess) {
+            set_last_error("relayout launch", cudaGetErrorString(e));
+            return B200CB_ERR_CUDA;
+        }
+        return B200CB_OK;
+    }
     dim3 grid((P + 31) / 32, (C4pad + 31) / 32, B);
     if (grid.z > 65535 || grid.y > 65535)
         return B200CB_UNSUPPORTED_SHAPE;

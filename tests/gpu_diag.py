@@ -107,6 +107,16 @@ def stage_cases(stage):
                     ("dw5s1_" + kind, K.dw_desc(kind, 2, 48, 9, 9, 1, f=5, nonline=3), {}),
                     ("dw3s1_c144_" + kind, K.dw_desc(kind, 3, 144, 7, 7, 1), {})]
         out.append(("dw7_generic_bf16", K.dw_desc("bf16", 2, 32, 12, 12, 1, f=7), {}))
+        # TMA bandwidth kernel: channel tails (64-blocks + 16 / 32 / 40-channel tail launches), wide and
+        # partial tiles, z, stride 2, odd sizes; channel counts the TMA path cannot take (C % 8 != 0)
+        out += [("dw3_tma_c144_56", K.dw_desc("bf16", 2, 144, 56, 56, 1, has_z=True), {}),
+                ("dw3_tma_c96_s2_57", K.dw_desc("bf16", 2, 96, 57, 57, 2), {}),
+                ("dw3_tma_c232_s2", K.dw_desc("f16", 2, 232, 14, 14, 2, nonline=3), {}),
+                ("dw3_tma_c24_s2", K.dw_desc("bf16", 3, 24, 30, 30, 2), {}),
+                ("dw3_tma_c16", K.dw_desc("bf16", 2, 16, 20, 20, 1, has_z=True), {}),
+                ("dw3_tma_c8_wide", K.dw_desc("f16", 1, 8, 9, 130, 1), {}),
+                ("dw3_reg_c58", K.dw_desc("bf16", 2, 58, 28, 28, 1), {}),
+                ("dw3_reg_c116_s2_z", K.dw_desc("f16", 2, 116, 28, 28, 2, has_z=True), {})]
         return out
     raise SystemExit("unknown stage " + stage)
 

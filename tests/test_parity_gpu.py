@@ -90,6 +90,9 @@ NCHW4_CASES = [
     ("3x3_z", 3, 32, 9, 11, 64, 3, 1, 1, C.NL_RELU, True),
     ("5x5_s2", 2, 16, 17, 17, 32, 5, 2, 2, C.NL_IDENTITY, False),
     ("7x7_ic4_stem", 2, 4, 30, 30, 64, 7, 2, 3, C.NL_RELU, False),
+    ("7x7_ic8_stem_wide_z", 1, 8, 12, 300, 64, 7, 2, 3, C.NL_RELU, True),
+    ("3x3_ic4_stem_oc32_identity", 3, 4, 18, 22, 32, 3, 2, 1, C.NL_IDENTITY, False),
+    ("7x7_ic8_s2_oc128_folded", 2, 8, 30, 30, 128, 7, 2, 3, C.NL_H_SWISH, False),
     ("oc_tail_36_z_hswish", 2, 24, 8, 8, 36, 3, 1, 1, C.NL_H_SWISH, True),
     ("identity_z", 1, 128, 7, 7, 256, 1, 1, 0, C.NL_IDENTITY, True),
     ("resnet_l3_c2_pairable", 2, 256, 14, 14, 256, 3, 1, 1, C.NL_RELU, False),
