@@ -107,6 +107,83 @@ __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint3
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
 }
 
+// ---- packed fp32x2 forms (sm_100 FMUL2 / FFMA2 / FADD2 with explicit rounding): two elements per
+// instruction on the FMA pipe, each lane rounded exactly as the scalar op
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t f2_pack(float lo, float hi) {
+    f32x2_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(f32x2_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2_t f2_mul(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_fma(f32x2_t a, f32x2_t b, f32x2_t c) {
+    f32x2_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_add(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_add_rz(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rz.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+__device__ __forceinline__ f32x2_t f2_add_rm(f32x2_t a, f32x2_t b) {
+    f32x2_t r;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+    return r;
+}
+// loop-invariant operands of the packed requantize
+struct RequantPacked {
+    f32x2_t s_bias, s_z, inv, neg_s, half, magic, neg_zoff;
+};
+__device__ __forceinline__ RequantPacked make_requant_packed(const RequantParams& q) {
+    RequantPacked r;
+    r.s_bias = f2_pack(q.s_bias, q.s_bias);
+    r.s_z = f2_pack(q.s_z, q.s_z);
+    r.inv = f2_pack(q.inv_dst, q.inv_dst);
+    r.neg_s = f2_pack(-q.s_dst, -q.s_dst);
+    r.half = f2_pack(0.5f, 0.5f);
+    r.magic = f2_pack(8388608.f, 8388608.f);
+    r.neg_zoff = f2_pack(-8388736.f, -8388736.f);
+    return r;
+}
+// two RELU outputs at once: (acc + bias) pairs -> the two result bytes in the low bytes of lo / hi.
+// Same operation sequence as dequant + fmaxf + div_by_scale_noguard + round_sat_s8_nonneg.
+template <bool HAS_Z>
+__device__ __forceinline__ void requant_pair_nonneg(
+        int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
+        uint32_t& hi) {
+    f32x2_t x = f2_mul(f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1)), k.s_bias);
+    if constexpr (HAS_Z) {
+        const f32x2_t zf = f2_add(f2_pack(__uint_as_float(zbits0), __uint_as_float(zbits1)), k.neg_zoff);
+        x = f2_add(x, f2_mul(zf, k.s_z));
+    }
+    float x0, x1;
+    f2_unpack(x, x0, x1);
+    x = f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
+    const f32x2_t q0 = f2_mul(x, k.inv);
+    const f32x2_t e = f2_fma(q0, k.neg_s, x);   // x - q0 * s, exact
+    const f32x2_t q1 = f2_fma(e, k.inv, q0);
+    float c0, c1;
+    f2_unpack(q1, c0, c1);
+    const f32x2_t u = f2_add_rm(f2_add_rz(f2_pack(fminf(c0, 127.f), fminf(c1, 127.f)), k.half), k.magic);
+    float u0, u1;
+    f2_unpack(u, u0, u1);
+    lo = __float_as_uint(u0);
+    hi = __float_as_uint(u1);
+}
+
 __device__ __forceinline__ int32_t requant_s8(int32_t sfb, int32_t zq, uint32_t nl, const RequantParams& q) {
     return quant_s8(act_f(dequant_acc(sfb, zq, q), nl), q);
 }

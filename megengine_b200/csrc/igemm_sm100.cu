@@ -173,6 +173,7 @@ template <bool HAS_Z, bool NONNEG>
 __device__ __forceinline__ void requant_row32(
         const uint32_t (&r)[32], const uint32_t* bcol, const uint8_t* zrow, uint8_t* drow, uint32_t h,
         uint32_t lane, const RequantParams& rq) {
+    const RequantPacked kp = make_requant_packed(rq);
 #pragma unroll
     for (uint32_t j = 0; j < 2; ++j) {
         // 64-byte rows, SWIZZLE_64B: 16-byte piece index ^= (row >> 1) & 3
@@ -189,6 +190,17 @@ __device__ __forceinline__ void requant_row32(
             const uint4 bv = *reinterpret_cast<const uint4*>(bcol + j * 16 + w * 4);
             const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
             uint32_t ub[4];
+            if constexpr (NONNEG) {
+                // RELU: two elements per instruction (FMUL2 / FFMA2 / FADD2)
+#pragma unroll
+                for (uint32_t b = 0; b < 4; b += 2) {
+                    const int32_t s0 = static_cast<int32_t>(r[j * 16 + w * 4 + b] + bb[b]);
+                    const int32_t s1 = static_cast<int32_t>(r[j * 16 + w * 4 + b + 1] + bb[b + 1]);
+                    requant_pair_nonneg<HAS_Z>(
+                            s0, s1, __byte_perm(zx[w], 0x4B000000u, 0x7540u | b),
+                            __byte_perm(zx[w], 0x4B000000u, 0x7540u | (b + 1)), kp, ub[b], ub[b + 1]);
+                }
+            } else
 #pragma unroll
             for (uint32_t b = 0; b < 4; ++b) {
                 const int32_t sfb = static_cast<int32_t>(r[j * 16 + w * 4 + b] + bb[b]);
@@ -220,6 +232,7 @@ template <bool HAS_Z, int MODE>
 __device__ __forceinline__ void requant_row32_nchw4(
         const uint32_t (&r)[32], const uint32_t* bcol, const uint32_t* zw, uint32_t* dw,
         size_t plane_words, uint32_t nwords, uint32_t nl, const RequantParams& rq) {
+    const RequantPacked kp = make_requant_packed(rq);
     uint32_t zv[8];
 #pragma unroll
     for (uint32_t j = 0; j < 8; ++j)
@@ -230,6 +243,16 @@ __device__ __forceinline__ void requant_row32_nchw4(
         const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
         const uint32_t zx = zv[j] ^ 0x80808080u;
         uint32_t ub[4];
+        if constexpr (MODE == 2) {
+#pragma unroll
+            for (uint32_t b = 0; b < 4; b += 2) {
+                const int32_t s0 = static_cast<int32_t>(r[j * 4 + b] + bb[b]);
+                const int32_t s1 = static_cast<int32_t>(r[j * 4 + b + 1] + bb[b + 1]);
+                requant_pair_nonneg<HAS_Z>(
+                        s0, s1, __byte_perm(zx, 0x4B000000u, 0x7540u | b),
+                        __byte_perm(zx, 0x4B000000u, 0x7540u | (b + 1)), kp, ub[b], ub[b + 1]);
+            }
+        } else
 #pragma unroll
         for (uint32_t b = 0; b < 4; ++b) {
             const int32_t sfb = static_cast<int32_t>(r[j * 4 + b] + bb[b]);
