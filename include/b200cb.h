@@ -157,7 +157,8 @@ int b200cb_exec_host(
 
 /* Device self-tests (synchronise `stream`). which == 0: the requantize epilogue's reciprocal-based
  * division against IEEE division over all 2^32 dividends; which == 1: the ALU-only quantize of the
- * fast int8 epilogue against roundf(IEEE division) + clamp.  *mismatches must come back 0. */
+ * fast int8 epilogue against roundf(IEEE division) + clamp; which == 2: the packed fp32x2 form of that
+ * epilogue against the scalar one over all 2^32 accumulators.  *mismatches must come back 0. */
 int b200cb_selftest(int which, void* stream, uint64_t* mismatches);
 
 const char* b200cb_strerror(int code);

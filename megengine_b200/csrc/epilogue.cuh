@@ -145,17 +145,24 @@ __device__ __forceinline__ f32x2_t f2_add_rm(f32x2_t a, f32x2_t b) {
 }
 // loop-invariant operands of the packed requantize
 struct RequantPacked {
-    f32x2_t s_bias, s_z, inv, neg_s, half, magic, neg_zoff;
+    f32x2_t s_bias, inv, neg_s, half, magic;
+    float s_bias1, s_z1;
 };
+// A product that feeds an add must stay a separately rounded product -- and ptxas (12.9) contracts
+// mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 although the explicit .rn forbids that for the scalar
+// forms; --fmad=false does not stop it, and fma(a, b, -0.0) is simplified back and fused as well
+// (b200cb_selftest(2) caught the resulting 1-in-2e7 off-by-one outputs).  So the only mul -> add
+// adjacency of the sequence, the dequantisation with z, stays on scalar mul.rn.f32 / add.rn.f32 (never
+// contracted); everything after it has no product feeding an add: FMUL2 -> {FMNMX | FMUL2 | FFMA2
+// multiplicand}, explicit FFMA2s, FADD2.RZ -> FADD2.RM.
 __device__ __forceinline__ RequantPacked make_requant_packed(const RequantParams& q) {
     RequantPacked r;
     r.s_bias = f2_pack(q.s_bias, q.s_bias);
-    r.s_z = f2_pack(q.s_z, q.s_z);
+    r.s_bias1 = q.s_bias, r.s_z1 = q.s_z;
     r.inv = f2_pack(q.inv_dst, q.inv_dst);
     r.neg_s = f2_pack(-q.s_dst, -q.s_dst);
     r.half = f2_pack(0.5f, 0.5f);
     r.magic = f2_pack(8388608.f, 8388608.f);
-    r.neg_zoff = f2_pack(-8388736.f, -8388736.f);
     return r;
 }
 // two RELU outputs at once: (acc + bias) pairs -> the two result bytes in the low bytes of lo / hi.
@@ -164,10 +171,14 @@ template <bool HAS_Z>
 __device__ __forceinline__ void requant_pair_nonneg(
         int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
         uint32_t& hi) {
-    f32x2_t x = f2_mul(f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1)), k.s_bias);
+    f32x2_t x;
     if constexpr (HAS_Z) {
-        const f32x2_t zf = f2_add(f2_pack(__uint_as_float(zbits0), __uint_as_float(zbits1)), k.neg_zoff);
-        x = f2_add(x, f2_mul(zf, k.s_z));
+        const float z0 = __fadd_rn(__uint_as_float(zbits0), -8388736.f);
+        const float z1 = __fadd_rn(__uint_as_float(zbits1), -8388736.f);
+        x = f2_pack(__fadd_rn(__fmul_rn(__int2float_rn(sfb0), k.s_bias1), __fmul_rn(z0, k.s_z1)),
+                    __fadd_rn(__fmul_rn(__int2float_rn(sfb1), k.s_bias1), __fmul_rn(z1, k.s_z1)));
+    } else {
+        x = f2_mul(f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1)), k.s_bias);
     }
     float x0, x1;
     f2_unpack(x, x0, x1);
@@ -182,6 +193,36 @@ __device__ __forceinline__ void requant_pair_nonneg(
     f2_unpack(u, u0, u1);
     lo = __float_as_uint(u0);
     hi = __float_as_uint(u1);
+}
+
+// the IDENTITY (any sign) form of the same: clamp to [-128, 127], round the magnitude, negate the byte
+template <bool HAS_Z>
+__device__ __forceinline__ void requant_pair_signed(
+        int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
+        uint32_t& hi) {
+    f32x2_t x;
+    if constexpr (HAS_Z) {
+        const float z0 = __fadd_rn(__uint_as_float(zbits0), -8388736.f);
+        const float z1 = __fadd_rn(__uint_as_float(zbits1), -8388736.f);
+        x = f2_pack(__fadd_rn(__fmul_rn(__int2float_rn(sfb0), k.s_bias1), __fmul_rn(z0, k.s_z1)),
+                    __fadd_rn(__fmul_rn(__int2float_rn(sfb1), k.s_bias1), __fmul_rn(z1, k.s_z1)));
+    } else {
+        x = f2_mul(f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1)), k.s_bias);
+    }
+    const f32x2_t q0 = f2_mul(x, k.inv);
+    const f32x2_t e = f2_fma(q0, k.neg_s, x);
+    const f32x2_t q1 = f2_fma(e, k.inv, q0);
+    float c0, c1;
+    f2_unpack(q1, c0, c1);
+    c0 = fminf(fmaxf(c0, -128.f), 127.f);
+    c1 = fminf(fmaxf(c1, -128.f), 127.f);
+    const f32x2_t u = f2_add_rm(f2_add_rz(f2_pack(fabsf(c0), fabsf(c1)), k.half), k.magic);
+    float u0, u1;
+    f2_unpack(u, u0, u1);
+    const uint32_t s0 = static_cast<uint32_t>(static_cast<int32_t>(__float_as_uint(c0)) >> 31);
+    const uint32_t s1 = static_cast<uint32_t>(static_cast<int32_t>(__float_as_uint(c1)) >> 31);
+    lo = (__float_as_uint(u0) ^ s0) - s0;
+    hi = (__float_as_uint(u1) ^ s1) - s1;
 }
 
 __device__ __forceinline__ int32_t requant_s8(int32_t sfb, int32_t zq, uint32_t nl, const RequantParams& q) {

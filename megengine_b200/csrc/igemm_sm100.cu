@@ -200,21 +200,14 @@ __device__ __forceinline__ void requant_row32(
                             s0, s1, __byte_perm(zx[w], 0x4B000000u, 0x7540u | b),
                             __byte_perm(zx[w], 0x4B000000u, 0x7540u | (b + 1)), kp, ub[b], ub[b + 1]);
                 }
-            } else
+            } else {
 #pragma unroll
-            for (uint32_t b = 0; b < 4; ++b) {
-                const int32_t sfb = static_cast<int32_t>(r[j * 16 + w * 4 + b] + bb[b]);
-                float x = __fmul_rn(__int2float_rn(sfb), rq.s_bias);
-                if constexpr (HAS_Z) {
-                    const float zf =
-                            __uint_as_float(__byte_perm(zx[w], 0x4B000000u, 0x7540u | b)) - 8388736.f;
-                    x = __fadd_rn(x, __fmul_rn(zf, rq.s_z));
-                }
-                if constexpr (NONNEG) {
-                    x = fmaxf(x, 0.f);  // RELU: x <= 0 ? 0 : x
-                    ub[b] = round_sat_s8_nonneg(div_by_scale_noguard(x, rq));
-                } else {
-                    ub[b] = round_sat_s8_signed(div_by_scale_noguard(x, rq));
+                for (uint32_t b = 0; b < 4; b += 2) {
+                    const int32_t s0 = static_cast<int32_t>(r[j * 16 + w * 4 + b] + bb[b]);
+                    const int32_t s1 = static_cast<int32_t>(r[j * 16 + w * 4 + b + 1] + bb[b + 1]);
+                    requant_pair_signed<HAS_Z>(
+                            s0, s1, __byte_perm(zx[w], 0x4B000000u, 0x7540u | b),
+                            __byte_perm(zx[w], 0x4B000000u, 0x7540u | (b + 1)), kp, ub[b], ub[b + 1]);
                 }
             }
             ow[w] = pack_low_bytes(ub[0], ub[1], ub[2], ub[3]);
@@ -243,14 +236,17 @@ __device__ __forceinline__ void requant_row32_nchw4(
         const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
         const uint32_t zx = zv[j] ^ 0x80808080u;
         uint32_t ub[4];
-        if constexpr (MODE == 2) {
+        if constexpr (MODE != 0) {
 #pragma unroll
             for (uint32_t b = 0; b < 4; b += 2) {
                 const int32_t s0 = static_cast<int32_t>(r[j * 4 + b] + bb[b]);
                 const int32_t s1 = static_cast<int32_t>(r[j * 4 + b + 1] + bb[b + 1]);
-                requant_pair_nonneg<HAS_Z>(
-                        s0, s1, __byte_perm(zx, 0x4B000000u, 0x7540u | b),
-                        __byte_perm(zx, 0x4B000000u, 0x7540u | (b + 1)), kp, ub[b], ub[b + 1]);
+                const uint32_t z0 = __byte_perm(zx, 0x4B000000u, 0x7540u | b);
+                const uint32_t z1 = __byte_perm(zx, 0x4B000000u, 0x7540u | (b + 1));
+                if constexpr (MODE == 2)
+                    requant_pair_nonneg<HAS_Z>(s0, s1, z0, z1, kp, ub[b], ub[b + 1]);
+                else
+                    requant_pair_signed<HAS_Z>(s0, s1, z0, z1, kp, ub[b], ub[b + 1]);
             }
         } else
 #pragma unroll
@@ -1170,6 +1166,42 @@ __global__ void selftest_fastq_kernel(const float* scales, int nscales, unsigned
 // `grid` == 0: one CTA per SM (clusters: as many whole clusters as the device keeps co-resident, asked
 // from the occupancy API once per kernel variant / cluster size -- GPC boundaries strand a few SMs for
 // clusters of 4), capped by the number of tiles.
+// Self-test 2: the packed fp32x2 requantize (both lanes, RELU and signed forms, with z) against the
+// scalar fast sequence that self-test 1 pins to IEEE division, over all 2^32 accumulator values.
+// (This test is what caught ptxas contracting mul.rn.f32x2 + add.rn.f32x2: see the Makefile.)
+__global__ void selftest_packed_kernel(const float* scales, int nscales, unsigned long long* bad) {
+    unsigned long long local = 0;
+    for (int si = 0; si < nscales; ++si) {
+        RequantParams q;
+        q.s_bias = 0.0013f * (si + 1), q.s_z = 0.07f, q.s_dst = scales[si], q.inv_dst = 1.0f / scales[si];
+        q.fast_div = 2;
+        const RequantPacked kp = make_requant_packed(q);
+        for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+             i < (1ull << 32); i += (unsigned long long)gridDim.x * blockDim.x) {
+            const int32_t a0 = static_cast<int32_t>(static_cast<uint32_t>(i));
+            const int32_t a1 = static_cast<int32_t>(static_cast<uint32_t>(i * 2654435761ull));
+            const uint32_t zw = static_cast<uint32_t>(i * 40503ull) ^ 0x80808080u;  // int8x4 word ^ 0x80
+            const uint32_t zb0 = __byte_perm(zw, 0x4B000000u, 0x7540u), zb1 = __byte_perm(zw, 0x4B000000u, 0x7541u);
+            auto scalar = [&](int32_t sfb, uint32_t zbits, bool relu) {
+                float x = __fmul_rn(__int2float_rn(sfb), q.s_bias);
+                x = __fadd_rn(x, __fmul_rn(__fadd_rn(__uint_as_float(zbits), -8388736.f), q.s_z));
+                if (relu)
+                    return round_sat_s8_nonneg(div_by_scale_noguard(fmaxf(x, 0.f), q)) & 0xffu;
+                return round_sat_s8_signed(div_by_scale_noguard(x, q)) & 0xffu;
+            };
+            uint32_t lo, hi;
+            requant_pair_nonneg<true>(a0, a1, zb0, zb1, kp, lo, hi);
+            if ((lo & 0xffu) != scalar(a0, zb0, true) || (hi & 0xffu) != scalar(a1, zb1, true))
+                ++local;
+            requant_pair_signed<true>(a0, a1, zb0, zb1, kp, lo, hi);
+            if ((lo & 0xffu) != scalar(a0, zb0, false) || (hi & 0xffu) != scalar(a1, zb1, false))
+                ++local;
+        }
+    }
+    if (local)
+        atomicAdd(bad, local);
+}
+
 template <int KIND, int BN, int OUT32, int PAIR>
 cudaError_t launch_variant(
         const IgemmParams& p, uint32_t grid, uint64_t total_tiles, uint32_t smem, cudaStream_t stream) {
@@ -1364,7 +1396,7 @@ RequantParams make_requant(const b200cb_desc& d) {
 }
 
 int igemm_selftest(int which, cudaStream_t stream, uint64_t* mismatches) {
-    if ((which != 0 && which != 1) || !mismatches)
+    if (which < 0 || which > 2 || !mismatches)
         return B200CB_UNSUPPORTED_PARAM;
     const float h_scales[8] = {19.99f, 0.3f, 0.41f, 0.9f, 1.0f, 0.11f, 3.0e-3f, 1.7e4f};
     float* d_scales = nullptr;
@@ -1379,8 +1411,10 @@ int igemm_selftest(int which, cudaStream_t stream, uint64_t* mismatches) {
     if (e == cudaSuccess) {
         if (which == 0)
             selftest_div_kernel<<<148 * 16, 256, 0, stream>>>(d_scales, 8, d_bad);
-        else
+        else if (which == 1)
             selftest_fastq_kernel<<<148 * 16, 256, 0, stream>>>(d_scales, 8, d_bad);
+        else
+            selftest_packed_kernel<<<148 * 16, 256, 0, stream>>>(d_scales, 8, d_bad);
         e = cudaGetLastError();
     }
     unsigned long long bad = 0;

@@ -136,3 +136,30 @@ def test_product_has_no_oracle_or_cpu_fallback():
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("liboracle", "ref_driver", "_oracle", "oracle/", "oracle_convbias", "libmegdnn"):
                     assert needle not in text, (f, needle)
+
+
+def test_int8_epilogue_sass_has_no_contracted_packed_ops():
+    """Bit-exactness guard.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (see
+    megengine_b200/csrc/epilogue.cuh), so the packed requantize keeps no product that feeds an add.  In
+    every QuantizedS8 igemm kernel the machine code must then hold exactly the explicit FMAs of the
+    division (2 FFMA2 per FADD2.RM pair rounding) and no round-to-nearest FADD2 at all."""
+    import re
+    import shutil
+    import subprocess
+    lib = os.path.join(ROOT, "megengine_b200", "lib", "libb200cb.so")
+    if shutil.which("cuobjdump") is None or not os.path.exists(lib):
+        pytest.skip("cuobjdump or the built library not available")
+    sass = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True, check=True).stdout
+    funcs = re.split(r"\n\s*Function : ", sass)
+    checked = 0
+    for f in funcs[1:]:
+        name = f.split("\n", 1)[0]
+        if "igemm_kernelILi2E" not in name or "ELi1ELi" in name.split("igemm_kernelILi2E")[1][:12]:
+            continue  # QuantizedS8 -> QuantizedS8 kernels only (KIND 2, OUT32 0)
+        ffma2, rm, rz = f.count("FFMA2"), f.count("FADD2.RM"), f.count("FADD2.RZ")
+        plain = len(re.findall(r"FADD2 ", f))
+        assert rm > 0 and rm == rz, (name, rm, rz)
+        assert ffma2 == 2 * rm, (name, ffma2, rm)
+        assert plain == 0, (name, plain)
+        checked += 1
+    assert checked >= 6, checked

@@ -240,6 +240,17 @@ def test_requant_fast_quantize_selftest():
     assert rc == 0 and bad.value == 0, (rc, bad.value)
 
 
+def test_requant_packed_selftest():
+    """the packed fp32x2 requantize (FMUL2 / FFMA2 / FADD2.RZ / .RM, RELU and signed forms, with z) equals
+    the scalar fast sequence for all 2^32 accumulator values x 8 scales, both lanes."""
+    import ctypes
+    import torch
+    lib = C.load()
+    bad = ctypes.c_uint64(123)
+    rc = lib.b200cb_selftest(2, torch.cuda.current_stream().cuda_stream, ctypes.byref(bad))
+    assert rc == 0 and bad.value == 0, (rc, bad.value)
+
+
 @pytest.mark.parametrize("kind", ["bf16", "qs8"])
 def test_stem_weight_preprocess_path(kind):
     """exec_preprocess + exec(preprocessed_filter) (nn.h:400-447) == the workspace path, bit for bit."""
