@@ -28,6 +28,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <type_traits>
 #include "common.h"
 #include "ptx.cuh"
 #include "epilogue.cuh"
@@ -624,53 +625,94 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         }
     } else if (warp == 1) {
         // ============================ MMA issuer ============================
-        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-        const uint32_t mma_per_kb = p.kb_bytes / 32;
+        // ONE thread runs the whole loop.  tcgen05.mma is asynchronous, but the issuing thread must stay
+        // ahead of the tensor pipe: a 128 x 64 MMA occupies it 48 clk, a 128 x 128 one 64 clk
+        // (tools/microbench/mma_shapes.cu), so every instruction between two MMAs counts.  Hence: no
+        // per-k-block elect / warp sync, descriptors advanced by one add, the MMAs of a k-block unrolled
+        // with immediate offsets and a constant accumulate predicate, commit variants chosen outside.
         // UMMA layout type: 2 = SWIZZLE_128B, 4 = SWIZZLE_64B, 6 = SWIZZLE_32B; SBO = 8 rows
         const uint32_t layout = p.kb_bytes == 128 ? 2u : (p.kb_bytes == 64 ? 4u : 6u);
         const uint32_t ab_hi = desc_hi(8 * p.kb_bytes, layout);
         // pair: M = 256 in the instruction descriptor, only the leader CTA issues
         constexpr uint32_t IDESC_PAIR = (IDESC & ~(0x1Fu << 24)) | ((256u >> 4) << 24);
-        const uint32_t ct_end = (pair && crank != 0) ? 0 : total_ct;
-        for (uint32_t ct = cl_id; ct < ct_end; ct += cl_num) {
-            TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * BN;
-            for (uint32_t kb = 0; kb < num_kb; ++kb) {
-                TIMED_WAIT(2, bar_full + 8 * stage, phase);
+        constexpr uint32_t IDESC_USE = pair ? IDESC_PAIR : IDESC;
+        auto issue_first = [&](uint32_t taddr, uint32_t a_lo, uint32_t b_lo, uint32_t accum) {
+            if constexpr (pair)
+                mma_issue_2sm<KIND>(taddr, a_lo, ab_hi, b_lo, ab_hi, IDESC_USE, accum);
+            else
+                mma_issue<KIND>(taddr, a_lo, ab_hi, b_lo, ab_hi, IDESC_USE, accum);
+        };
+        auto issue_acc = [&](uint32_t taddr, uint32_t a_lo, uint32_t b_lo) {
+            const uint64_t adesc = (static_cast<uint64_t>(ab_hi) << 32) | a_lo;
+            const uint64_t bdesc = (static_cast<uint64_t>(ab_hi) << 32) | b_lo;
+            if constexpr (pair) {
+                if constexpr (KIND == KIND_S8)
+                    mma_i8_2sm_acc(taddr, adesc, bdesc, IDESC_USE);
+                else
+                    mma_f16_2sm_acc(taddr, adesc, bdesc, IDESC_USE);
+            } else {
+                if constexpr (KIND == KIND_S8)
+                    mma_i8_acc(taddr, adesc, bdesc, IDESC_USE);
+                else
+                    mma_f16_acc(taddr, adesc, bdesc, IDESC_USE);
+            }
+        };
+        auto run = [&](auto NM_) {
+            constexpr uint32_t NM = decltype(NM_)::value;  // MMAs (32 bytes of K each) per k-block
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            const uint32_t stage16 = stage_bytes >> 4;     // descriptor units are 16 bytes
+            const uint32_t a0 = desc_lo(sStage, 16), b0 = desc_lo(sStage + a_bytes, 16);
+            uint32_t soff = 0;
+            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+                TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
-                if (elect_one()) {
-                    const uint32_t sa = sStage + stage * stage_bytes;
-                    const uint32_t sb = sa + a_bytes;
-                    const uint32_t a_lo = desc_lo(sa, 16), b_lo = desc_lo(sb, 16);
-                    if (pair) {
-                        for (uint32_t k = 0; k < mma_per_kb; ++k)
-                            mma_issue_2sm<KIND>(
-                                    taddr, a_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC_PAIR, (kb | k) != 0);
-                        mma_commit_2sm_mc(bar_empty + 8 * stage, 3);  // frees the stage in both CTAs
+                const uint32_t taddr = tmem_base + acc * BN;
+                uint32_t accum = 0;  // the tile's first MMA overwrites the accumulator
+                for (uint32_t kb = 0; kb < num_kb; ++kb) {
+                    TIMED_WAIT(2, bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t a_lo = a0 + soff, b_lo = b0 + soff;
+                    issue_first(taddr, a_lo, b_lo, accum);
+                    accum = 1;
+#pragma unroll
+                    for (uint32_t k = 1; k < NM; ++k)
+                        issue_acc(taddr, a_lo + 2 * k, b_lo + 2 * k);
+                    const uint32_t be = bar_empty + 8 * stage;
+                    if constexpr (pair) {
+                        mma_commit_2sm_mc(be, 3);  // frees the stage in both CTAs
                         if (kb == num_kb - 1)
                             mma_commit_2sm_mc(bar_tfull + 8 * acc, 3);  // both CTAs' epilogues
                     } else {
-                        for (uint32_t k = 0; k < mma_per_kb; ++k)
-                            mma_issue<KIND>(taddr, a_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC, (kb | k) != 0);
                         if (C == 1)
-                            mma_commit(bar_empty + 8 * stage);
+                            mma_commit(be);
                         else
-                            mma_commit_mc(bar_empty + 8 * stage, cmask);  // frees the stage in every CTA
+                            mma_commit_mc(be, cmask);  // frees the stage in every CTA
                         if (kb == num_kb - 1)
                             mma_commit(bar_tfull + 8 * acc);
                     }
+                    soff += stage16;
+                    if (++stage == p.stages) {
+                        stage = 0;
+                        soff = 0;
+                        phase ^= 1;
+                    }
                 }
-                __syncwarp();
-                if (++stage == p.stages) {
-                    stage = 0;
-                    phase ^= 1;
-                }
+                acc ^= 1;
+                if (acc == 0)
+                    acc_phase ^= 1;
             }
-            acc ^= 1;
-            if (acc == 0)
-                acc_phase ^= 1;
+        };
+        // (elect.sync, not `lane == 0`: the compiler then knows that exactly one lane is active and emits
+        // plain UTCHMMA / UTCBAR instead of a per-instruction ELECT + R2UR.BROADCAST loop)
+        if (!(pair && crank != 0) && elect_one()) {
+            if (p.kb_bytes == 128)
+                run(std::integral_constant<uint32_t, 4>{});
+            else if (p.kb_bytes == 64)
+                run(std::integral_constant<uint32_t, 2>{});
+            else
+                run(std::integral_constant<uint32_t, 1>{});
         }
+        __syncwarp();
     } else if (warp == 2) {
         // ============================ z prefetch (TMA) ============================
         if (p.has_z) {

@@ -287,6 +287,36 @@ __device__ __forceinline__ void mma_commit_2sm_mc(uint32_t bar, uint16_t mask) {
             "h"(mask)
             : "memory");
 }
+// accumulate-always forms: the enable-input-d predicate is a compile-time constant (folds to PT), so the
+// issuing thread spends no instruction on it
+__device__ __forceinline__ void mma_f16_acc(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(taddr),
+            "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+}
+__device__ __forceinline__ void mma_i8_acc(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\n"
+            "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(taddr),
+            "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+}
+__device__ __forceinline__ void mma_f16_2sm_acc(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n}\n" ::"r"(taddr),
+            "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+}
+__device__ __forceinline__ void mma_i8_2sm_acc(uint32_t taddr, uint64_t adesc, uint64_t bdesc, uint32_t idesc) {
+    asm volatile(
+            "{\n.reg .pred p;\nsetp.ne.b32 p, 1, 0;\n"
+            "tcgen05.mma.cta_group::2.kind::i8 [%0], %1, %2, %3, p;\n}\n" ::"r"(taddr),
+            "l"(adesc), "l"(bdesc), "r"(idesc)
+            : "memory");
+}
 // all previously issued MMAs of this thread arrive on `bar` when complete
 __device__ __forceinline__ void mma_commit(uint32_t bar) {
     asm volatile(
