@@ -155,6 +155,7 @@ constexpr uint32_t OFF_BRES = 424;     // stem: resident filter barrier
 // the z / dst streams, so their spare shared memory holds z chunks (a tile or more ahead) rather than
 // more A/B stages
 constexpr uint32_t NZ_MIN = 4, NZ_MAX = 8;
+constexpr uint32_t STEM_NJ_K = 136;    // pixel pairs per staged stem input row (== STEM_NJ on the host)
 constexpr uint32_t OFF_BIAS = 1024;    // (4 * GROUPS) warps x BN x 4 bytes, rounded up to 1 KiB
 // host mirror of Traits::slabs_bytes
 __host__ __device__ constexpr uint32_t slabs_bytes(uint32_t groups, uint32_t bn, uint32_t row_bytes) {
@@ -425,45 +426,77 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         }
     } else if (warp == 1 && stem) {
         // ============================ MMA issuer, stem mode ============================
-        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-        TIMED_WAIT(6, bar_bres, 0);
-        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
-            TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
-            TIMED_WAIT(2, bar_full + 8 * stage, phase);
-            tc_fence_after();
-            if (elect_one()) {
+        // One thread, every MMA of a tile unrolled per filter row with immediate descriptor offsets and a
+        // constant accumulate predicate: a 128 x 64 MMA occupies the tensor pipe only 48 clk, so the
+        // issue loop itself bounds this mode (tools/microbench/mma_shapes.cu).
+        // A: rows = output pixels (16 bytes apart), K = [even pixel 8ch | odd pixel 8ch]: no swizzle,
+        // LBO = parity-plane distance, SBO = 128 B; one entry (16 B) per tap pair.
+        // stem4: K = [pair j | pair j + 1], the two halves 16 bytes apart, one K step per two pairs.
+        auto mma_acc = [&](uint32_t taddr, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi) {
+            const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | a_lo;
+            const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | b_lo;
+            if constexpr (KIND == KIND_S8)
+                mma_i8_acc(taddr, adesc, bdesc, IDESC);
+            else
+                mma_f16_acc(taddr, adesc, bdesc, IDESC);
+        };
+        auto run = [&](auto KS_, auto AS_) {
+            constexpr uint32_t KS = decltype(KS_)::value;   // K steps (MMAs) per filter row
+            constexpr uint32_t AS = decltype(AS_)::value;   // A entries (16 B) per K step
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            const uint32_t a_hi = desc_hi(128, 0);
+            const uint32_t b_hi = AS == 2 ? desc_hi(512, 4) : desc_hi(1024, 2);
+            const uint32_t a0 = desc_lo(sStage, AS == 2 ? 16u : plane_bytes), b0 = desc_lo(sBres, 16);
+            const uint32_t stage16 = stage_bytes >> 4, brow = BN * stem_rb / 16u;
+            uint32_t soff = 0;
+            TIMED_WAIT(6, bar_bres, 0);
+            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+                TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
+                TIMED_WAIT(2, bar_full + 8 * stage, phase);
+                tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * BN;
-                const uint32_t sa = sStage + stage * stage_bytes;
-                // A: rows = output pixels (16 bytes apart), K = [even pixel 8ch | odd pixel 8ch]:
-                // no swizzle, LBO = parity-plane distance, SBO = 128 B; one entry (16 B) per tap pair
-                // stem4: K = [pair j | pair j + 1], the two halves 16 bytes apart, one K step per two pairs
-                const uint32_t a_hi = desc_hi(128, 0);
-                const uint32_t b_hi = p.stem4 ? desc_hi(512, 4) : desc_hi(1024, 2);
-                uint32_t a_lo = desc_lo(sa, p.stem4 ? 16u : plane_bytes);
-                uint32_t b_lo = desc_lo(sBres, 16);
-                const uint32_t ksteps = p.stem4 ? (p.stem_fw2 + 1) / 2 : p.stem_fw2;
-                const uint32_t a_step = p.stem4 ? 2u : 1u;
-                uint32_t first = 0;
-                for (uint32_t fh = 0; fh < p.stem_fh; ++fh) {
-                    for (uint32_t t2 = 0; t2 < ksteps; ++t2) {
-                        mma_issue<KIND>(taddr, a_lo + t2 * a_step, a_hi, b_lo + 2 * t2, b_hi, IDESC, first);
-                        first = 1;
-                    }
-                    a_lo += p.stem_nj;            // next filter row: stem_nj entries further
-                    b_lo += BN * stem_rb / 16u;   // next K row block of the resident filter
+                uint32_t a_lo = a0 + soff, b_lo = b0;
+                mma_issue<KIND>(taddr, a_lo, a_hi, b_lo, b_hi, IDESC, 0);  // overwrites the accumulator
+#pragma unroll
+                for (uint32_t t2 = 1; t2 < KS; ++t2)
+                    mma_acc(taddr, a_lo + t2 * AS, a_hi, b_lo + 2 * t2, b_hi);
+                for (uint32_t fh = 1; fh < p.stem_fh; ++fh) {
+                    a_lo += STEM_NJ_K;   // next filter row: one staged input row further
+                    b_lo += brow;        // next K row block of the resident filter
+#pragma unroll
+                    for (uint32_t t2 = 0; t2 < KS; ++t2)
+                        mma_acc(taddr, a_lo + t2 * AS, a_hi, b_lo + 2 * t2, b_hi);
                 }
                 mma_commit(bar_empty + 8 * stage);
                 mma_commit(bar_tfull + 8 * acc);
+                soff += stage16;
+                if (++stage == p.stages) {
+                    stage = 0;
+                    soff = 0;
+                    phase ^= 1;
+                }
+                acc ^= 1;
+                if (acc == 0)
+                    acc_phase ^= 1;
             }
-            __syncwarp();
-            if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1;
+        };
+        using U1 = std::integral_constant<uint32_t, 1>;
+        using U2 = std::integral_constant<uint32_t, 2>;
+        using U3 = std::integral_constant<uint32_t, 3>;
+        using U4 = std::integral_constant<uint32_t, 4>;
+        if (elect_one()) {
+            const uint32_t ksteps = p.stem4 ? (p.stem_fw2 + 1) / 2 : p.stem_fw2;
+            if (p.stem4) {
+                if (ksteps == 1) run(U1{}, U2{});
+                else run(U2{}, U2{});
+            } else {
+                if (ksteps == 1) run(U1{}, U1{});
+                else if (ksteps == 2) run(U2{}, U1{});
+                else if (ksteps == 3) run(U3{}, U1{});
+                else run(U4{}, U1{});
             }
-            acc ^= 1;
-            if (acc == 0)
-                acc_phase ^= 1;
         }
+        __syncwarp();
     } else if (warp == 0 && rows) {
         // ============================ TMA producer, rows mode ============================
         if (elect_one()) {
@@ -498,56 +531,74 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     } else if (warp == 1 && rows) {
         // ============================ MMA issuer, rows mode ============================
         // tap (fh, fw) of output m' reads slab entry m' - r0*PW + fh*PW + fw: a pure row shift of the
-        // A descriptor (128-byte rows, SWIZZLE_128B keyed on absolute smem address bits)
-        uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-        TIMED_WAIT(6, bar_bres, 0);
-        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
-            const uint32_t tile = ct;  // C == 1 in this mode
-            const uint32_t t = tile % p.tiles_per_img;
-            const uint32_t off0 = (t * IGEMM_BLOCK_M) % p.PW;
-            TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
-            TIMED_WAIT(2, bar_full + 8 * stage, phase);
-            tc_fence_after();
-            if (elect_one()) {
+        // A descriptor (128-byte rows, SWIZZLE_128B keyed on absolute smem address bits).  The slab row
+        // a tap starts on is usually not a multiple of 8: the swizzle is keyed on absolute address bits
+        // (as TMA wrote it), so a plain row-shifted start address is correct (base-offset field 0;
+        // verified on B200 against the oracle).  One thread issues; the four MMAs of a (tap, channel
+        // block) are unrolled with immediate offsets and a constant accumulate predicate.
+        if (elect_one()) {
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
+            const uint32_t ab_hi = desc_hi(1024, 2);
+            const uint32_t plane16 = plane_bytes >> 4, stage16 = stage_bytes >> 4, brow = BN * 128u / 16u;
+            const uint32_t a0 = desc_lo(sStage, 16), b0 = desc_lo(sBres, 16);
+            const uint32_t FH = p.num_taps / p.FW, roww = p.PW * 8;
+            uint32_t soff = 0;
+            auto mma4 = [&](uint32_t taddr, uint32_t a_lo, uint32_t b_lo) {
+#pragma unroll
+                for (uint32_t k = 0; k < 4; ++k) {
+                    const uint64_t adesc = (static_cast<uint64_t>(ab_hi) << 32) | (a_lo + 2 * k);
+                    const uint64_t bdesc = (static_cast<uint64_t>(ab_hi) << 32) | (b_lo + 2 * k);
+                    if constexpr (KIND == KIND_S8)
+                        mma_i8_acc(taddr, adesc, bdesc, IDESC);
+                    else
+                        mma_f16_acc(taddr, adesc, bdesc, IDESC);
+                }
+            };
+            TIMED_WAIT(6, bar_bres, 0);
+            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+                const uint32_t t = ct % p.tiles_per_img;  // C == 1 in this mode: ct is the tile
+                const uint32_t off0 = (t * IGEMM_BLOCK_M) % p.PW;
+                TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
+                TIMED_WAIT(2, bar_full + 8 * stage, phase);
+                tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * BN;
-                const uint32_t sa = sStage + stage * stage_bytes;
-                // The slab row a tap starts on is usually not a multiple of 8: the 128B swizzle is
-                // keyed on absolute smem address bits (as TMA wrote it), so a plain row-shifted start
-                // address is correct (base-offset field 0; verified on B200 against the oracle).
-                const uint32_t ab_hi = desc_hi(1024, 2);
-                const uint32_t plane16 = plane_bytes >> 4;
-                uint32_t row_lo = desc_lo(sa + off0 * 128u, 16);  // tap (fh, 0)
-                uint32_t b_lo = desc_lo(sBres, 16);
-                uint32_t first = 0;
-                for (uint32_t fh = 0; fh < p.num_taps / p.FW; ++fh) {
+                uint32_t row_lo = a0 + soff + off0 * 8;  // tap (fh, 0); 128-byte rows = 8 units
+                uint32_t b_lo = b0;
+                // the very first MMA of the tile overwrites the accumulator
+                mma_issue<KIND>(taddr, row_lo, ab_hi, b_lo, ab_hi, IDESC, 0);
+#pragma unroll
+                for (uint32_t k = 1; k < 4; ++k)
+                    mma_issue<KIND>(taddr, row_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC, 1);
+                bool skip = true;  // (fh, fw, kc) == (0, 0, 0) is done
+                for (uint32_t fh = 0; fh < FH; ++fh) {
                     uint32_t tap_lo = row_lo;
                     for (uint32_t fw = 0; fw < p.FW; ++fw) {
                         uint32_t a_lo = tap_lo;
                         for (uint32_t kc = 0; kc < p.num_kc; ++kc) {
-#pragma unroll
-                            for (uint32_t k = 0; k < 4; ++k) {
-                                mma_issue<KIND>(taddr, a_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC, first);
-                                first = 1;
-                            }
+                            if (!skip)
+                                mma4(taddr, a_lo, b_lo);
+                            skip = false;
                             a_lo += plane16;
-                            b_lo += BN * 128u / 16u;
+                            b_lo += brow;
                         }
                         tap_lo += 8;  // next pixel: 128 bytes
                     }
-                    row_lo += p.PW * 8;  // next input row
+                    row_lo += roww;  // next input row
                 }
                 mma_commit(bar_empty + 8 * stage);
                 mma_commit(bar_tfull + 8 * acc);
+                soff += stage16;
+                if (++stage == p.stages) {
+                    stage = 0;
+                    soff = 0;
+                    phase ^= 1;
+                }
+                acc ^= 1;
+                if (acc == 0)
+                    acc_phase ^= 1;
             }
-            __syncwarp();
-            if (++stage == p.stages) {
-                stage = 0;
-                phase ^= 1;
-            }
-            acc ^= 1;
-            if (acc == 0)
-                acc_phase ^= 1;
         }
+        __syncwarp();
     } else if (warp == 0) {
         // ============================ TMA producer (A, B) ============================
         uint32_t stage = 0, phase = 0;
@@ -1309,7 +1360,7 @@ struct Geometry {
     bool stem;            // a_mode 2: resident filter + one input-row slab per tile
     bool stem4;           // ... with a pixel pair per 16-byte unit (IC * es == 8)
 };
-constexpr uint32_t STEM_NJ = 136;  // 128 output pixels + up to 4 tap pairs - 1, rounded up to 8
+constexpr uint32_t STEM_NJ = STEM_NJ_K;  // 128 output pixels + up to 4 tap pairs - 1, rounded up to 8
 
 // The NCHW4 cells run on an NHWC / KRSC copy of src / filter in the workspace (relayout.cu), with the
 // channels zero-padded to a TMA-legal multiple of 16: this is the descriptor of that equivalent conv.
