@@ -922,18 +922,29 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                         : slab_gen + db * T::SLAB_BYTES + lane * T::ROW_BYTES;
                 const uint32_t st_src = p.has_z ? sZ + zb * T::ZBUF_BYTES + quad * T::SLAB_BYTES
                                                 : slab_u32 + db * T::SLAB_BYTES;
+                // the whole chunk (EPI_N columns) goes to registers first, so that the accumulator is handed
+                // back to the MMA warp before any epilogue arithmetic (short-k layers live on that overlap)
+                // (16-bit kinds; the int8 requantize needs the registers and loads 32 columns at a time)
+                constexpr uint32_t HALVES = T::EPI_N / 32;
+                constexpr uint32_t HB = (KIND == KIND_S8) ? 1 : HALVES;  // halves loaded per batch
+                uint32_t rr[HB][32];
 #pragma unroll
-                for (uint32_t h = 0; h < T::EPI_N / 32; ++h) {
-                    uint32_t r[32];
-                    tmem_ld_32x32(tmem_base + ((quad * 32) << 16) + acc * BN + c * T::EPI_N + h * 32, r);
-                    tmem_ld_wait();
-                    if (static_cast<int32_t>(c) == last_c && h == T::EPI_N / 32 - 1) {
-                        // accumulator fully drained into registers: hand TMEM back to the MMA warp
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0)
-                            arrive_tempty(bar_tempty + 8 * acc);
+                for (uint32_t h = 0; h < HALVES; ++h) {
+                    if (h % HB == 0) {
+#pragma unroll
+                        for (uint32_t hh = 0; hh < HB; ++hh)
+                            tmem_ld_32x32(
+                                    tmem_base + ((quad * 32) << 16) + acc * BN + c * T::EPI_N + (h + hh) * 32, rr[hh]);
+                        tmem_ld_wait();
+                        if (static_cast<int32_t>(c) == last_c && h + HB == HALVES) {
+                            // accumulator fully drained into registers: hand TMEM back to the MMA warp
+                            tc_fence_before();
+                            __syncwarp();
+                            if (lane == 0)
+                                arrive_tempty(bar_tempty + 8 * acc);
+                        }
                     }
+                    const uint32_t (&r)[32] = rr[h % HB];
                     const uint32_t* bcol = sbias + c * T::EPI_N + h * 32;
                     constexpr uint32_t COLS_PER_16B = 16 / T::OUT_ES;
                     constexpr uint32_t PIECES = 32 / COLS_PER_16B;  // 16-byte pieces per 32 columns

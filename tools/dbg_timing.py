@@ -19,7 +19,7 @@ names = ["empty", "tempty", "full", "tfull", "zfull", "zempty", "bres", "stwait"
 for layer in K.RESNET50_LAYERS:
     if only and layer[0] not in only:
         continue
-    d = K.resnet50_desc(layer, kind, 256, ic_pad=16 if kind == "qs8" else 8)
+    d = K.resnet50_desc(layer, kind, 256, ic_pad=8 if kind == "qs8" else 4)
     plan = C.Plan()
     assert lib.b200cb_query(ctypes.byref(d), ctypes.byref(plan)) == 0
     tdt = torch.int8 if kind == "qs8" else torch.bfloat16
