@@ -171,7 +171,7 @@ def cpu_reference(steps, warmup, budget_s, batch=None):
             "_steps": len(times), "_ms": t_med * 1e3, "_batch": n}
 
 
-def run_reference_arm(args):
+def run_reference_arm(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -184,7 +184,7 @@ def run_reference_arm(args):
             "cpu_baseline": {k: v for k, v in cb.items() if not k.startswith("_")},
             "e2e": {"value": cb["value"], "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------ GPU arm
@@ -310,8 +310,20 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
 
+    # stdout carries exactly one JSON line: library chatter (e.g. NCCL's version banner, printed at
+    # communicator creation) is routed to stderr until that line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        run_reference_arm(args)
+        run_reference_arm(args, emit)
         return
 
     import torch
@@ -484,7 +496,7 @@ def main():
         }
         if cpu is not None:
             line["cpu_baseline"] = cpu
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
