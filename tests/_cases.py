@@ -161,3 +161,22 @@ MOBILENETV2_DW = [
 
 def dw_desc(kind, n, c, h, w, stride, f=3, nonline=C.NL_RELU, has_z=False):
     return make_desc(kind, n, c, h, w, c, f, stride=stride, pad=f // 2, group=c, nonline=nonline, has_z=has_z)
+
+
+# BASELINE.json configs[0]: the ResNet-18 conv stack (fp32 NCHW, 224x224) the reference runs on its CPU
+# handles -- conv1 7x7/2, four stages of two BasicBlocks (3x3) with 1x1/2 projections
+# (lite/load_and_run/examples/script/resnet50_mge.py:12-53, src/gopt/test/network.cpp:188-224).
+# (name, ic, h, w, oc, f, stride, pad, count)
+RESNET18_LAYERS = [
+    ("conv1", 3, 224, 224, 64, 7, 2, 3, 1),
+    ("l1.c3x3", 64, 56, 56, 64, 3, 1, 1, 4),
+    ("l2.b0.c1", 64, 56, 56, 128, 3, 2, 1, 1), ("l2.ds", 64, 56, 56, 128, 1, 2, 0, 1), ("l2.c3x3", 128, 28, 28, 128, 3, 1, 1, 3),
+    ("l3.b0.c1", 128, 28, 28, 256, 3, 2, 1, 1), ("l3.ds", 128, 28, 28, 256, 1, 2, 0, 1), ("l3.c3x3", 256, 14, 14, 256, 3, 1, 1, 3),
+    ("l4.b0.c1", 256, 14, 14, 512, 3, 2, 1, 1), ("l4.ds", 256, 14, 14, 512, 1, 2, 0, 1), ("l4.c3x3", 512, 7, 7, 512, 3, 1, 1, 3),
+]
+
+
+def resnet18_desc(layer, n):
+    name, ic, h, w, oc, f, s, p, _cnt = layer
+    return make_desc("f32", n, ic, h, w, oc, f, stride=s, pad=p, fmt=C.FORMAT_NCHW,
+                     nonline=C.NL_IDENTITY if name.endswith(".ds") else C.NL_RELU)

@@ -129,3 +129,21 @@ def test_x86_baseline_agrees_with_naive():
     x86, _s, algo = O.ref_convbias(d, src, flt, bias, None, handle_kind=0, threads=2)
     assert algo != "DEFAULT"
     assert O.megdnn_rel_err(naive, x86).max() < 1e-3
+
+
+@pytest.mark.skipif(not O.have_ref(), reason="oracle/_ref (compiled reference) not present on this box")
+@pytest.mark.parametrize("layer", K.RESNET18_LAYERS, ids=[l[0] for l in K.RESNET18_LAYERS])
+def test_resnet18_fp32_nchw_cpu_config(layer):
+    """BASELINE.json configs[0] (the reference's own CPU-runnable case): every ConvBias shape of ResNet-18,
+    fp32 NCHW, bias + ReLU, at N = 1 -- the C restatement equals the reference's naive operator bit for bit,
+    and the reference's x86 / fallback fast path (the CPU baseline arm) agrees with it to the reference
+    tests' fp32 eps (dnn/test/cuda/conv_bias.cpp:96)."""
+    d = K.resnet18_desc(layer, 1)
+    if layer[0] == "conv1":   # naive at 224x224 takes a while: same filter / stride / pad on 96x96
+        d = K.make_desc("f32", 1, 3, 96, 96, 64, 7, stride=2, pad=3, fmt=C.FORMAT_NCHW, nonline=C.NL_RELU)
+    src, flt, bias, _ = K.gen_inputs(d, 18)
+    naive, _s, _a = O.ref_convbias(d, src, flt, bias, None, handle_kind=2)
+    port = O.oracle_convbias(d, src, flt, bias, None)
+    assert np.array_equal(port, naive)
+    x86, _s, algo = O.ref_convbias(d, src, flt, bias, None, handle_kind=0, threads=4)
+    assert O.megdnn_rel_err(naive, x86).max() < 1e-3, algo
