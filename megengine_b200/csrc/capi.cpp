@@ -79,6 +79,50 @@ double igemm_cost(const b200cb_desc& d, uint32_t bn, int sms) {
         return 1.0 / bn;           // enough parallelism: widest first
     return 1.0 + 1.0 / tiles;      // small problems: most tiles first
 }
+// ---- NCHW adapter (fp16 / bf16): the tensor-core kernels want channels innermost, so NCHW tensors are
+// re-tiled into NHWC / KRSC copies in the workspace (channels zero-padded to what TMA needs), the NHWC
+// plan of the same algorithm runs on those, and dst is re-tiled back.  Functional coverage of the
+// reference's default layout (imperative F.conv2d); the fast path is NHWC.
+bool is_nchw16(const b200cb_desc& d) {
+    return d.format == B200CB_FORMAT_NCHW && (d.src_dtype == B200CB_DT_BF16 || d.src_dtype == B200CB_DT_F16);
+}
+bool nchw_depthwise(const b200cb_desc& d) {
+    return d.sparse == B200CB_SPARSE_GROUP && d.group == d.ic && d.ic == d.oc;
+}
+b200cb_desc nchw_equivalent(const b200cb_desc& d) {
+    b200cb_desc e = d;
+    e.format = B200CB_FORMAT_NHWC;
+    if (!nchw_depthwise(d)) {
+        // stems (IC <= 4, stride 2) take 8-byte pixels, everything else 16-byte channel granules
+        const bool stem_like = d.ic <= 4 && d.stride_w == 2 && d.stride_h == 2 && d.iw % 2 == 0 &&
+                               d.dilate_w == 1 && d.dilate_h == 1 && d.mode == B200CB_MODE_CROSS_CORRELATION;
+        e.ic = stem_like ? 4 : (d.ic + 7) / 8 * 8;
+    }
+    e.src_batch_stride = e.z_batch_stride = e.dst_batch_stride = 0;
+    return e;
+}
+size_t a256(size_t v) {
+    return (v + 255) & ~size_t(255);
+}
+struct NchwLayout {
+    size_t src, flt, z, dst, inner, total;
+};
+NchwLayout nchw_layout(const b200cb_desc& d, const b200cb_desc& e, uint64_t inner_ws) {
+    NchwLayout l{};
+    size_t off = 0;
+    l.src = off, off += a256((size_t)e.n * e.ih * e.iw * e.ic * 2);
+    l.flt = off, off += nchw_depthwise(d) ? 0 : a256((size_t)e.oc * e.fh * e.fw * e.ic * 2);
+    l.z = off, off += d.has_z ? a256((size_t)e.n * e.oh * e.ow * e.oc * 2) : 0;
+    l.dst = off, off += a256((size_t)e.n * e.oh * e.ow * e.oc * 2);
+    l.inner = off, off += a256(inner_ws);
+    l.total = off;
+    return l;
+}
+int query_one(const b200cb_desc& d, int algo, b200cb_plan* plan) {
+    const AlgoEntry& a = g_algos[algo];
+    return a.kernel == KERNEL_IGEMM ? igemm_query(d, a.block_n, plan) : dwconv_query(d, plan);
+}
+
 }  // namespace
 
 void set_last_error(const char* what, const char* detail) {
@@ -110,13 +154,20 @@ int b200cb_query_algo(const b200cb_desc* desc, int algo, b200cb_plan* plan) {
     if (rc != B200CB_OK)
         return rc;
     memset(plan, 0, sizeof(*plan));
-    const AlgoEntry& a = g_algos[algo];
-    if (a.kernel == KERNEL_IGEMM)
-        rc = igemm_query(*desc, a.block_n, plan);
-    else
-        rc = dwconv_query(*desc, plan);
-    if (rc != B200CB_OK)
-        return rc;
+    if (is_nchw16(*desc)) {
+        if (desc->bias_mode == B200CB_BIAS_FULL || (desc->oc % 8 != 0 && !nchw_depthwise(*desc)))
+            return B200CB_UNSUPPORTED_ALIGNMENT;
+        const b200cb_desc e = nchw_equivalent(*desc);
+        rc = query_one(e, algo, plan);
+        if (rc != B200CB_OK)
+            return rc;
+        plan->workspace_bytes = nchw_layout(*desc, e, plan->workspace_bytes).total;
+        plan->desc = *desc;
+    } else {
+        rc = query_one(*desc, algo, plan);
+        if (rc != B200CB_OK)
+            return rc;
+    }
     plan->algo = algo;
     fill_accounting(plan);
     return B200CB_OK;
@@ -158,6 +209,36 @@ int b200cb_launch(
     if (workspace_bytes < plan->workspace_bytes || (plan->workspace_bytes && !workspace))
         return B200CB_ERR_WORKSPACE;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (is_nchw16(plan->desc)) {
+        const b200cb_desc& d = plan->desc;
+        const b200cb_desc e = nchw_equivalent(d);
+        b200cb_plan inner;
+        int rc = b200cb_query_algo(&e, plan->algo, &inner);
+        if (rc != B200CB_OK)
+            return rc > 0 ? B200CB_ERR_BAD_PLAN : rc;
+        const NchwLayout l = nchw_layout(d, e, inner.workspace_bytes);
+        if (!workspace || workspace_bytes < l.total || !src || !filter || !dst || (d.has_z && !z))
+            return !workspace || workspace_bytes < l.total ? B200CB_ERR_WORKSPACE : B200CB_ERR_NULL;
+        uint8_t* ws = static_cast<uint8_t*>(workspace);
+        const uint32_t P = d.ih * d.iw, OP = d.oh * d.ow;
+        // src (N, C, P) -> (N, P, Cpad); filter (OC, IC, FHFW) -> (OC, FHFW, ICpad) (depthwise: same order)
+        rc = relayout_transpose16(src, ws + l.src, d.n, d.ic, P, e.ic, d.src_batch_stride, 0, s);
+        const void* flt = filter;
+        if (rc == B200CB_OK && !nchw_depthwise(d)) {
+            rc = relayout_transpose16(filter, ws + l.flt, d.oc, d.ic, d.fh * d.fw, e.ic, 0, 0, s);
+            flt = ws + l.flt;
+        }
+        if (rc == B200CB_OK && d.has_z)
+            rc = relayout_transpose16(z, ws + l.z, d.n, d.oc, OP, d.oc, d.z_batch_stride, 0, s);
+        if (rc == B200CB_OK)
+            rc = b200cb_launch(
+                    &inner, ws + l.src, flt, bias, d.has_z ? ws + l.z : nullptr, ws + l.dst, ws + l.inner,
+                    inner.workspace_bytes, stream);
+        // dst (N, OP, OC) -> (N, OC, OP)
+        if (rc == B200CB_OK)
+            rc = relayout_transpose16(ws + l.dst, dst, d.n, OP, d.oc, OP, 0, d.dst_batch_stride, s);
+        return rc;
+    }
     switch (plan->kernel) {
         case KERNEL_IGEMM:
             return igemm_launch(*plan, src, filter, bias, z, dst, workspace, workspace_bytes, s);
@@ -171,6 +252,13 @@ int b200cb_launch(
 int b200cb_plan_num_launches(const b200cb_plan* plan) {
     if (!plan || plan->magic != PLAN_MAGIC)
         return 0;
+    if (is_nchw16(plan->desc)) {  // re-tile src (+ filter, + z), the NHWC plan, re-tile dst
+        const b200cb_desc e = nchw_equivalent(plan->desc);
+        b200cb_plan inner;
+        if (b200cb_query_algo(&e, plan->algo, &inner) != B200CB_OK)
+            return 0;
+        return 2 + (nchw_depthwise(plan->desc) ? 0 : 1) + (plan->desc.has_z ? 1 : 0) + b200cb_plan_num_launches(&inner);
+    }
     // NCHW4: src re-tile + filter re-tile (+ stem filter re-pack) + conv
     if (plan->kernel == KERNEL_IGEMM && plan->desc.format == B200CB_FORMAT_NCHW4)
         return plan->reserved[4] ? 4 : 3;
@@ -182,7 +270,7 @@ int b200cb_plan_num_launches(const b200cb_plan* plan) {
 
 size_t b200cb_preprocessed_filter_bytes(const b200cb_plan* plan) {
     // KRSC filters are consumed in place by TMA; only the W-folded stem needs a packed copy.
-    if (!plan || plan->magic != PLAN_MAGIC || plan->kernel != KERNEL_IGEMM)
+    if (!plan || plan->magic != PLAN_MAGIC || plan->kernel != KERNEL_IGEMM || is_nchw16(plan->desc))
         return 0;
     return igemm_packed_filter_bytes(*plan);
 }
@@ -192,7 +280,7 @@ int b200cb_preprocess_filter(const b200cb_plan* plan, const void* filter, void* 
         return B200CB_ERR_NULL;
     if (plan->magic != PLAN_MAGIC)
         return B200CB_ERR_BAD_PLAN;
-    if (plan->kernel != KERNEL_IGEMM || !plan->reserved[4] || plan->desc.format == B200CB_FORMAT_NCHW4)
+    if (plan->kernel != KERNEL_IGEMM || !plan->reserved[4] || plan->desc.format != B200CB_FORMAT_NHWC)
         return B200CB_OK;  // nothing to pack (NCHW4 filters are re-tiled per exec)
     if (!filter || !packed)
         return B200CB_ERR_NULL;
@@ -204,7 +292,7 @@ int b200cb_plan_use_preprocessed_filter(b200cb_plan* plan) {
         return B200CB_ERR_NULL;
     if (plan->magic != PLAN_MAGIC)
         return B200CB_ERR_BAD_PLAN;
-    if (plan->kernel == KERNEL_IGEMM && plan->reserved[4] && plan->desc.format != B200CB_FORMAT_NCHW4) {
+    if (plan->kernel == KERNEL_IGEMM && plan->reserved[4] && plan->desc.format == B200CB_FORMAT_NHWC) {
         plan->reserved[3] = 1;
         plan->workspace_bytes = 0;
     }

@@ -55,6 +55,11 @@ int relayout_c4_to_channels_last(
         const void* in, void* out, uint32_t B, uint32_t C, uint32_t Cpad, uint32_t P,
         uint64_t in_batch_elems, cudaStream_t stream);
 
+// in[b][r][s] -> out[b][s][r] for 16-bit elements, output rows zero-padded to out_ld (relayout.cu)
+int relayout_transpose16(
+        const void* in, void* out, uint32_t B, uint32_t R, uint32_t S, uint32_t out_ld, uint64_t in_batch,
+        uint64_t out_batch, cudaStream_t stream);
+
 int device_sm_count();
 
 inline uint32_t dtype_size(uint32_t dt) {

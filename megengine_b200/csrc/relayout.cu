@@ -58,7 +58,51 @@ __global__ void __launch_bounds__(256) gather_words_kernel(
         dst[c] = w[c];
 }
 
+// Batched transpose of 16-bit elements, in[b][r][s] -> out[b][s][r], rows of the output zero-padded up
+// to out_ld (NCHW <-> NHWC of fp16 / bf16 tensors).  32 x 32 tiles through shared memory.
+__global__ void __launch_bounds__(256) transpose_u16_kernel(
+        const uint16_t* __restrict__ in, uint16_t* __restrict__ out, uint32_t R, uint32_t S, uint32_t out_ld,
+        uint64_t in_batch, uint64_t out_batch) {
+    __shared__ uint16_t tile[32][34];
+    const uint32_t b = blockIdx.z;
+    const uint32_t s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint16_t* src = in + static_cast<size_t>(b) * in_batch;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t r = r0 + ty + 8 * i, sidx = s0 + tx;
+        tile[ty + 8 * i][tx] = (r < R && sidx < S) ? src[static_cast<size_t>(r) * S + sidx] : uint16_t(0);
+    }
+    __syncthreads();
+    uint16_t* dst = out + static_cast<size_t>(b) * out_batch;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t sidx = s0 + ty + 8 * i, r = r0 + tx;
+        if (sidx < S && r < out_ld)
+            dst[static_cast<size_t>(sidx) * out_ld + r] = tile[tx][ty + 8 * i];
+    }
+}
+
 }  // namespace
+
+int relayout_transpose16(
+        const void* in, void* out, uint32_t B, uint32_t R, uint32_t S, uint32_t out_ld, uint64_t in_batch,
+        uint64_t out_batch, cudaStream_t stream) {
+    if (B == 0 || R == 0 || S == 0 || out_ld < R)
+        return B200CB_UNSUPPORTED_SHAPE;
+    dim3 grid((S + 31) / 32, (out_ld + 31) / 32, B);
+    if (grid.y > 65535 || grid.z > 65535)
+        return B200CB_UNSUPPORTED_SHAPE;
+    transpose_u16_kernel<<<grid, 256, 0, stream>>>(
+            static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), R, S, out_ld,
+            in_batch ? in_batch : static_cast<uint64_t>(R) * S, out_batch ? out_batch : static_cast<uint64_t>(S) * out_ld);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("relayout launch", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    return B200CB_OK;
+}
 
 // (B, C/4, P, 4) int8 -> (B, P, Cpad) int8; `in_batch_elems` = elements between consecutive b (0 = dense)
 int relayout_c4_to_channels_last(

@@ -83,7 +83,9 @@ def test_unsupported_cells_are_rejected_not_silently_wrong(lib):
     ok = K.make_desc("bf16", 2, 64, 14, 14, 64, 3, pad=1)
     assert _query(lib, ok)[0] == 0
     cases = []
-    d = ok.copy(); d.format = C.FORMAT_NCHW; cases.append(d)                      # format
+    d = ok.copy(); d.format = 2; cases.append(d)                                   # format (NHWCD4)
+    d = K.make_desc("f32", 2, 64, 14, 14, 64, 3, pad=1, fmt=C.FORMAT_NCHW); cases.append(d)  # NCHW fp32: not on this path
+    d = K.make_desc("bf16", 2, 64, 14, 14, 60, 3, pad=1, fmt=C.FORMAT_NCHW); cases.append(d)  # NCHW adapter needs OC % 8
     d = ok.copy(); d.src_dtype = d.filter_dtype = C.DT_F32; d.dst_dtype = d.bias_dtype = C.DT_F32; cases.append(d)
     d = ok.copy(); d.ic = 60; cases.append(d)                                      # 16-byte channel alignment
     d = ok.copy(); d.bias_mode = C.BIAS_FULL; cases.append(d)
@@ -97,6 +99,19 @@ def test_unsupported_cells_are_rejected_not_silently_wrong(lib):
         rc, _p = _query(lib, d)
         assert rc > 0, K.desc_str(d)
         assert lib.b200cb_strerror(rc) not in (b"ok", b"unknown error")
+
+
+def test_nchw_16bit_plans_carry_the_relayout_workspace(lib):
+    """NCHW fp16 / bf16 runs through the relayout adapter: the plan's workspace holds the NHWC copies of
+    src / filter / z / dst (channels padded for TMA) and the launch count includes the re-tiling passes."""
+    d = K.make_desc("bf16", 2, 20, 14, 14, 64, 3, pad=1, fmt=C.FORMAT_NCHW, has_z=True)
+    rc, p = _query(lib, d)
+    assert rc == 0
+    icp, a = 24, lambda v: (v + 255) & ~255
+    need = a(2 * 14 * 14 * icp * 2) + a(64 * 9 * icp * 2) + 2 * a(2 * 14 * 14 * 64 * 2)
+    assert p.workspace_bytes >= need
+    assert lib.b200cb_plan_num_launches(ctypes.byref(p)) == 5   # src, filter, z, conv, dst
+    assert lib.b200cb_preprocessed_filter_bytes(ctypes.byref(p)) == 0
 
 
 def test_query_algo_enumeration_and_heuristic_pick(lib):

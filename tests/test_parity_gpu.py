@@ -110,6 +110,27 @@ def test_nchw4_int8_bit_exact(case):
     assert info["mismatch"] == 0
 
 
+NCHW_CASES = [
+    # name, kind, n, ic, h, w, oc, f, stride, pad, group, nonline, has_z
+    ("bf16_1x1", "bf16", 2, 64, 14, 14, 128, 1, 1, 0, 1, C.NL_RELU, False),
+    ("bf16_3x3_z", "bf16", 3, 32, 9, 11, 64, 3, 1, 1, 1, C.NL_RELU, True),
+    ("f16_5x5_s2_ic20", "f16", 2, 20, 17, 17, 32, 5, 2, 2, 1, C.NL_IDENTITY, False),
+    ("bf16_7x7_ic3_stem", "bf16", 2, 3, 30, 30, 64, 7, 2, 3, 1, C.NL_RELU, False),
+    ("f16_3x3_hswish_z", "f16", 2, 24, 8, 8, 40, 3, 1, 1, 1, C.NL_H_SWISH, True),
+    ("bf16_depthwise3x3", "bf16", 2, 32, 14, 14, 32, 3, 1, 1, 32, C.NL_RELU, False),
+    ("f16_depthwise3x3_s2_z", "f16", 2, 48, 15, 15, 48, 3, 2, 1, 48, C.NL_RELU, True),
+]
+
+
+@pytest.mark.parametrize("case", NCHW_CASES, ids=[c[0] for c in NCHW_CASES])
+def test_nchw_16bit_through_relayout_adapter(case):
+    """NCHW fp16 / bf16 (the reference's default layout): re-tiled to NHWC in the workspace, the NHWC plan
+    runs, dst is re-tiled back -- same tolerances against the fp32 oracle as the NHWC path."""
+    _name, kind, n, ic, h, w, oc, f, s, pd, grp, nl, has_z = case
+    d = K.make_desc(kind, n, ic, h, w, oc, f, stride=s, pad=pd, group=grp, fmt=C.FORMAT_NCHW, nonline=nl, has_z=has_z)
+    _check(d, seed=41 + ic)
+
+
 def test_nchw4_equals_nhwc_full_size():
     """N = 64 ResNet-50 l2 3x3 (pair tiles): the NCHW4 run equals the NHWC run of the same logical
     tensors, element for element (layout independence at a size the oracle does not reach)."""
