@@ -106,6 +106,10 @@ bool run_case(Handle* host, cudaStream_t stream, const Case& c) {
         lsrc = TensorLayout({c.n, c.h, c.w, c.ic}, sd);
         lflt = grp ? TensorLayout({c.group, ocpg, c.f, c.f, icpg}, fd) : TensorLayout({c.oc, c.f, c.f, c.ic}, fd);
         lbias = TensorLayout({1, 1, 1, c.oc}, bd);
+    } else if (c.format == param::ConvBias::Format::NCHW) {
+        lsrc = TensorLayout({c.n, c.ic, c.h, c.w}, sd);
+        lflt = grp ? TensorLayout({c.group, ocpg, icpg, c.f, c.f}, fd) : TensorLayout({c.oc, c.ic, c.f, c.f}, fd);
+        lbias = TensorLayout({1, c.oc, 1, 1}, bd);
     } else {  // NCHW4
         lsrc = TensorLayout({c.n, c.ic / 4, c.h, c.w, 4}, sd);
         lflt = TensorLayout({c.oc, c.ic / 4, c.f, c.f, 4}, fd);
@@ -221,6 +225,9 @@ int main() {
             {"nhwc_bf16_3x3_z_relu", F::NHWC, DTypeEnum::BFloat16, 2, 64, 14, 14, 256, 3, 1, 1, 1, NL::RELU, true},
             {"nhwc_f16_1x1s2_identity", F::NHWC, DTypeEnum::Float16, 2, 64, 14, 14, 128, 1, 2, 0, 1, NL::IDENTITY, false},
             {"nhwc_bf16_depthwise3x3", F::NHWC, DTypeEnum::BFloat16, 2, 32, 14, 14, 32, 3, 1, 1, 32, NL::RELU, false},
+            {"nchw_bf16_3x3_z_relu", F::NCHW, DTypeEnum::BFloat16, 2, 24, 12, 12, 64, 3, 1, 1, 1, NL::RELU, true},
+            {"nchw_f16_7x7s2_ic3_stem", F::NCHW, DTypeEnum::Float16, 2, 3, 30, 30, 64, 7, 2, 3, 1, NL::RELU, false},
+            {"nchw_f16_depthwise3x3s2", F::NCHW, DTypeEnum::Float16, 2, 48, 15, 15, 48, 3, 2, 1, 48, NL::RELU, false},
             {"nhwc_qs8_depthwise3x3s2", F::NHWC, DTypeEnum::QuantizedS8, 2, 32, 15, 15, 32, 3, 2, 1, 32, NL::RELU, false},
     };
     int failed = 0;
