@@ -274,17 +274,51 @@ __global__ void __launch_bounds__(256) dwconv_nhwc_kernel(const DwParams p) {
             if constexpr (KIND == B200CB_DT_QS8) {
                 const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
                 uint32_t o[4];
+                // IDENTITY / RELU with ordinary scales: the packed ALU / FMA-pipe requantize of the
+                // implicit-GEMM epilogue (epilogue.cuh; no conversion-pipe instructions), else the
+                // generic sequence
+                const bool fast = p.rq.fast_div == 2 &&
+                                  (p.nonline == B200CB_NL_RELU || p.nonline == B200CB_NL_IDENTITY);
+                if (fast) {
+                    const RequantPacked kp = make_requant_packed(p.rq);
+                    const bool relu = p.nonline == B200CB_NL_RELU;
 #pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                    uint32_t packed = 0;
+                    for (int w = 0; w < 4; ++w) {
+                        const uint32_t zx = zw[w] ^ 0x80808080u;
+                        uint32_t ub[4];
 #pragma unroll
-                    for (int b = 0; b < 4; ++b) {
-                        const int32_t sfb = acc[t][4 * w + b] + bias[4 * w + b];
-                        const int32_t zq = (int32_t)(int8_t)((zw[w] >> (8 * b)) & 0xff);
-                        const int32_t q = requant_s8(sfb, zq, p.nonline, p.rq);
-                        packed |= ((uint32_t)q & 0xff) << (8 * b);
+                        for (int b = 0; b < 4; b += 2) {
+                            const int32_t s0 = acc[t][4 * w + b] + bias[4 * w + b];
+                            const int32_t s1 = acc[t][4 * w + b + 1] + bias[4 * w + b + 1];
+                            const uint32_t z0 = __byte_perm(zx, 0x4B000000u, 0x7540u | b);
+                            const uint32_t z1 = __byte_perm(zx, 0x4B000000u, 0x7540u | (b + 1));
+                            if (p.has_z) {
+                                if (relu)
+                                    requant_pair_nonneg<true>(s0, s1, z0, z1, kp, ub[b], ub[b + 1]);
+                                else
+                                    requant_pair_signed<true>(s0, s1, z0, z1, kp, ub[b], ub[b + 1]);
+                            } else {
+                                if (relu)
+                                    requant_pair_nonneg<false>(s0, s1, z0, z1, kp, ub[b], ub[b + 1]);
+                                else
+                                    requant_pair_signed<false>(s0, s1, z0, z1, kp, ub[b], ub[b + 1]);
+                            }
+                        }
+                        o[w] = pack_low_bytes(ub[0], ub[1], ub[2], ub[3]);
                     }
-                    o[w] = packed;
+                } else {
+#pragma unroll
+                    for (int w = 0; w < 4; ++w) {
+                        uint32_t packed = 0;
+#pragma unroll
+                        for (int b = 0; b < 4; ++b) {
+                            const int32_t sfb = acc[t][4 * w + b] + bias[4 * w + b];
+                            const int32_t zq = (int32_t)(int8_t)((zw[w] >> (8 * b)) & 0xff);
+                            const int32_t q = requant_s8(sfb, zq, p.nonline, p.rq);
+                            packed |= ((uint32_t)q & 0xff) << (8 * b);
+                        }
+                        o[w] = packed;
+                    }
                 }
                 ov = make_uint4(o[0], o[1], o[2], o[3]);
             } else {

@@ -169,12 +169,14 @@ def test_int8_epilogue_sass_has_no_contracted_packed_ops():
     checked = 0
     for f in funcs[1:]:
         name = f.split("\n", 1)[0]
-        if "igemm_kernelILi2E" not in name or "ELi1ELi" in name.split("igemm_kernelILi2E")[1][:12]:
-            continue  # QuantizedS8 -> QuantizedS8 kernels only (KIND 2, OUT32 0)
+        is_igemm8 = "igemm_kernelILi2E" in name and "ELi1ELi" not in name.split("igemm_kernelILi2E")[1][:12]
+        is_dw8 = "dwconv_nhwc_kernelILi3E" in name
+        if not (is_igemm8 or is_dw8):
+            continue  # QuantizedS8 -> QuantizedS8 kernels only (igemm KIND 2 / OUT32 0, depthwise KIND 3)
         ffma2, rm, rz = f.count("FFMA2"), f.count("FADD2.RM"), f.count("FADD2.RZ")
         plain = len(re.findall(r"FADD2 ", f))
         assert rm > 0 and rm == rz, (name, rm, rz)
         assert ffma2 == 2 * rm, (name, ffma2, rm)
         assert plain == 0, (name, plain)
         checked += 1
-    assert checked >= 6, checked
+    assert checked >= 11, checked
