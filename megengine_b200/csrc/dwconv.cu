@@ -551,12 +551,13 @@ __global__ void __launch_bounds__(256, 2) dw3x3_kernel(const Dw3Params q) {
 // channel pairs hits consecutive banks, and all tile offsets are immediates or one register.
 struct Dw3TmaParams {
     Dw3Common c;
-    CUtensorMap tmS;       // src (C, IW, IH, N), box (CB, IWT, IHT, 1), zero fill = conv padding
+    CUtensorMap tmS;       // src (C, IW, IH, N), box (CB, IWT, IHT, NB), zero fill = conv padding
     uint32_t TH, TWT;      // output rows / columns per tile
     uint32_t IHT, IWT;     // input rows / columns per tile
     uint32_t tiles_h, tiles_w, cblks;
     uint32_t spatial_tiles;      // N * tiles_h * tiles_w
     uint32_t RS, strips, units;  // rows per unit, column strips per tile, units per tile (<= 15)
+    uint32_t NB, spans, N;       // images per tile (small images: whole images side by side), row spans
     uint32_t stage_bytes, tile_bytes, stages;  // ring stride (128-byte aligned) / bytes one TMA box delivers
 };
 constexpr uint32_t DW3_COMPUTE_WARPS = 15;  // + 1 producer warp = 16 warps: 128 registers per thread
@@ -597,7 +598,7 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
                 tma_load_4d(
                         stage0 + st * q.stage_bytes, &q.tmS, bar_full + 8 * st,
                         static_cast<int32_t>(cblk * CB), static_cast<int32_t>(tw * q.TWT) * S - p.pad_w,
-                        static_cast<int32_t>(th * q.TH) * S - p.pad_h, static_cast<int32_t>(n));
+                        static_cast<int32_t>(th * q.TH) * S - p.pad_h, static_cast<int32_t>(n * q.NB));
             }
             __syncwarp();
             if (++st == q.stages) {
@@ -616,9 +617,9 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
     load_weights<KIND>(p, ch_ok ? c : 0, w, bias);
     const uint32_t u = warp * SUBS + sub;          // this thread's unit in every tile
     const bool has_unit = u < q.units;
-    const uint32_t strip = u % q.strips, span = u / q.strips;
+    const uint32_t strip = u % q.strips, span = (u / q.strips) % q.spans, img = u / (q.strips * q.spans);
     const uint32_t srow = q.IWT * PIX;                                  // bytes per tile row
-    const uint32_t unit_off = (span * q.RS * S * q.IWT + strip * TW * S) * PIX + cpl * 4;
+    const uint32_t unit_off = ((img * q.IHT + span * q.RS * S) * q.IWT + strip * TW * S) * PIX + cpl * 4;
     const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
     const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
     const uint32_t cstride = p.CP;                 // words between adjacent output pixels
@@ -626,7 +627,7 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
     uint32_t st = 0, ph = 0;
     for (uint32_t sp = sp0; sp < q.spatial_tiles; sp += sp_step) {
         const uint32_t tw = sp % q.tiles_w, r = sp / q.tiles_w;
-        const uint32_t th = r % q.tiles_h, n = r / q.tiles_h;
+        const uint32_t th = r % q.tiles_h, n = (r / q.tiles_h) * q.NB + img;
         mbar_wait(bar_full + 8 * st, ph);
         const uint32_t oh0 = th * q.TH + span * q.RS;
         uint32_t oh1 = oh0 + q.RS;
@@ -635,7 +636,7 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
         if (oh1 > p.OH)
             oh1 = p.OH;
         const uint32_t ow0 = tw * q.TWT + strip * TW;
-        if (has_unit && oh0 < oh1 && ow0 < p.OW) {
+        if (has_unit && oh0 < oh1 && ow0 < p.OW && n < q.N) {
             // next tile row to read (generic pointer into the staged tile; offsets fold into the LDS)
             const uint8_t* a = dsm + 128 + st * q.stage_bytes + unit_off;
             uint32_t cmask = 0;                                    // columns this thread stores
@@ -728,6 +729,220 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
     }
 }
 
+// ---------------------------------------------------------------- front end 3: bulk-copied row blocks
+// Channel counts whose pixels are not 16-byte multiples (ShuffleNetV2's 58 / 116) cannot go through a
+// tensor map, but full-width input rows of an NHWC image are ONE contiguous byte range, and it is
+// 16-byte aligned whenever IW * C * 2 is: a persistent CTA stages the rows of a tile (halo included,
+// clipped to the image) with a single cp.async.bulk per tile into a ring of stages, and the same window
+// code reads them with the padding masks of the global-memory front end.  Thread = (channel pair, unit):
+// the channel pair is fixed for the thread's life (weights in registers), units = column strip x row
+// span, walked in passes of floor(480 / CP) units.
+struct Dw3BulkParams {
+    Dw3Common c;
+    const uint8_t* src;
+    uint64_t src_bbytes;
+    uint32_t row_bytes;          // IW * C * 2: what one bulk copy delivers
+    uint32_t row_stride;         // (IW + 4) * C * 2: staged row = 4 zero pixels + the image row
+    uint32_t TH, RS, IHT;        // output rows per tile / per unit, input rows per tile
+    uint32_t strips, spans, U;   // units per tile = strips * spans, walked U at a time
+    uint32_t tiles_h, total_tiles;
+    uint32_t zrow_bytes, stage_bytes, stages, smem_bytes;
+};
+
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
+// Shared memory: [barriers 128 B][zero row][stages x IHT staged rows][4 zero pixels].  A staged row is
+// 4 zero pixels followed by the IW image pixels: the left padding column of a row is the pixel before
+// it, the right padding columns are the zero pixels of the next row, so the window code needs no column
+// masks; tap rows above / below the image read the zero row instead.
+template <int KIND, int S, int TW>
+__global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1) dw3x3_bulk_kernel(const Dw3BulkParams q) {
+    constexpr int IN = (TW - 1) * S + 3;
+    using namespace ptx;
+    const Dw3Common& p = q.c;
+    extern __shared__ __align__(128) uint8_t dsm[];
+    const uint32_t sbase = smem_u32(dsm);
+    const uint32_t bar_full = sbase, bar_empty = sbase + 64;
+    const uint32_t zrow = sbase + 128, stage0 = zrow + q.zrow_bytes;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t pix = p.CP * 4;
+    if (threadIdx.x == 0) {
+        for (uint32_t i = 0; i < q.stages; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, DW3_COMPUTE_WARPS);
+        }
+        fence_mbar_init();
+    }
+    // zero row, the 4 leading pixels of every staged row, the 4 trailing pixels (never written by copies)
+    for (uint32_t i = threadIdx.x * 4; i < q.zrow_bytes; i += blockDim.x * 4)
+        *reinterpret_cast<uint32_t*>(dsm + 128 + i) = 0u;
+    {
+        const uint32_t rows = q.stages * q.IHT + 1, padw = 4 * p.CP;  // words per pad
+        for (uint32_t i = threadIdx.x; i < rows * padw; i += blockDim.x) {
+            const uint32_t r = i / padw, wd = i % padw;
+            *reinterpret_cast<uint32_t*>(dsm + 128 + q.zrow_bytes + static_cast<size_t>(r) * q.row_stride + wd * 4) = 0u;
+        }
+    }
+    __syncthreads();
+    if (warp == DW3_COMPUTE_WARPS) {
+        uint32_t st = 0, ph = 0;
+        for (uint32_t t = blockIdx.x; t < q.total_tiles; t += gridDim.x) {
+            const uint32_t th = t % q.tiles_h, n = t / q.tiles_h;
+            const int32_t ih_lo = static_cast<int32_t>(th * q.TH) * S - p.pad_h;
+            const int32_t lo = ih_lo < 0 ? 0 : ih_lo;
+            int32_t hi = ih_lo + static_cast<int32_t>(q.IHT);
+            if (hi > static_cast<int32_t>(p.IH))
+                hi = static_cast<int32_t>(p.IH);
+            mbar_wait(bar_empty + 8 * st, ph ^ 1);
+            if (lane == 0)
+                mbar_arrive_expect_tx(bar_full + 8 * st, static_cast<uint32_t>(hi - lo) * q.row_bytes);
+            __syncwarp();
+            const uint8_t* img = q.src + n * q.src_bbytes;
+            for (int32_t ih = lo + static_cast<int32_t>(lane); ih < hi; ih += 32)
+                bulk_load_1d(
+                        stage0 + st * q.stage_bytes + static_cast<uint32_t>(ih - ih_lo) * q.row_stride + 4 * pix,
+                        img + static_cast<uint64_t>(ih) * q.row_bytes, q.row_bytes, bar_full + 8 * st);
+            __syncwarp();
+            if (++st == q.stages) {
+                st = 0;
+                ph ^= 1;
+            }
+        }
+        return;
+    }
+    const uint32_t cp = threadIdx.x % p.CP, u0 = threadIdx.x / p.CP;
+    const bool active = u0 < q.U;
+    float2 w[9], bias;
+    load_weights<KIND>(p, cp * 2, w, bias);
+    const uint32_t units = q.strips * q.spans;
+    const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
+    const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
+    const uint32_t cstride = p.CP, rstride = p.OW * p.CP;
+    uint32_t st = 0, ph = 0;
+    for (uint32_t t = blockIdx.x; t < q.total_tiles; t += gridDim.x) {
+        const uint32_t th = t % q.tiles_h, n = t / q.tiles_h;
+        const int32_t ih_lo = static_cast<int32_t>(th * q.TH) * S - p.pad_h;
+        mbar_wait(bar_full + 8 * st, ph);
+        if (active) {
+            for (uint32_t u = u0; u < units; u += q.U) {
+                const uint32_t strip = u % q.strips, span = u / q.strips;
+                const uint32_t oh0 = th * q.TH + span * q.RS;
+                uint32_t oh1 = oh0 + q.RS;
+                if (oh1 > (th + 1) * q.TH)
+                    oh1 = (th + 1) * q.TH;
+                if (oh1 > p.OH)
+                    oh1 = p.OH;
+                const uint32_t ow0 = strip * TW;
+                if (oh0 >= oh1)
+                    continue;
+                // column offset of the unit's first tap inside a staged row (4 zero pixels lead the row)
+                const uint32_t coff = (4u + ow0 * S - static_cast<uint32_t>(p.pad_w)) * pix + cp * 4;
+                uint32_t a = stage0 + st * q.stage_bytes + span * q.RS * S * q.row_stride + coff;
+                const uint32_t za = zrow + coff;
+                int32_t ih = ih_lo + static_cast<int32_t>(span * q.RS) * S;  // image row of the next tap row
+                uint32_t cmask = 0;
+#pragma unroll
+                for (int t2 = 0; t2 < TW; ++t2)
+                    cmask |= (ow0 + t2 < p.OW ? 1u : 0u) << t2;
+                uint32_t* drow = p.dst + n * p.dst_bwords + (static_cast<size_t>(oh0) * p.OW + ow0) * p.CP + cp;
+                const uint32_t* zrowp = p.z + n * p.z_bwords + (static_cast<size_t>(oh0) * p.OW + ow0) * p.CP + cp;
+                float2 buf[3][IN];
+                auto lds_row = [&](float2 (&dstrow)[IN]) {
+                    const uint32_t src_a = static_cast<uint32_t>(ih) < p.IH ? a : za;
+                    uint32_t raw[IN];
+#pragma unroll
+                    for (int j = 0; j < IN; ++j)
+                        raw[j] = lds_u32(src_a + j * pix);
+#pragma unroll
+                    for (int j = 0; j < IN; ++j)
+                        dstrow[j] = unpack2<KIND>(raw[j]);
+                    a += q.row_stride;
+                    ++ih;
+                };
+                lds_row(buf[0]);
+                if constexpr (S == 1)
+                    lds_row(buf[1]);
+                auto step = [&](auto TT, auto MM, auto BB) {
+                    constexpr int T = decltype(TT)::value, M = decltype(MM)::value, B = decltype(BB)::value;
+                    if constexpr (S == 2)
+                        lds_row(buf[M]);
+                    lds_row(buf[B]);
+                    float2 acc[TW];
+#pragma unroll
+                    for (int t2 = 0; t2 < TW; ++t2) {
+                        acc[t2] = bias;
+#pragma unroll
+                        for (int fw = 0; fw < 3; ++fw) {
+                            acc[t2] = __ffma2_rn(buf[T][t2 * S + fw], w[fw], acc[t2]);
+                            acc[t2] = __ffma2_rn(buf[M][t2 * S + fw], w[3 + fw], acc[t2]);
+                            acc[t2] = __ffma2_rn(buf[B][t2 * S + fw], w[6 + fw], acc[t2]);
+                        }
+                    }
+                    if (p.has_z) {
+#pragma unroll
+                        for (int t2 = 0; t2 < TW; ++t2)
+                            if ((cmask >> t2) & 1) {
+                                const float2 zf = unpack2<KIND>(__ldg(zrowp + t2 * cstride));
+                                acc[t2].x += zf.x, acc[t2].y += zf.y;
+                            }
+                        zrowp += rstride;
+                    }
+                    if (generic_act) {
+#pragma unroll
+                        for (int t2 = 0; t2 < TW; ++t2)
+                            acc[t2].x = act_generic(acc[t2].x, p.nonline), acc[t2].y = act_generic(acc[t2].y, p.nonline);
+                    } else {
+#pragma unroll
+                        for (int t2 = 0; t2 < TW; ++t2)
+                            acc[t2].x = fmaxf(acc[t2].x, act_lo), acc[t2].y = fmaxf(acc[t2].y, act_lo);
+                    }
+#pragma unroll
+                    for (int t2 = 0; t2 < TW; ++t2)
+                        if ((cmask >> t2) & 1)
+                            drow[t2 * cstride] = KIND == B200CB_DT_BF16 ? pack_bf16x2(acc[t2].x, acc[t2].y)
+                                                                        : pack_f16x2(acc[t2].x, acc[t2].y);
+                    drow += rstride;
+                };
+                using I0 = std::integral_constant<int, 0>;
+                using I1 = std::integral_constant<int, 1>;
+                using I2 = std::integral_constant<int, 2>;
+                uint32_t rows = oh1 - oh0;
+                while (true) {
+                    step(I0{}, I1{}, I2{});
+                    if (--rows == 0) break;
+                    if constexpr (S == 1) {
+                        step(I1{}, I2{}, I0{});
+                        if (--rows == 0) break;
+                        step(I2{}, I0{}, I1{});
+                    } else {
+                        step(I2{}, I0{}, I1{});
+                        if (--rows == 0) break;
+                        step(I1{}, I2{}, I0{});
+                    }
+                    if (--rows == 0) break;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(bar_empty + 8 * st);
+        if (++st == q.stages) {
+            st = 0;
+            ph ^= 1;
+        }
+    }
+}
+
+// experiment knobs (tools/): integer environment override with a default
+int env_flag(const char* name, int dflt) {
+    const char* e = getenv(name);
+    return e ? atoi(e) : dflt;
+}
+
 bool dw3_applicable(const b200cb_desc& d) {
     return (d.src_dtype == B200CB_DT_BF16 || d.src_dtype == B200CB_DT_F16) && d.fh == 3 && d.fw == 3 &&
            d.stride_h == d.stride_w && (d.stride_h == 1 || d.stride_h == 2) && d.dilate_h == 1 &&
@@ -736,6 +951,78 @@ bool dw3_applicable(const b200cb_desc& d) {
 }
 bool dw3_tma_applicable(const b200cb_desc& d) {
     return dw3_applicable(d) && d.ic % 8 == 0 && (d.src_batch_stride * 2) % 16 == 0 && d.pad_h <= 8 && d.pad_w <= 8;
+}
+
+bool dw3_bulk_applicable(const b200cb_desc& d) {
+    const uint64_t row = (uint64_t)d.iw * d.ic * 2;
+    return dw3_applicable(d) && row % 16 == 0 && (d.src_batch_stride * 2) % 16 == 0 && d.pad_h <= 1 &&
+           d.pad_w <= 1 && d.ic / 2 <= DW3_COMPUTE_WARPS * 32 && 3 * (row + 8 * d.ic) <= 100 * 1024;
+}
+
+template <int KIND>
+int launch_dw3_bulk(const b200cb_desc& d, const Dw3Common& c, const void* src, cudaStream_t stream) {
+    if (reinterpret_cast<uintptr_t>(src) % 16)
+        return B200CB_UNSUPPORTED_SHAPE;  // falls through to the global-memory front end
+    Dw3BulkParams q;
+    memset(&q, 0, sizeof(q));
+    q.c = c;
+    q.src = static_cast<const uint8_t*>(src);
+    q.src_bbytes = (d.src_batch_stride ? d.src_batch_stride : (uint64_t)d.ih * d.iw * d.ic) * 2;
+    q.row_bytes = d.iw * d.ic * 2;
+    q.row_stride = (d.iw + 4) * d.ic * 2;
+    const uint32_t pix = d.ic * 2;
+    const uint32_t S = d.stride_h, TW = S == 1 ? 4 : 2;
+    q.strips = (d.ow + TW - 1) / TW;
+    q.U = DW3_COMPUTE_WARPS * 32 / (d.ic / 2);
+    uint32_t spans = q.strips >= q.U ? 1 : q.U / q.strips;
+    if (spans > d.oh)
+        spans = d.oh;
+    // rows per unit from the stage budget (3 stages of <= 64 KiB, else 2 of <= 100 KiB), then balanced
+    // over the tiles of one image
+    uint32_t budget = 64 * 1024;
+    if (3 * q.row_stride > budget)
+        budget = 100 * 1024;
+    if (((spans - 1) * S + 3) * (uint64_t)q.row_stride > budget)
+        spans = 1;
+    uint32_t rs_max = 1;
+    while (((spans * (rs_max + 1) - 1) * S + 3) * (uint64_t)q.row_stride <= budget && spans * rs_max < d.oh)
+        ++rs_max;
+    const uint32_t th_max = spans * rs_max;
+    q.tiles_h = (d.oh + th_max - 1) / th_max;
+    const uint32_t th_need = (d.oh + q.tiles_h - 1) / q.tiles_h;
+    q.RS = (th_need + spans - 1) / spans;
+    q.spans = spans;
+    q.TH = spans * q.RS;
+    q.IHT = (q.TH - 1) * S + 3;
+    q.tiles_h = (d.oh + q.TH - 1) / q.TH;
+    const uint64_t total = (uint64_t)d.n * q.tiles_h;
+    if (total > 0x7fffffffull)
+        return B200CB_UNSUPPORTED_SHAPE;
+    q.total_tiles = (uint32_t)total;
+    q.zrow_bytes = q.row_stride;     // followed by the zero pixels of stage 0's first row
+    q.stage_bytes = q.IHT * q.row_stride;
+    const uint32_t fixed = 128 + q.zrow_bytes + 4 * pix;
+    if (fixed + 2 * q.stage_bytes > MAX_DYN_SMEM)
+        return B200CB_UNSUPPORTED_SHAPE;
+    q.stages = (MAX_DYN_SMEM - fixed) / q.stage_bytes;
+    if (q.stages > 4)
+        q.stages = 4;
+    q.smem_bytes = fixed + q.stages * q.stage_bytes;
+    const uint32_t sms = (uint32_t)device_sm_count();
+    const uint32_t grid = total < sms ? (uint32_t)total : sms;
+    auto go = [&](auto kern) -> cudaError_t {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM);
+        if (e != cudaSuccess)
+            return e;
+        kern<<<grid, (DW3_COMPUTE_WARPS + 1) * 32, q.smem_bytes, stream>>>(q);
+        return cudaGetLastError();
+    };
+    const cudaError_t e = S == 1 ? go(dw3x3_bulk_kernel<KIND, 1, 4>) : go(dw3x3_bulk_kernel<KIND, 2, 2>);
+    if (e != cudaSuccess) {
+        set_last_error("dw3x3 bulk launch", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    return B200CB_OK;
 }
 
 template <int KIND>
@@ -783,7 +1070,11 @@ int launch_dw3_tma(const b200cb_desc& d, const Dw3Common& c, const void* src, cu
     memset(&q, 0, sizeof(q));
     q.c = c;
     const uint32_t S = d.stride_h, TW = S == 1 ? 4 : 2;
-    const uint32_t CB = d.ic > 32 ? 64 : 32, CPB = CB / 2, SUBS = 32 / CPB;
+    // channel block: 64 channels per warp, or 32 (two units per warp) when that pads the channel count less
+    uint32_t CB = d.ic > 32 ? 64 : 32;
+    if (env_flag("B200CB_DW_CB32", 1) && (d.ic + 31) / 32 * 32 < (d.ic + 63) / 64 * 64)
+        CB = 32;
+    const uint32_t CPB = CB / 2, SUBS = 32 / CPB;
     // column strips per tile: 7 (28 / 14 output columns) divides the MobileNet widths; small images
     // take their whole width.  One unit per compute warp (x SUBS): spans = floor(15 * SUBS / strips).
     const uint32_t strips_full = (d.ow + TW - 1) / TW;
@@ -800,20 +1091,38 @@ int launch_dw3_tma(const b200cb_desc& d, const Dw3Common& c, const void* src, cu
     uint32_t rs = (d.oh + spans - 1) / spans;
     while (rs > 1 && ((spans * rs - 1) * S + 3) * q.IWT * CB * 2 > budget)
         --rs;
+    q.NB = 1;
+    if (spans * rs >= d.oh && q.TWT >= d.ow) {
+        // the whole image fits in one tile: give every unit a full-height strip and put several images
+        // side by side in the tile (a 7 x 7 image alone is 10 KiB and one output row per unit)
+        const uint32_t img_bytes = ((d.oh - 1) * S + 3) * q.IWT * CB * 2;
+        uint32_t nb = DW3_COMPUTE_WARPS * SUBS / q.strips;
+        if (nb > budget / img_bytes)
+            nb = budget / img_bytes;
+        if (nb > d.n)
+            nb = d.n;
+        if (nb >= 2 && env_flag("B200CB_DW_NB", 1)) {
+            q.NB = nb;
+            spans = 1;
+            rs = d.oh;
+        }
+    }
     q.RS = rs;
+    q.spans = spans;
+    q.N = d.n;
     q.TH = spans * rs;
-    q.units = q.strips * spans;
+    q.units = q.strips * spans * q.NB;
     q.IHT = (q.TH - 1) * S + 3;
     if (q.IHT > 256 || q.IWT > 256 || q.units > DW3_COMPUTE_WARPS * SUBS)
         return B200CB_UNSUPPORTED_SHAPE;
     q.tiles_h = (d.oh + q.TH - 1) / q.TH;
     q.tiles_w = (d.ow + q.TWT - 1) / q.TWT;
     q.cblks = (d.ic + CB - 1) / CB;
-    const uint64_t spatial = (uint64_t)d.n * q.tiles_h * q.tiles_w;
+    const uint64_t spatial = (uint64_t)((d.n + q.NB - 1) / q.NB) * q.tiles_h * q.tiles_w;
     if (spatial > 0x7fffffffull)
         return B200CB_UNSUPPORTED_SHAPE;
     q.spatial_tiles = (uint32_t)spatial;
-    q.tile_bytes = q.IHT * q.IWT * CB * 2;
+    q.tile_bytes = q.NB * q.IHT * q.IWT * CB * 2;
     q.stage_bytes = (q.tile_bytes + 127) & ~127u;
     q.stages = (MAX_DYN_SMEM - 128) / q.stage_bytes;
     if (q.stages > 4)
@@ -823,7 +1132,7 @@ int launch_dw3_tma(const b200cb_desc& d, const Dw3Common& c, const void* src, cu
     const uint64_t src_b = d.src_batch_stride ? d.src_batch_stride : (uint64_t)d.ih * d.iw * d.ic;
     uint64_t dims[4] = {d.ic, d.iw, d.ih, d.n};
     uint64_t strides[3] = {(uint64_t)d.ic * 2, (uint64_t)d.iw * d.ic * 2, src_b * 2};
-    uint32_t box[4] = {CB, q.IWT, q.IHT, 1};
+    uint32_t box[4] = {CB, q.IWT, q.IHT, q.NB};
     CUresult cr = encode_tiled(
             &q.tmS, KIND == B200CB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
             src, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
@@ -973,6 +1282,12 @@ int dwconv_launch(
         if (dw3_tma_applicable(d) && plan.reserved[2] != 2) {  // reserved[2] == 2: force the register front end
             int rc = d.src_dtype == B200CB_DT_BF16 ? launch_dw3_tma<B200CB_DT_BF16>(d, c, src, stream)
                                                    : launch_dw3_tma<B200CB_DT_F16>(d, c, src, stream);
+            if (rc != B200CB_UNSUPPORTED_SHAPE)
+                return rc;
+        }
+        if (dw3_bulk_applicable(d) && plan.reserved[2] != 2 && env_flag("B200CB_DW_BULK", 1)) {
+            int rc = d.src_dtype == B200CB_DT_BF16 ? launch_dw3_bulk<B200CB_DT_BF16>(d, c, src, stream)
+                                                   : launch_dw3_bulk<B200CB_DT_F16>(d, c, src, stream);
             if (rc != B200CB_UNSUPPORTED_SHAPE)
                 return rc;
         }

@@ -122,6 +122,13 @@ __device__ __forceinline__ void tma_load_4d(
             "l"(reinterpret_cast<uint64_t>(tmap)), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
             : "memory");
 }
+// plain bulk copy (no tensor map): `bytes` contiguous bytes, 16-byte aligned on both sides
+__device__ __forceinline__ void bulk_load_1d(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+            "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+            "l"(reinterpret_cast<uint64_t>(src)), "r"(bytes), "r"(bar)
+            : "memory");
+}
 // im2col mode, NHWC tensor seen as (C, W, H, N): coordinates are the channel start and the
 // *base pixel* (top-left tap of the window, may be negative); {off_w, off_h} select the tap.
 __device__ __forceinline__ void tma_load_im2col_4d(

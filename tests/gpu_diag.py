@@ -115,8 +115,21 @@ def stage_cases(stage):
                 ("dw3_tma_c24_s2", K.dw_desc("bf16", 3, 24, 30, 30, 2), {}),
                 ("dw3_tma_c16", K.dw_desc("bf16", 2, 16, 20, 20, 1, has_z=True), {}),
                 ("dw3_tma_c8_wide", K.dw_desc("f16", 1, 8, 9, 130, 1), {}),
-                ("dw3_reg_c58", K.dw_desc("bf16", 2, 58, 28, 28, 1), {}),
-                ("dw3_reg_c116_s2_z", K.dw_desc("f16", 2, 116, 28, 28, 2, has_z=True), {})]
+                # small images: several whole images per tile (ragged last tile: N not a multiple)
+                ("dw3_tma_7x7_n3", K.dw_desc("bf16", 3, 64, 7, 7, 1), {}),
+                ("dw3_tma_7x7_n11_z", K.dw_desc("f16", 11, 136, 7, 7, 1, has_z=True), {}),
+                ("dw3_tma_14s2_n5", K.dw_desc("bf16", 5, 72, 14, 14, 2, nonline=3), {}),
+                ("dw3_tma_5x6_n9_c32", K.dw_desc("bf16", 9, 32, 5, 6, 1), {}),
+                # pixels that are not 16-byte multiples: bulk-copied row blocks when the rows are 16-byte
+                # multiples (several tiles per image, ragged spans, stride 2, z), else the register front end
+                ("dw3_bulk_c58", K.dw_desc("bf16", 2, 58, 28, 28, 1), {}),
+                ("dw3_bulk_c116_s2_z", K.dw_desc("f16", 2, 116, 28, 28, 2, has_z=True), {}),
+                ("dw3_bulk_c116_56", K.dw_desc("bf16", 2, 116, 56, 56, 1, nonline=3), {}),
+                ("dw3_bulk_c36_22x30_s2_z", K.dw_desc("bf16", 3, 36, 22, 30, 2, has_z=True), {}),
+                ("dw3_bulk_c58_56_s2", K.dw_desc("f16", 5, 58, 56, 56, 2), {}),
+                ("dw3_bulk_c6_3x8", K.dw_desc("bf16", 2, 6, 3, 8, 1), {}),
+                ("dw3_reg_c58_14", K.dw_desc("bf16", 2, 58, 14, 14, 1), {}),
+                ("dw3_reg_c116_15_s2_z", K.dw_desc("f16", 2, 116, 15, 15, 2, has_z=True), {})]
         return out
     raise SystemExit("unknown stage " + stage)
 

@@ -95,8 +95,8 @@ def main():
         for c, h, w, s in K.MOBILENETV2_DW + SHUFFLENET_DW:
             if args.dtype == "qs8" and c % 16:
                 continue
-            if c % 8:
-                continue  # 16-byte channel vectors (58, 116 * ... are padded by the layout pass upstream)
+            if args.dtype == "f32" and c % 4:
+                continue
             descs.append(K.dw_desc(args.dtype, args.batch, c, h, w, s))
     elif args.set == "pw":
         for oc, ic, h, w in MOBILENET_PW:
@@ -116,6 +116,16 @@ def main():
     summary = {"set": args.set, "dtype": args.dtype, "batch": args.batch, "layers": len(ok), "total_ms": round(tot_ms, 4),
                "total_gbs": round(tot_b / tot_ms / 1e6, 1), "frac_hbm": round(tot_b / tot_ms / 1e6 / peaks["hbm_gbs"], 3),
                "peak_hbm_gbs": peaks["hbm_gbs"]}
+    if args.set == "dw":
+        # per-network aggregates: MobileNetV2 (channel counts in 16-byte pixels, TMA-staged kernel) and
+        # ShuffleNetV2-1x (58 / 116 channels are not 16-byte rows: register-path kernel)
+        nm = len([1 for c, _h, _w, _s in K.MOBILENETV2_DW if not (args.dtype == "qs8" and c % 16)])
+        for name, part in (("mobilenetv2", rows[:nm]), ("shufflenetv2", rows[nm:])):
+            part = [r for r in part if "ms" in r]
+            if part:
+                b, ms = sum(r["bytes"] for r in part), sum(r["ms"] for r in part)
+                summary[name] = {"layers": len(part), "total_ms": round(ms, 4), "total_gbs": round(b / ms / 1e6, 1),
+                                 "frac_hbm": round(b / ms / 1e6 / peaks["hbm_gbs"], 3)}
     print(json.dumps(summary), flush=True)
     if args.out:
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
