@@ -584,10 +584,14 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
         fence_mbar_init();
     }
     __syncthreads();
+    // programmatic dependent launch: the next kernel's CTAs may take this SM as soon as it is free; this
+    // one touches activations (src / z / dst) only after the kernel before it has completed
+    pdl_launch_dependents();
     // gridDim.x is a multiple of cblks: this CTA's channel block never changes
     const uint32_t cblk = blockIdx.x % q.cblks;
     const uint32_t sp0 = blockIdx.x / q.cblks, sp_step = gridDim.x / q.cblks;
     if (warp == DW3_COMPUTE_WARPS) {
+        pdl_wait();
         uint32_t st = 0, ph = 0;
         for (uint32_t sp = sp0; sp < q.spatial_tiles; sp += sp_step) {
             const uint32_t tw = sp % q.tiles_w, r = sp / q.tiles_w;
@@ -614,7 +618,8 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
     const uint32_t c = cblk * CB + cpl * 2;
     const bool ch_ok = c < p.C;
     float2 w[9], bias;
-    load_weights<KIND>(p, ch_ok ? c : 0, w, bias);
+    load_weights<KIND>(p, ch_ok ? c : 0, w, bias);   // constants: read before the dependency wait
+    pdl_wait();
     const uint32_t u = warp * SUBS + sub;          // this thread's unit in every tile
     const bool has_unit = u < q.units;
     const uint32_t strip = u % q.strips, span = (u / q.strips) % q.spans, img = u / (q.strips * q.spans);
@@ -788,7 +793,9 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1) dw3x3_bulk_ke
         }
     }
     __syncthreads();
+    pdl_launch_dependents();
     if (warp == DW3_COMPUTE_WARPS) {
+        pdl_wait();
         uint32_t st = 0, ph = 0;
         for (uint32_t t = blockIdx.x; t < q.total_tiles; t += gridDim.x) {
             const uint32_t th = t % q.tiles_h, n = t / q.tiles_h;
@@ -818,6 +825,7 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1) dw3x3_bulk_ke
     const bool active = u0 < q.U;
     float2 w[9], bias;
     load_weights<KIND>(p, cp * 2, w, bias);
+    pdl_wait();
     const uint32_t units = q.strips * q.spans;
     const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
     const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
@@ -943,6 +951,24 @@ int env_flag(const char* name, int dflt) {
     return e ? atoi(e) : dflt;
 }
 
+// launch with programmatic stream serialization (the kernels above call griddepcontrol themselves)
+template <class Kern, class Params>
+cudaError_t launch_pdl(Kern kern, uint32_t grid, uint32_t threads, uint32_t smem, cudaStream_t stream, const Params& q) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid, 1, 1);
+    cfg.blockDim = dim3(threads, 1, 1);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    static const bool use_pdl = getenv("B200CB_NO_PDL") == nullptr;
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, q);
+}
+
 bool dw3_applicable(const b200cb_desc& d) {
     return (d.src_dtype == B200CB_DT_BF16 || d.src_dtype == B200CB_DT_F16) && d.fh == 3 && d.fw == 3 &&
            d.stride_h == d.stride_w && (d.stride_h == 1 || d.stride_h == 2) && d.dilate_h == 1 &&
@@ -1014,8 +1040,7 @@ int launch_dw3_bulk(const b200cb_desc& d, const Dw3Common& c, const void* src, c
         cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM);
         if (e != cudaSuccess)
             return e;
-        kern<<<grid, (DW3_COMPUTE_WARPS + 1) * 32, q.smem_bytes, stream>>>(q);
-        return cudaGetLastError();
+        return launch_pdl(kern, grid, (DW3_COMPUTE_WARPS + 1) * 32, q.smem_bytes, stream, q);
     };
     const cudaError_t e = S == 1 ? go(dw3x3_bulk_kernel<KIND, 1, 4>) : go(dw3x3_bulk_kernel<KIND, 2, 2>);
     if (e != cudaSuccess) {
@@ -1059,8 +1084,7 @@ cudaError_t launch_dw3_tma_variant(const Dw3TmaParams& q, uint32_t grid, uint32_
             return e;
         attr_set[dev] = true;
     }
-    kern<<<grid, (DW3_COMPUTE_WARPS + 1) * 32, smem, stream>>>(q);
-    return cudaGetLastError();
+    return launch_pdl(kern, grid, (DW3_COMPUTE_WARPS + 1) * 32, smem, stream, q);
 }
 
 // tile geometry + tensor map of the TMA front end
