@@ -944,6 +944,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                 arrive_tempty(bar_tempty + 8 * acc);
                         }
                     }
+                    if (col0 + h * 32 >= p.OC)
+                        continue;  // 32 columns entirely past OC (OC = 16 / 96 / 144 ...): the store clips them
                     const uint32_t (&r)[32] = rr[h % HB];
                     const uint32_t* bcol = sbias + c * T::EPI_N + h * 32;
                     constexpr uint32_t COLS_PER_16B = 16 / T::OUT_ES;

@@ -36,9 +36,10 @@ def rand(shape, dt, lo=-8, hi=8):
     return torch.randn(shape, dtype=torch.float32, device="cuda").to(dt)
 
 
-def time_desc(lib, d, reps, peaks):
+def time_desc(lib, d, reps, peaks, algo=-1):
     plan = C.Plan()
-    rc = lib.b200cb_query(ctypes.byref(d), ctypes.byref(plan))
+    rc = lib.b200cb_query(ctypes.byref(d), ctypes.byref(plan)) if algo < 0 else \
+        lib.b200cb_query_algo(ctypes.byref(d), algo, ctypes.byref(plan))
     if rc != 0:
         return {"desc": K.desc_str(d), "error": lib.b200cb_strerror(rc).decode()}
     sdt, ddt = TORCH_DT[d.src_dtype], TORCH_DT[d.dst_dtype]
@@ -85,6 +86,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--reps", type=int, default=50)
     ap.add_argument("--out", default="")
+    ap.add_argument("--algo", type=int, default=-1, help="force an algorithm index (default: heuristic)")
     args = ap.parse_args()
     lib = C.load()
     pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(
@@ -108,7 +110,7 @@ def main():
             descs.append(K.resnet50_desc(layer, args.dtype, args.batch, ic_pad=16 if args.dtype == "qs8" else 8))
     rows = []
     for d in descs:
-        r = time_desc(lib, d, args.reps, peaks)
+        r = time_desc(lib, d, args.reps, peaks, args.algo)
         rows.append(r)
         print(json.dumps(r), flush=True)
     ok = [r for r in rows if "ms" in r]

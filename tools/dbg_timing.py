@@ -16,10 +16,15 @@ lib = C.load()
 kind = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 only = set(sys.argv[2:])
 names = ["empty", "tempty", "full", "tfull", "zfull", "zempty", "bres", "stwait"]
-for layer in K.RESNET50_LAYERS:
-    if only and layer[0] not in only:
-        continue
-    d = K.resnet50_desc(layer, kind, 256, ic_pad=8 if kind == "qs8" else 4)
+# "pw" as the only layer name: the MobileNet pointwise table (tools/bench_layers.py) instead of ResNet-50
+if only == {"pw"}:
+    from tools.bench_layers import MOBILENET_PW
+    work = [(("pw_%dto%d_%d" % (ic, oc, h),), K.make_desc(kind, 256, ic, h, w, oc, 1, nonline=C.NL_RELU))
+            for oc, ic, h, w in MOBILENET_PW]
+else:
+    work = [(layer, K.resnet50_desc(layer, kind, 256, ic_pad=8 if kind == "qs8" else 4))
+            for layer in K.RESNET50_LAYERS if not only or layer[0] in only]
+for layer, d in work:
     plan = C.Plan()
     assert lib.b200cb_query(ctypes.byref(d), ctypes.byref(plan)) == 0
     tdt = torch.int8 if kind == "qs8" else torch.bfloat16

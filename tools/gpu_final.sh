@@ -15,6 +15,7 @@ timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__byte
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:igemm -s 159 -c 5 -f -o gpurun_out/prof_l1 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l1.log 2>&1; echo ncu2=$?
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:igemm -s 192 -c 3 -f -o gpurun_out/prof_l3 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l3.log 2>&1; echo ncu3=$?
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:dw3x3 -s 4 -c 2 -f -o gpurun_out/prof_dw3 python tools/dw_one.py 96 112 112 2 bf16 4 > gpurun_out/ncu_dw3.log 2>&1; echo ncu4=$?
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:dw3x3 -s 4 -c 1 -f -o gpurun_out/prof_dwbulk python tools/dw_one.py 58 56 56 2 bf16 4 > gpurun_out/ncu_dwbulk.log 2>&1; echo ncu5=$?
 python - <<'PY'
 import json
 for f in ['bf16','qs8','f16','bf16_ic8']:
