@@ -16,6 +16,13 @@ timeout 900 ncu --set full --clock-control none --import-source on -k regex:igem
 timeout 900 ncu --set full --clock-control none --import-source on -k regex:igemm -s 192 -c 3 -f -o gpurun_out/prof_l3 python bench.py --steps 2 --warmup 3 --no-cpu-baseline > gpurun_out/ncu_l3.log 2>&1; echo ncu3=$?
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:dw3x3 -s 4 -c 2 -f -o gpurun_out/prof_dw3 python tools/dw_one.py 96 112 112 2 bf16 4 > gpurun_out/ncu_dw3.log 2>&1; echo ncu4=$?
 timeout 300 ncu --set full --clock-control none --import-source on -k regex:dw3x3 -s 4 -c 1 -f -o gpurun_out/prof_dwbulk python tools/dw_one.py 58 56 56 2 bf16 4 > gpurun_out/ncu_dwbulk.log 2>&1; echo ncu5=$?
+# the reports are too large to travel back (gpurun_out/ is capped at 64 MiB): condense them here
+python tools/ncu_summary.py gpurun_out/prof_l1.ncu-rep conv1 l1.b0.c1 l1.c2 l1.ds l1.c3 > gpurun_out/ncu_igemm_l1_summary.txt 2>&1
+python tools/ncu_summary.py gpurun_out/prof_l3.ncu-rep l3.bN.c1 l3.bN.c2 l3.bN.c3 > gpurun_out/ncu_igemm_l3_pair_summary.txt 2>&1
+python tools/ncu_summary.py gpurun_out/prof_dw3.ncu-rep "dw 96x112x112 s2 bf16" "dw 96x112x112 s2 bf16" > gpurun_out/ncu_dw3x3_summary.txt 2>&1
+python tools/ncu_summary.py gpurun_out/prof_dwbulk.ncu-rep "dw 58x56x56 s2 bf16 (bulk rows)" >> gpurun_out/ncu_dw3x3_summary.txt 2>&1
+rm -f gpurun_out/prof_l1.ncu-rep gpurun_out/prof_l3.ncu-rep gpurun_out/prof_dw3.ncu-rep
+du -sh gpurun_out
 python - <<'PY'
 import json
 for f in ['bf16','qs8','f16','bf16_ic8']:
