@@ -1037,9 +1037,17 @@ int launch_dw3_bulk(const b200cb_desc& d, const Dw3Common& c, const void* src, c
     const uint32_t sms = (uint32_t)device_sm_count();
     const uint32_t grid = total < sms ? (uint32_t)total : sms;
     auto go = [&](auto kern) -> cudaError_t {
-        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM);
-        if (e != cudaSuccess)
-            return e;
+        // (both stride variants have the same function type: the flag is keyed by device AND stride)
+        static bool attr_set[64][2] = {{false}};
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (dev < 0 || dev >= 64 || !attr_set[dev][S - 1]) {
+            cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM);
+            if (e != cudaSuccess)
+                return e;
+            if (dev >= 0 && dev < 64)
+                attr_set[dev][S - 1] = true;
+        }
         return launch_pdl(kern, grid, (DW3_COMPUTE_WARPS + 1) * 32, q.smem_bytes, stream, q);
     };
     const cudaError_t e = S == 1 ? go(dw3x3_bulk_kernel<KIND, 1, 4>) : go(dw3x3_bulk_kernel<KIND, 2, 2>);
