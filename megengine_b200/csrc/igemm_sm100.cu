@@ -831,8 +831,17 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 zphase ^= 1;
             }
         };
-        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
-            const uint32_t m_blk = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
+        // (m, n) tile indices advance incrementally: a division per tile is a ~25-instruction MUFU chain on
+        // the critical path of short tiles (10 % of the low-K pointwise layers' samples)
+        uint32_t tq = cl_id / p.n_tiles, tr = cl_id % p.n_tiles;
+        const uint32_t dq = cl_num / p.n_tiles, dr = cl_num % p.n_tiles, ntl = p.n_tiles;
+        auto next_tile = [&]() {
+            tq += dq, tr += dr;
+            if (tr >= ntl)
+                tr -= ntl, ++tq;
+        };
+        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num, next_tile()) {
+            const uint32_t m_blk = tq * C + crank, n_blk = tr;
             if (TILE_SPLIT && acc != group) {
                 // the other group's tile (it has one z chunk unless it is a phantom tile)
                 if (m_blk < p.m_tiles)
@@ -905,8 +914,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 #ifdef B200CB_DEBUG_TIMING
                 const long long tsw__ = clock64();
 #endif
+                // (elect.sync is deterministic for a given member mask: the same lane commits and waits
+                // on the bulk groups, and the compiler emits plain UTMASTG instead of a per-lane R2UR loop)
                 if (!p.has_z) {
-                    if (lane == 0)
+                    if (elect_one())
                         tma_store_wait_read<NSLAB - 1>();
                     __syncwarp();
                 }
@@ -1144,7 +1155,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 }
                 fence_proxy_async_smem();
                 __syncwarp();
-                if (lane == 0) {
+                if (elect_one()) {
                     if (stem)
                         tma_store_3d(
                                 &p.tmD, st_src, static_cast<int32_t>(col0),
@@ -1167,7 +1178,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             if (acc == 0)
                 acc_phase ^= 1;
         }
-        if (lane == 0)
+        if (elect_one())
             tma_store_wait<0>();
     }
 

@@ -128,6 +128,12 @@ def stage_cases(stage):
                 ("dw3_bulk_c36_22x30_s2_z", K.dw_desc("bf16", 3, 36, 22, 30, 2, has_z=True), {}),
                 ("dw3_bulk_c58_56_s2", K.dw_desc("f16", 5, 58, 56, 56, 2), {}),
                 ("dw3_bulk_c6_3x8", K.dw_desc("bf16", 2, 6, 3, 8, 1), {}),
+                # no padding (valid convolution) through the three front ends
+                ("dw3_tma_pad0", K.make_desc("bf16", 2, 64, 12, 12, 64, 3, stride=1, pad=0, group=64, nonline=1), {}),
+                ("dw3_tma_pad0_s2", K.make_desc("f16", 3, 40, 13, 13, 40, 3, stride=2, pad=0, group=40, nonline=1), {}),
+                ("dw3_bulk_pad0_s2", K.make_desc("bf16", 2, 36, 11, 16, 36, 3, stride=2, pad=0, group=36, nonline=1), {}),
+                ("dw3_bulk_pad0", K.make_desc("bf16", 2, 12, 9, 8, 12, 3, stride=1, pad=0, group=12, nonline=1, has_z=True), {}),
+                ("dw3_reg_pad0", K.make_desc("bf16", 2, 58, 9, 9, 58, 3, stride=1, pad=0, group=58, nonline=1), {}),
                 ("dw3_reg_c58_14", K.dw_desc("bf16", 2, 58, 14, 14, 1), {}),
                 ("dw3_reg_c116_15_s2_z", K.dw_desc("f16", 2, 116, 15, 15, 2, has_z=True), {})]
         return out
