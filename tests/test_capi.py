@@ -78,6 +78,22 @@ def test_query_mobilenet_depthwise_supported(lib):
             assert rc == 0 and lib.b200cb_algo_name(p.algo) == b"B200_DWCONV_DIRECT"
 
 
+def test_query_shufflenet_depthwise_channel_counts(lib):
+    """ShuffleNetV2-1x depthwise layers: 58 / 116 channels are not 16-byte pixels; the
+    16-bit kinds take them (bulk-row / register front ends), QuantizedS8 and fp32 need whole 16-byte vectors."""
+    shapes = [(24, 56, 56, 2), (58, 56, 56, 2), (58, 28, 28, 1), (116, 28, 28, 2), (116, 14, 14, 1),
+              (232, 14, 14, 2), (232, 7, 7, 1)]
+    for kind in ("bf16", "f16"):
+        for c, h, w, s in shapes:
+            rc, p = _query(lib, K.dw_desc(kind, 256, c, h, w, s))
+            assert rc == 0 and lib.b200cb_algo_name(p.algo) == b"B200_DWCONV_DIRECT", (kind, c)
+            assert p.workspace_bytes == 0 and lib.b200cb_plan_num_launches(ctypes.byref(p)) == 1
+            assert p.bytes == 2 * 256 * c * (h * w + (h // s) * (w // s)) + 2 * c * 9 + 2 * c
+    assert _query(lib, K.dw_desc("qs8", 256, 58, 28, 28, 1))[0] > 0
+    assert _query(lib, K.dw_desc("f32", 256, 58, 28, 28, 1))[0] > 0
+    assert _query(lib, K.dw_desc("bf16", 256, 57, 28, 28, 1))[0] > 0   # odd channel count: no channel pairs
+
+
 def test_unsupported_cells_are_rejected_not_silently_wrong(lib):
     """everything outside the supported-cell matrix must come back > 0 (is_available false)."""
     ok = K.make_desc("bf16", 2, 64, 14, 14, 64, 3, pad=1)
