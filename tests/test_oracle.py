@@ -103,6 +103,12 @@ def _sweep_cases():
                 out.append(K.make_desc(kind, 1, 8, 7, 7, 12, 3, pad=1, group=4, fmt=fmt))
                 out.append(K.make_desc(kind, 1, 4, 7, 7, 4, 3, pad=1, mode=1, fmt=fmt))
                 out.append(K.make_desc(kind, 1, 4, 9, 9, 4, 3, pad=2, dilate=2, fmt=fmt, has_z=True))
+            # depthwise 3x3 as the GPU parity cases run it (get_chanwise_args, dnn/test/cuda/conv_bias.cpp:650-714):
+            # channel counts that are not vector multiples, stride 2 on odd extents, no padding, z
+            if fmt == C.FORMAT_NHWC and kind in ("f16", "bf16"):
+                out.append(K.make_desc(kind, 3, 58, 9, 8, 58, 3, stride=1, pad=1, group=58, fmt=fmt, nonline=1))
+                out.append(K.make_desc(kind, 2, 36, 11, 16, 36, 3, stride=2, pad=0, group=36, fmt=fmt, nonline=1, has_z=True))
+                out.append(K.make_desc(kind, 2, 12, 9, 8, 12, 3, stride=1, pad=0, group=12, fmt=fmt, nonline=3))
     return out
 
 
