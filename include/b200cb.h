@@ -155,6 +155,29 @@ int b200cb_exec_host(
         const b200cb_plan* plan, const void* src, const void* filter, const void* bias,
         const void* z, void* dst, void* dev_scratch, size_t dev_scratch_bytes, void* stream);
 
+/* First-class layout operators either side of the path: what megdnn's RelayoutFormat
+ * (dnn/include/megdnn/oprs/general.h RelayoutFormat, modes param::RelayoutFormat::Mode in
+ * dnn/scripts/opr_param_defs.py; CUDA kernels dnn/src/cuda/relayout_format/) and gopt's channel padding
+ * (src/gopt/impl/padding_channel.cpp) put around an NHWC / NCHW4 ConvBias.  `c` = channels of src, `c_out` =
+ * channels of dst (>= c: zero padded; NCHW4 sides need multiples of 4); dense tensors; enqueue only.
+ *   NCHW_NHWC   (n,c,h,w)      -> (n,h,w,c_out)        NHWC_NCHW   (n,h,w,c)     -> (n,c_out,h,w)
+ *   NCHW_NCHW4  (n,c,h,w)      -> (n,c_out/4,h,w,4)    NCHW4_NCHW  (n,c/4,h,w,4) -> (n,c_out,h,w)  (c_out <= c: drops padding)
+ *   NCHW4_NHWC  (n,c/4,h,w,4)  -> (n,h,w,c_out)        NHWC_NCHW4  (n,h,w,c)     -> (n,c_out/4,h,w,4)
+ *   NHWC_PAD_C  (n,h,w,c)      -> (n,h,w,c_out)
+ * elem_bytes = 1, 2 or 4. */
+enum {
+    B200CB_RELAYOUT_NCHW_NHWC = 0,
+    B200CB_RELAYOUT_NHWC_NCHW = 1,
+    B200CB_RELAYOUT_NCHW_NCHW4 = 2,
+    B200CB_RELAYOUT_NCHW4_NCHW = 3,
+    B200CB_RELAYOUT_NCHW4_NHWC = 4,
+    B200CB_RELAYOUT_NHWC_NCHW4 = 5,
+    B200CB_RELAYOUT_NHWC_PAD_C = 6
+};
+int b200cb_relayout(
+        uint32_t mode, uint32_t elem_bytes, uint32_t n, uint32_t c, uint32_t h, uint32_t w, uint32_t c_out,
+        const void* src, void* dst, void* stream);
+
 /* Device self-tests (synchronise `stream`). which == 0: the requantize epilogue's reciprocal-based
  * division against IEEE division over all 2^32 dividends; which == 1: the ALU-only quantize of the
  * fast int8 epilogue against roundf(IEEE division) + clamp; which == 2: the packed fp32x2 form of that

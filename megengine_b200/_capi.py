@@ -18,6 +18,9 @@ COMPUTE_DEFAULT, COMPUTE_FLOAT32 = 0, 1
 BIAS_NONE, BIAS_CHANNEL, BIAS_FULL = 0, 1, 2
 DT_F32, DT_F16, DT_BF16, DT_QS8, DT_QS32, DT_NONE = 0, 1, 2, 3, 4, 255
 
+RELAYOUT_NCHW_NHWC, RELAYOUT_NHWC_NCHW, RELAYOUT_NCHW_NCHW4, RELAYOUT_NCHW4_NCHW = 0, 1, 2, 3
+RELAYOUT_NCHW4_NHWC, RELAYOUT_NHWC_NCHW4, RELAYOUT_NHWC_PAD_C = 4, 5, 6
+
 DT_SIZE = {DT_F32: 4, DT_F16: 2, DT_BF16: 2, DT_QS8: 1, DT_QS32: 4}
 DT_NAME = {DT_F32: "Float32", DT_F16: "Float16", DT_BF16: "BFloat16", DT_QS8: "QuantizedS8",
            DT_QS32: "QuantizedS32", DT_NONE: "none"}
@@ -78,6 +81,9 @@ SYMBOLS = [
     ("b200cb_host_scratch_bytes", ctypes.c_size_t, [ctypes.POINTER(Plan)]),
     ("b200cb_exec_host", ctypes.c_int,
      [ctypes.POINTER(Plan), _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
+    ("b200cb_relayout", ctypes.c_int,
+     [ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_uint32,
+      ctypes.c_uint32, _P, _P, _P]),
     ("b200cb_strerror", ctypes.c_char_p, [ctypes.c_int]),
     ("b200cb_last_error_detail", ctypes.c_char_p, []),
 ]

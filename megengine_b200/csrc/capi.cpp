@@ -72,12 +72,18 @@ int validate_desc(const b200cb_desc* d) {
 // (tools/sweep_resnet.py, profiles/): the widest tile that is not wider than OC wins whenever it still
 // yields at least one tile per SM -- operand traffic per flop falls with the tile width and the
 // kernels are shared-memory / L2 feed bound -- and below that the tile count is what matters.
-double igemm_cost(const b200cb_desc& d, uint32_t bn, int sms) {
+double igemm_cost(const b200cb_desc& d, const b200cb_plan& plan, uint32_t bn, int sms) {
     const double M = (double)d.n * d.oh * d.ow;
     const double tiles = ceil(M / IGEMM_BLOCK_M) * ceil((double)d.oc / bn);
-    if (tiles >= sms)
-        return 1.0 / bn;           // enough parallelism: widest first
-    return 1.0 + 1.0 / tiles;      // small problems: most tiles first
+    if (tiles < sms)
+        return 1.0 + 1.0 / tiles;  // small problems: most tiles first
+    double cost = 1.0 / bn;        // enough parallelism: widest first ...
+    // ... unless the wide tile leaves no room for a two-deep z ring per epilogue group: the residual
+    // stream then stalls every chunk (ResNet-50 l3.c3: 128x128 with the deep ring beats 128x256, r02 sweep)
+    if (d.has_z && plan.kernel == KERNEL_IGEMM && d.format == B200CB_FORMAT_NHWC && (plan.reserved[5] >> 16) < 8 &&
+        bn > 128 && (uint64_t)d.fh * d.fw * d.ic * dtype_size(d.src_dtype) <= 512)
+        cost *= 2.5;
+    return cost;
 }
 // ---- NCHW adapter (fp16 / bf16): the tensor-core kernels want channels innermost, so NCHW tensors are
 // re-tiled into NHWC / KRSC copies in the workspace (channels zero-padded to what TMA needs), the NHWC
@@ -189,7 +195,7 @@ int b200cb_query(const b200cb_desc* desc, b200cb_plan* plan) {
                 first_err = rc;
             continue;
         }
-        double cost = g_algos[a].kernel == KERNEL_IGEMM ? igemm_cost(*desc, g_algos[a].block_n, 148) : 0.0;
+        double cost = g_algos[a].kernel == KERNEL_IGEMM ? igemm_cost(*desc, tmp, g_algos[a].block_n, 148) : 0.0;
         if (best < 0 || cost < best_cost) {
             best = a;
             best_cost = cost;
@@ -297,6 +303,16 @@ int b200cb_plan_use_preprocessed_filter(b200cb_plan* plan) {
         plan->workspace_bytes = 0;
     }
     return B200CB_OK;
+}
+
+int b200cb_relayout(
+        uint32_t mode, uint32_t elem_bytes, uint32_t n, uint32_t c, uint32_t h, uint32_t w, uint32_t c_out,
+        const void* src, void* dst, void* stream) {
+    if (!src || !dst)
+        return B200CB_ERR_NULL;
+    if (n == 0 || c == 0 || h == 0 || w == 0 || c_out == 0)
+        return B200CB_UNSUPPORTED_SHAPE;
+    return relayout_generic(mode, elem_bytes, n, c, h, w, c_out, src, dst, static_cast<cudaStream_t>(stream));
 }
 
 int b200cb_selftest(int which, void* stream, uint64_t* mismatches) {

@@ -60,6 +60,15 @@ int relayout_transpose16(
         const void* in, void* out, uint32_t B, uint32_t R, uint32_t S, uint32_t out_ld, uint64_t in_batch,
         uint64_t out_batch, cudaStream_t stream);
 
+// in [pixels][C] -> out [pixels][Cpad], zero-padded channels; es = element bytes (relayout.cu)
+int relayout_pad_channels(
+        const void* in, void* out, uint64_t pixels, uint32_t C, uint32_t Cpad, uint32_t es, cudaStream_t stream);
+
+// b200cb_relayout (relayout.cu): every mode of include/b200cb.h
+int relayout_generic(
+        uint32_t mode, uint32_t es, uint32_t n, uint32_t c, uint32_t h, uint32_t w, uint32_t c_out, const void* src,
+        void* dst, cudaStream_t stream);
+
 int device_sm_count();
 
 inline uint32_t dtype_size(uint32_t dt) {

@@ -947,8 +947,13 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1) dw3x3_bulk_ke
 
 // experiment knobs (tools/): integer environment override with a default
 int env_flag(const char* name, int dflt) {
+#ifdef B200CB_TOOLS  // the product library never reads the environment
     const char* e = getenv(name);
     return e ? atoi(e) : dflt;
+#else
+    (void)name;
+    return dflt;
+#endif
 }
 
 // launch with programmatic stream serialization (the kernels above call griddepcontrol themselves)
@@ -961,7 +966,7 @@ cudaError_t launch_pdl(Kern kern, uint32_t grid, uint32_t threads, uint32_t smem
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[1];
-    static const bool use_pdl = getenv("B200CB_NO_PDL") == nullptr;
+    static const bool use_pdl = env_flag("B200CB_NO_PDL", 0) == 0;
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
     cfg.attrs = attr;

@@ -237,6 +237,17 @@ __device__ __forceinline__ uint32_t pack_f16x2(float lo, float hi) {
     __half2 v = __floats2half2_rn(lo, hi);
     return *reinterpret_cast<uint32_t*>(&v);
 }
+// RELU on a packed pair of 16-bit outputs: max(x, 0), NaN propagated (the oracle's `x <= 0 ? 0 : x` keeps it)
+__device__ __forceinline__ uint32_t relu_bf16x2(uint32_t v) {
+    uint32_t r;
+    asm("max.NaN.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
+    return r;
+}
+__device__ __forceinline__ uint32_t relu_f16x2(uint32_t v) {
+    uint32_t r;
+    asm("max.NaN.f16x2 %0, %1, %2;" : "=r"(r) : "r"(v), "r"(0u));
+    return r;
+}
 __device__ __forceinline__ float bf16lo(uint32_t v) { return __uint_as_float(v << 16); }
 __device__ __forceinline__ float bf16hi(uint32_t v) { return __uint_as_float(v & 0xffff0000u); }
 __device__ __forceinline__ float f16lo(uint32_t v) {

@@ -28,7 +28,9 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <mutex>
 #include <type_traits>
+#include <unordered_map>
 #include "common.h"
 #include "ptx.cuh"
 #include "epilogue.cuh"
@@ -71,9 +73,14 @@ struct IgemmParams {
     // NCHW4 destination (N, OC/4, OH, OW, 4): dst and z are accessed in place by the epilogue
     uint32_t nz;  // z ring depth
     uint32_t nchw4, z_direct;
+    // 1: the epilogue copies its staged rows out with coalesced st.global instead of a TMA store.  A TMA
+    // store queues behind every load the producer has in flight, so waiting for it to release a slab or
+    // a z chunk costs a whole queue drain (thousands of clocks when the layer is HBM bound); plain
+    // stores free the staging memory as soon as the warp has read it back.
+    uint32_t direct_store;
     const void* z;
     RequantParams rq;
-    long long* dbg;   // -DB200CB_DEBUG_TIMING builds only: 148 x 3 roles x 9 counters
+    long long* dbg;   // -DB200CB_DEBUG_TIMING builds only: 148 x 3 roles x 17 counters
 };
 
 namespace {
@@ -89,8 +96,12 @@ using namespace ptx;
         mbar_wait(bar, parity);                        \
         dbg_acc[slot] += clock64() - t0__;             \
     } while (0)
+#define DBG_MARK(v) const long long v = clock64()
+#define DBG_ADD(slot, since) dbg_acc[slot] += clock64() - (since)
 #else
 #define TIMED_WAIT(slot, bar, parity) mbar_wait(bar, parity)
+#define DBG_MARK(v) do {} while (0)
+#define DBG_ADD(slot, since) do {} while (0)
 #endif
 
 // UMMA shared-memory descriptor split into its 32-bit halves so that the single MMA-issuing thread
@@ -131,38 +142,42 @@ struct Traits {
     static constexpr int OUT_ES = OUT32 ? 4 : IN_ES;
     static constexpr int EPI_N = OUT32 ? 32 : 64;       // columns per epilogue chunk
     static constexpr int ROW_BYTES = EPI_N * OUT_ES;    // 128 (16-bit, 32-bit) or 64 (int8)
-    static constexpr int GROUPS = OUT32 ? 1 : 2;        // epilogue warp groups (4 warps each)
+    // Epilogue warp groups (4 warps each, one per TMEM lane quadrant).  Layers with a short k-loop are
+    // bound by the epilogue, and the epilogue by latency, not by issue slots (profiles/r02: with 8 warps
+    // the MMA warp waits 70-85 % of the time for an accumulator while the epilogue warps run at ~0.6
+    // instructions / clk / scheduler): 16 epilogue warps, every group on its own chunk.
+    static constexpr int GROUPS = OUT32 ? 1 : 4;
     static constexpr int THREADS = 128 + 128 * GROUPS;
     static constexpr int SLAB_BYTES = 32 * ROW_BYTES;   // one warp's staging slab (32 rows)
-    // slabs per warp: double buffered where 32 KiB allow it (int8), single for 8 warps x 4 KiB
-    // double buffered where 32 KiB allow it (int8, int32), and for BN == 64 tiles, whose short epilogue
-    // would otherwise wait for the previous TMA store to drain its only slab (64 KiB there)
-    __host__ __device__ static constexpr int nslab(int bn) { return (bn == 64 || 4 * GROUPS * 2 * SLAB_BYTES <= 32768) ? 2 : 1; }
+    // slabs per warp: double buffered where 64 KiB allow it (int8, int32)
+    __host__ __device__ static constexpr int nslab(int) { return (4 * GROUPS * 2 * SLAB_BYTES <= 65536) ? 2 : 1; }
     __host__ __device__ static constexpr int slabs_bytes(int bn) { return 4 * GROUPS * nslab(bn) * SLAB_BYTES; }
     static constexpr int ZBUF_BYTES = 128 * ROW_BYTES;  // one z chunk
+    // accumulator buffers in TMEM (512 columns): 4 for tiles up to 128 columns, 2 for 256
+    __host__ __device__ static constexpr int nacc(int bn) { return (OUT32 || bn > 128) ? 2 : 4; }
 };
 
 // shared memory map (offsets from the 1024-aligned base)
 constexpr uint32_t OFF_FULL = 0;       // [16] x 8
 constexpr uint32_t OFF_EMPTY = 128;    // [16] x 8
-constexpr uint32_t OFF_TFULL = 256;    // [2]
-constexpr uint32_t OFF_TEMPTY = 272;   // [2]
-constexpr uint32_t OFF_ZFULL = 288;    // [8]
-constexpr uint32_t OFF_ZEMPTY = 352;   // [8]
-constexpr uint32_t OFF_TMEM = 416;
-constexpr uint32_t OFF_BRES = 424;     // stem: resident filter barrier
-// z ring depth: 4 (2 epilogue groups busy + 2 chunks in flight) up to 8 -- short-k layers are bound by
+constexpr uint32_t OFF_TFULL = 256;    // [4]
+constexpr uint32_t OFF_TEMPTY = 288;   // [4]
+constexpr uint32_t OFF_ZFULL = 320;    // [8]
+constexpr uint32_t OFF_ZEMPTY = 384;   // [8]
+constexpr uint32_t OFF_TMEM = 448;
+constexpr uint32_t OFF_BRES = 456;     // stem: resident filter barrier
+// z ring depth: 6 (4 epilogue groups busy + 2 chunks in flight) up to 8 -- short-k layers are bound by
 // the z / dst streams, so their spare shared memory holds z chunks (a tile or more ahead) rather than
 // more A/B stages
-constexpr uint32_t NZ_MIN = 4, NZ_MAX = 8;
+constexpr uint32_t NZ_MIN = 4, NZ_MAX = 8;  // GROUPS sub-rings of depth 1 or 2 (see the z prefetch warp)
 constexpr uint32_t STEM_NJ_K = 136;    // pixel pairs per staged stem input row (== STEM_NJ on the host)
-constexpr uint32_t OFF_BIAS = 1024;    // (4 * GROUPS) warps x BN x 4 bytes, rounded up to 1 KiB
+constexpr uint32_t OFF_BIAS = 1024;    // 1 KiB: per epilogue group the 64 bias values of its chunk (OUT32: the tile's BN)
 // host mirror of Traits::slabs_bytes
-__host__ __device__ constexpr uint32_t slabs_bytes(uint32_t groups, uint32_t bn, uint32_t row_bytes) {
-    return 4 * groups * ((bn == 64 || 4 * groups * 2 * 32 * row_bytes <= 32768) ? 2u : 1u) * 32 * row_bytes;
+__host__ __device__ constexpr uint32_t slabs_bytes(uint32_t groups, uint32_t /*bn*/, uint32_t row_bytes) {
+    return 4 * groups * ((4 * groups * 2 * 32 * row_bytes <= 65536) ? 2u : 1u) * 32 * row_bytes;
 }
-__host__ __device__ constexpr uint32_t off_sd(uint32_t groups, uint32_t bn) {
-    return OFF_BIAS + ((4 * groups * bn * 4 + 1023u) & ~1023u);
+__host__ __device__ constexpr uint32_t off_sd(uint32_t /*groups*/, uint32_t /*bn*/) {
+    return OFF_BIAS + 1024u;
 }
 // With z: the epilogue area is a ring of NZ z chunks (128 rows x ROW_BYTES, TMA-prefetched) and the
 // epilogue works IN PLACE -- each warp overwrites its 32 rows of the z chunk with the outputs and
@@ -283,11 +298,13 @@ template <int KIND, int BN, int OUT32, int PAIR>
 __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         igemm_kernel(const __grid_constant__ IgemmParams p) {
     using T = Traits<KIND, OUT32>;
-    constexpr uint32_t TMEM_COLS = 2 * BN;  // 128 / 256 / 512: powers of two >= 32
+    constexpr uint32_t NACC = T::nacc(BN);  // accumulator buffers: tile sequence number % NACC
+    constexpr uint32_t TMEM_COLS = NACC * BN;  // 128 / 256 / 512: powers of two >= 32
     constexpr uint32_t NUM_CHUNKS = BN / T::EPI_N;
-    // BN == 64: a tile is ONE epilogue chunk -- instead of idling the second epilogue group, whole tiles
-    // alternate between the groups (group g drains accumulator buffer g)
-    constexpr bool TILE_SPLIT = NUM_CHUNKS == 1 && T::GROUPS == 2;
+    // chunk c of the CTA's ts-th tile belongs to epilogue group (ts * NUM_CHUNKS + c) % GROUPS: with 4
+    // groups a 256-column tile is drained by all of them at once, 128-column tiles alternate between
+    // two pairs of groups and 64-column tiles rotate through the four
+    constexpr uint32_t GROUPS_PER_TILE = NUM_CHUNKS < T::GROUPS ? NUM_CHUNKS : T::GROUPS;
     constexpr uint32_t IDESC =
             (KIND == KIND_S8) ? umma_idesc(2, 1, 128, BN)
                               : umma_idesc(1, KIND == KIND_BF16 ? 1 : 0, 128, BN);
@@ -331,7 +348,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     const uint32_t warp = threadIdx.x >> 5;
     const uint32_t lane = threadIdx.x & 31;
 #ifdef B200CB_DEBUG_TIMING
-    long long dbg_acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    long long dbg_acc[16] = {0};
     const long long dbg_t0 = clock64();
 #endif
     const uint32_t num_kb = p.num_taps * p.num_kc;
@@ -358,11 +375,11 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             // multicast clusters: one MMA commit per CTA; pair: one (multicast) commit of the leader
             mbar_init(bar_empty + 8 * i, pair ? 1 : C);
         }
-        for (uint32_t i = 0; i < 2; ++i) {
+        for (uint32_t i = 0; i < NACC; ++i) {
             mbar_init(bar_tfull + 8 * i, 1);
             // one arrive per epilogue warp that reads the accumulator (pair: of both CTAs, on the leader's
-            // barrier); single-chunk tiles alternate between the two groups, so only one group arrives
-            mbar_init(bar_tempty + 8 * i, (pair ? 2 : 1) * 4 * (TILE_SPLIT ? 1 : T::GROUPS));
+            // barrier)
+            mbar_init(bar_tempty + 8 * i, (pair ? 2 : 1) * 4 * GROUPS_PER_TILE);
         }
         for (uint32_t i = 0; i < nz; ++i) {
             mbar_init(bar_zfull + 8 * i, 1);
@@ -475,9 +492,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     soff = 0;
                     phase ^= 1;
                 }
-                acc ^= 1;
-                if (acc == 0)
+                if (++acc == NACC) {
+                    acc = 0;
                     acc_phase ^= 1;
+                }
             }
         };
         using U1 = std::integral_constant<uint32_t, 1>;
@@ -593,9 +611,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     soff = 0;
                     phase ^= 1;
                 }
-                acc ^= 1;
-                if (acc == 0)
+                if (++acc == NACC) {
+                    acc = 0;
                     acc_phase ^= 1;
+                }
             }
         }
         __syncwarp();
@@ -748,9 +767,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         phase ^= 1;
                     }
                 }
-                acc ^= 1;
-                if (acc == 0)
+                if (++acc == NACC) {
+                    acc = 0;
                     acc_phase ^= 1;
+                }
             }
         };
         // (elect.sync, not `lane == 0`: the compiler then knows that exactly one lane is active and emits
@@ -766,9 +786,16 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         __syncwarp();
     } else if (warp == 2) {
         // ============================ z prefetch (TMA) ============================
+        // Every epilogue group owns a private sub-ring of ZD = nz / GROUPS chunks: slot = group * ZD + (the
+        // group's chunk count % ZD).  A slot is then only ever consumed by ONE group, in order -- with a
+        // single ring shared by all groups a slot's consumer alternates, a fast group can wait for a slot
+        // a whole barrier phase ahead of it, and mbarrier parity waits alias one phase back (this hung /
+        // faulted l1.c3 with a 6-deep ring; compute-sanitizer racecheck flags the cross-group slot reuse).
         if (p.has_z) {
-            uint32_t zb = 0, zphase = 0;
-            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+            const uint32_t ZD = nz / T::GROUPS;
+            uint32_t zcnt = 0, zph = 0;  // per group: 4-bit slot counters / 1-bit phases, packed
+            uint32_t first = 0;
+            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num, first = (first + NUM_CHUNKS) % T::GROUPS) {
                 const uint32_t m_blk = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
                 if (m_blk >= p.m_tiles)
                     continue;  // phantom tile
@@ -777,7 +804,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     const uint32_t col0 = n_blk * BN + c * T::EPI_N;
                     if (col0 >= p.OC)
                         break;
-                    TIMED_WAIT(5, bar_zempty + 8 * zb, zphase ^ 1);
+                    const uint32_t g = (first + c) % T::GROUPS;
+                    const uint32_t zi = (zcnt >> (4 * g)) & 0xfu;
+                    const uint32_t zb = g * ZD + zi;
+                    TIMED_WAIT(5, bar_zempty + 8 * zb, ((zph >> g) & 1u) ^ 1u);
                     if (elect_one()) {
                         mbar_arrive_expect_tx(bar_zfull + 8 * zb, IGEMM_BLOCK_M * T::ROW_BYTES);
                         if (stem)
@@ -792,9 +822,11 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                     static_cast<int32_t>(col0), m0);
                     }
                     __syncwarp();
-                    if (++zb == nz) {
-                        zb = 0;
-                        zphase ^= 1;
+                    if (zi + 1 == ZD) {
+                        zcnt &= ~(0xfu << (4 * g));
+                        zph ^= 1u << g;
+                    } else {
+                        zcnt += 1u << (4 * g);
                     }
                 }
             }
@@ -802,12 +834,11 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     } else if (warp >= 4) {
         // ============================ epilogue ============================
         // warp e = warp - 4: TMEM lane quadrant (e & 3) == rows [32*(e&3), +32) of the tile;
-        // group (e >> 2) handles the chunks c with c % GROUPS == group.
+        // group (e >> 2) handles the chunks c with (tile sequence * NUM_CHUNKS + c) % GROUPS == group.
         const uint32_t e = warp - 4;
         const uint32_t quad = warp & 3;
         const uint32_t group = e >> 2;
         const uint32_t row = quad * 32 + lane;            // row of the tile == TMEM lane
-        uint32_t* sbias = reinterpret_cast<uint32_t*>(smem_gen + OFF_BIAS) + e * BN;
         const uint32_t slab_u32 = smem_base + OFF_SD + e * NSLAB * T::SLAB_BYTES;
         uint8_t* slab_gen = smem_gen + OFF_SD + e * NSLAB * T::SLAB_BYTES;
         const uint8_t* sZ_gen = smem_gen + OFF_SZ;
@@ -820,15 +851,18 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             else
                 mbar_arrive(bar);
         };
-        const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
+        const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;  // (int8 generic path)
         const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
         const bool fast8 = KIND == KIND_S8 && !generic_act && p.rq.fast_div == 2;
-        uint32_t acc = 0, acc_phase = 0, db = 0, cur_nblk = 0xffffffffu;
-        uint32_t zb = 0, zphase = 0;  // z ring position, advanced once per chunk of every valid tile
-        auto z_advance = [&]() {
-            if (++zb == nz) {
-                zb = 0;
-                zphase ^= 1;
+        uint32_t acc = 0, acc_phase = 0, db = 0, cur_key = 0xffffffffu;
+        // this group's z sub-ring (see the z prefetch warp): position and phase advance once per chunk the
+        // group consumes
+        const uint32_t ZD = nz / T::GROUPS;
+        uint32_t zi = 0, zphase = 0;
+        auto next_acc = [&]() {
+            if (++acc == NACC) {
+                acc = 0;
+                acc_phase ^= 1;
             }
         };
         // (m, n) tile indices advance incrementally: a division per tile is a ~25-instruction MUFU chain on
@@ -840,17 +874,19 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             if (tr >= ntl)
                 tr -= ntl, ++tq;
         };
-        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num, next_tile()) {
+        // bias values of the group's current chunk (OUT32: of the whole tile), shared by the group's 4 warps
+        uint32_t* sbias = reinterpret_cast<uint32_t*>(smem_gen + OFF_BIAS) + (T::GROUPS > 1 ? group * T::EPI_N : 0u);
+        constexpr uint32_t BIAS_COLS = T::GROUPS > 1 ? T::EPI_N : BN;
+        // group of the tile's chunk 0: (tile sequence number * NUM_CHUNKS) % GROUPS
+        uint32_t first = 0;
+        for (uint32_t ct = cl_id; ct < total_ct;
+             ct += cl_num, next_tile(), next_acc(), first = (first + NUM_CHUNKS) % T::GROUPS) {
             const uint32_t m_blk = tq * C + crank, n_blk = tr;
-            if (TILE_SPLIT && acc != group) {
-                // the other group's tile (it has one z chunk unless it is a phantom tile)
-                if (m_blk < p.m_tiles)
-                    z_advance();
-                acc ^= 1;
-                if (acc == 0)
-                    acc_phase ^= 1;
-                continue;
-            }
+            const uint32_t n0 = n_blk * BN;
+            // the chunks of this tile the group owns: c_own, c_own + GROUPS, ... (with 4 groups: at most one)
+            const uint32_t c_own = (group + T::GROUPS - first) % T::GROUPS;
+            if (c_own >= NUM_CHUNKS)
+                continue;  // a tile of the other groups
             if (m_blk >= p.m_tiles) {
                 // phantom tile: consume the accumulator and hand it straight back
                 TIMED_WAIT(3, bar_tfull + 8 * acc, acc_phase);
@@ -859,43 +895,44 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 __syncwarp();
                 if (lane == 0)
                     arrive_tempty(bar_tempty + 8 * acc);
-                acc ^= 1;
-                if (acc == 0)
-                    acc_phase ^= 1;
                 continue;
             }
             const int32_t m0 = static_cast<int32_t>(m_blk * IGEMM_BLOCK_M);
-            const uint32_t n0 = n_blk * BN;
-            // bias slice of this tile -> the warp's private smem (fp32 for float kinds, int32 for int8);
-            // only when the N tile changes (never again for single-N-tile layers)
-            __syncwarp();
-            if (n_blk != cur_nblk)
-            for (uint32_t i = lane; i < BN; i += 32) {
-                uint32_t v = 0;
-                if (p.has_bias && n0 + i < p.OC) {
-                    if constexpr (KIND == KIND_S8) {
-                        v = static_cast<uint32_t>(reinterpret_cast<const int32_t*>(p.bias)[n0 + i]);
-                    } else if constexpr (KIND == KIND_BF16) {
-                        v = static_cast<uint32_t>(
-                                    reinterpret_cast<const unsigned short*>(p.bias)[n0 + i])
-                            << 16;
-                    } else {
-                        v = __float_as_uint(
-                                __half2float(reinterpret_cast<const __half*>(p.bias)[n0 + i]));
-                    }
-                }
-                sbias[i] = v;
-            }
-            cur_nblk = n_blk;
-            __syncwarp();
+            // chunks of this tile that exist (OC tail)
             uint32_t nchunks = 0;
 #pragma unroll
             for (uint32_t c = 0; c < NUM_CHUNKS; ++c)
                 if (n0 + c * T::EPI_N < p.OC)
                     nchunks = c + 1;
+            // bias slice -> the group's smem (fp32 for float kinds, int32 for int8), only when it changes
+            // (never again for layers whose N tiles map to a fixed chunk per CTA); the 4 warps of a group
+            // walk the same tiles, a named barrier per group orders the refill against the readers
+            const uint32_t key = T::GROUPS > 1 ? n_blk * NUM_CHUNKS + c_own : n_blk;
+            if (key != cur_key) {
+                const uint32_t b0 = n0 + (T::GROUPS > 1 ? c_own * T::EPI_N : 0u);
+                named_bar_sync(1 + group, 128);
+                for (uint32_t i = quad * 32 + lane; i < BIAS_COLS; i += 128) {
+                    uint32_t v = 0;
+                    if (p.has_bias && b0 + i < p.OC) {
+                        if constexpr (KIND == KIND_S8) {
+                            v = static_cast<uint32_t>(reinterpret_cast<const int32_t*>(p.bias)[b0 + i]);
+                        } else if constexpr (KIND == KIND_BF16) {
+                            v = static_cast<uint32_t>(
+                                        reinterpret_cast<const unsigned short*>(p.bias)[b0 + i])
+                                << 16;
+                        } else {
+                            v = __float_as_uint(
+                                    __half2float(reinterpret_cast<const __half*>(p.bias)[b0 + i]));
+                        }
+                    }
+                    sbias[i] = v;
+                }
+                named_bar_sync(1 + group, 128);
+                cur_key = key;
+            }
             // last chunk this warp's group owns (decides when TMEM can be handed back)
             int32_t last_c = -1;
-            for (uint32_t c = TILE_SPLIT ? 0 : group; c < nchunks; c += TILE_SPLIT ? 1 : T::GROUPS)
+            for (uint32_t c = c_own; c < nchunks; c += T::GROUPS)
                 last_c = static_cast<int32_t>(c);
             TIMED_WAIT(3, bar_tfull + 8 * acc, acc_phase);
             tc_fence_after();
@@ -906,9 +943,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     arrive_tempty(bar_tempty + 8 * acc);
             }
 #pragma unroll 1
-            for (uint32_t c = 0; c < nchunks; ++c, z_advance()) {
-                if (!TILE_SPLIT && T::GROUPS > 1 && (c % T::GROUPS) != group)
-                    continue;
+            for (uint32_t c = c_own; c < nchunks; c += T::GROUPS) {
+                const uint32_t zb = group * ZD + zi;  // (has_z only)
                 const uint32_t col0 = n0 + c * T::EPI_N;
                 // slab db must have been drained by the TMA store issued NSLAB chunks ago
 #ifdef B200CB_DEBUG_TIMING
@@ -916,7 +952,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 #endif
                 // (elect.sync is deterministic for a given member mask: the same lane commits and waits
                 // on the bulk groups, and the compiler emits plain UTMASTG instead of a per-lane R2UR loop)
-                if (!p.has_z) {
+                if (!p.has_z && !p.direct_store) {
                     if (elect_one())
                         tma_store_wait_read<NSLAB - 1>();
                     __syncwarp();
@@ -926,6 +962,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 #endif
                 if (p.has_z)
                     TIMED_WAIT(4, bar_zfull + 8 * zb, zphase);
+                DBG_MARK(tbody__);
                 // with z the outputs overwrite the warp's 32 rows of the z chunk (each thread reads and
                 // writes only its own row's pieces), without z they go to the warp's private slab
                 const uint8_t* zrow = sZ_gen + zb * T::ZBUF_BYTES + row * T::ROW_BYTES;
@@ -933,20 +970,21 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                         : slab_gen + db * T::SLAB_BYTES + lane * T::ROW_BYTES;
                 const uint32_t st_src = p.has_z ? sZ + zb * T::ZBUF_BYTES + quad * T::SLAB_BYTES
                                                 : slab_u32 + db * T::SLAB_BYTES;
-                // the whole chunk (EPI_N columns) goes to registers first, so that the accumulator is handed
-                // back to the MMA warp before any epilogue arithmetic (short-k layers live on that overlap)
-                // (16-bit kinds; the int8 requantize needs the registers and loads 32 columns at a time)
+                // 32 columns at a time; the accumulator is handed back to the MMA warp as soon as the group's
+                // last columns are in registers
                 constexpr uint32_t HALVES = T::EPI_N / 32;
-                constexpr uint32_t HB = (KIND == KIND_S8) ? 1 : HALVES;  // halves loaded per batch
+                constexpr uint32_t HB = 1;  // halves loaded per batch (640 threads: <= 102 registers each)
                 uint32_t rr[HB][32];
 #pragma unroll
                 for (uint32_t h = 0; h < HALVES; ++h) {
                     if (h % HB == 0) {
+                        DBG_MARK(tld__);
 #pragma unroll
                         for (uint32_t hh = 0; hh < HB; ++hh)
                             tmem_ld_32x32(
                                     tmem_base + ((quad * 32) << 16) + acc * BN + c * T::EPI_N + (h + hh) * 32, rr[hh]);
                         tmem_ld_wait();
+                        DBG_ADD(8, tld__);
                         if (static_cast<int32_t>(c) == last_c && h + HB == HALVES) {
                             // accumulator fully drained into registers: hand TMEM back to the MMA warp
                             tc_fence_before();
@@ -958,7 +996,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     if (col0 + h * 32 >= p.OC)
                         continue;  // 32 columns entirely past OC (OC = 16 / 96 / 144 ...): the store clips them
                     const uint32_t (&r)[32] = rr[h % HB];
-                    const uint32_t* bcol = sbias + c * T::EPI_N + h * 32;
+                    const uint32_t* bcol = sbias + (T::GROUPS > 1 ? 0u : c * T::EPI_N) + h * 32;
                     constexpr uint32_t COLS_PER_16B = 16 / T::OUT_ES;
                     constexpr uint32_t PIECES = 32 / COLS_PER_16B;  // 16-byte pieces per 32 columns
                     if constexpr (KIND == KIND_S8 && OUT32) {
@@ -1072,14 +1110,20 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         }
                       }
                     } else {
-                        float x[32];
+                        // 16-bit kinds.  With 16 epilogue warps the epilogue is bound by instruction issue, so
+                        // the arithmetic is packed: fp32x2 adds (bias, z) on register pairs, one conversion per
+                        // output pair, RELU as a packed 16-bit max on the converted pair (max and the rounding
+                        // commute: both are monotonic and fix 0; NaN is propagated as the scalar select did)
+                        f32x2_t v[16];
 #pragma unroll
                         for (uint32_t j = 0; j < 8; ++j) {
                             const uint4 bv = *reinterpret_cast<const uint4*>(bcol + j * 4);
-                            x[j * 4 + 0] = __uint_as_float(r[j * 4 + 0]) + __uint_as_float(bv.x);
-                            x[j * 4 + 1] = __uint_as_float(r[j * 4 + 1]) + __uint_as_float(bv.y);
-                            x[j * 4 + 2] = __uint_as_float(r[j * 4 + 2]) + __uint_as_float(bv.z);
-                            x[j * 4 + 3] = __uint_as_float(r[j * 4 + 3]) + __uint_as_float(bv.w);
+                            v[2 * j] = f2_add(
+                                    f2_pack(__uint_as_float(r[j * 4 + 0]), __uint_as_float(r[j * 4 + 1])),
+                                    f2_pack(__uint_as_float(bv.x), __uint_as_float(bv.y)));
+                            v[2 * j + 1] = f2_add(
+                                    f2_pack(__uint_as_float(r[j * 4 + 2]), __uint_as_float(r[j * 4 + 3])),
+                                    f2_pack(__uint_as_float(bv.z), __uint_as_float(bv.w)));
                         }
                         if (p.has_z) {
 #pragma unroll
@@ -1089,40 +1133,88 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                 const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
 #pragma unroll
                                 for (uint32_t w = 0; w < 4; ++w) {
-                                    if constexpr (KIND == KIND_BF16) {
-                                        x[j * 8 + 2 * w] += bf16lo(zw[w]);
-                                        x[j * 8 + 2 * w + 1] += bf16hi(zw[w]);
-                                    } else {
-                                        x[j * 8 + 2 * w] += f16lo(zw[w]);
-                                        x[j * 8 + 2 * w + 1] += f16hi(zw[w]);
-                                    }
+                                    if constexpr (KIND == KIND_BF16)
+                                        v[j * 4 + w] = f2_add(v[j * 4 + w], f2_pack(bf16lo(zw[w]), bf16hi(zw[w])));
+                                    else
+                                        v[j * 4 + w] = f2_add(v[j * 4 + w], f2_pack(f16lo(zw[w]), f16hi(zw[w])));
                                 }
                             }
                         }
+                        uint32_t o[16];
                         if (generic_act) {
 #pragma unroll
-                            for (uint32_t i = 0; i < 32; ++i)
-                                x[i] = act_generic(x[i], p.nonline);
+                            for (uint32_t i = 0; i < 16; ++i) {
+                                float lo, hi;
+                                f2_unpack(v[i], lo, hi);
+                                lo = act_generic(lo, p.nonline), hi = act_generic(hi, p.nonline);
+                                o[i] = (KIND == KIND_BF16) ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi);
+                            }
                         } else {
 #pragma unroll
-                            for (uint32_t i = 0; i < 32; ++i)
-                                x[i] = x[i] <= act_lo ? act_lo : x[i];
+                            for (uint32_t i = 0; i < 16; ++i) {
+                                float lo, hi;
+                                f2_unpack(v[i], lo, hi);
+                                o[i] = (KIND == KIND_BF16) ? pack_bf16x2(lo, hi) : pack_f16x2(lo, hi);
+                            }
+                            if (p.nonline == B200CB_NL_RELU) {
+#pragma unroll
+                                for (uint32_t i = 0; i < 16; ++i)
+                                    o[i] = (KIND == KIND_BF16) ? relu_bf16x2(o[i]) : relu_f16x2(o[i]);
+                            }
                         }
 #pragma unroll
                         for (uint32_t j = 0; j < PIECES; ++j) {
-                            uint32_t ow[4];
-#pragma unroll
-                            for (uint32_t w = 0; w < 4; ++w)
-                                ow[w] = (KIND == KIND_BF16)
-                                                ? pack_bf16x2(x[j * 8 + 2 * w], x[j * 8 + 2 * w + 1])
-                                                : pack_f16x2(x[j * 8 + 2 * w], x[j * 8 + 2 * w + 1]);
                             const uint32_t off = (h * PIECES + j) ^ (lane & 7);
-                            *reinterpret_cast<uint4*>(drow + off * 16) = make_uint4(ow[0], ow[1], ow[2], ow[3]);
+                            *reinterpret_cast<uint4*>(drow + off * 16) =
+                                    make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
                         }
                     }
                 }
+                DBG_ADD(9, tbody__);
                 if (p.nchw4)
                     continue;  // written in place above, no slab / TMA store
+                DBG_MARK(tst__);
+                if (p.direct_store && !rows) {
+                    // the warp's 32 staged rows -> global memory, 8 (4) lanes per 128- (64-) byte row, every
+                    // store instruction covers whole rows; rows past M / OW and columns past OC are clipped
+                    __syncwarp();
+                    constexpr uint32_t PIECES_ROW = T::ROW_BYTES / 16;
+                    constexpr uint32_t ROWS_PER_IT = 32 / PIECES_ROW;
+                    const uint32_t piece = lane % PIECES_ROW;
+                    const uint8_t* rd = p.has_z ? sZ_gen + zb * T::ZBUF_BYTES + quad * T::SLAB_BYTES
+                                                : slab_gen + db * T::SLAB_BYTES;
+                    const uint32_t col = col0 + piece * (16 / T::OUT_ES);
+                    uint32_t lim, mbase;  // rows [0, lim) of the warp's 32 exist; mbase = their first pixel
+                    if (stem) {
+                        const uint32_t ow0 = (m_blk % p.nseg) * IGEMM_BLOCK_M + quad * 32;
+                        lim = ow0 < p.OW ? p.OW - ow0 : 0u;
+                        mbase = (m_blk / p.nseg) * p.OW + ow0;
+                    } else {
+                        mbase = static_cast<uint32_t>(m0) + quad * 32;
+                        lim = mbase < p.M ? p.M - mbase : 0u;
+                    }
+                    uint8_t* out = static_cast<uint8_t*>(p.dst) +
+                                   (static_cast<size_t>(mbase) * p.OC + col) * T::OUT_ES;
+                    const size_t pitch = static_cast<size_t>(p.OC) * T::OUT_ES;
+#pragma unroll
+                    for (uint32_t it = 0; it < 32 / ROWS_PER_IT; ++it) {
+                        const uint32_t r = it * ROWS_PER_IT + lane / PIECES_ROW;
+                        const uint32_t sw = T::ROW_BYTES == 128 ? (piece ^ (r & 7)) : (piece ^ ((r >> 1) & 3));
+                        const uint4 v = *reinterpret_cast<const uint4*>(rd + r * T::ROW_BYTES + sw * 16);
+                        if (r < lim && col < p.OC)
+                            *reinterpret_cast<uint4*>(out + r * pitch) = v;
+                    }
+                    __syncwarp();
+                    if (p.has_z && lane == 0)
+                        mbar_arrive(bar_zempty + 8 * zb);  // every lane has read the chunk's rows back
+                    db ^= (NSLAB - 1);
+                    if (++zi == ZD) {
+                        zi = 0;
+                        zphase ^= 1;
+                    }
+                    DBG_ADD(10, tst__);
+                    continue;
+                }
                 if (rows) {
                     // rows mode: the slab's 32 consecutive m' span several output rows and skip the
                     // PW - OW padding columns, which a TMA box cannot express (negative store
@@ -1168,15 +1260,19 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     tma_store_commit();
                     if (p.has_z) {
                         // the z chunk is free again once the store has read this warp's rows
+                        DBG_MARK(tzr__);
                         tma_store_wait_read<0>();
+                        DBG_ADD(11, tzr__);
                         mbar_arrive(bar_zempty + 8 * zb);
                     }
                 }
                 db ^= (NSLAB - 1);
+                if (++zi == ZD) {
+                    zi = 0;
+                    zphase ^= 1;
+                }
+                DBG_ADD(10, tst__);
             }
-            acc ^= 1;
-            if (acc == 0)
-                acc_phase ^= 1;
         }
         if (elect_one())
             tma_store_wait<0>();
@@ -1184,10 +1280,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 
 #ifdef B200CB_DEBUG_TIMING
     if (p.dbg && lane == 0 && (warp == 0 || warp == 1 || warp == 4)) {
-        long long* o = p.dbg + (static_cast<size_t>(blockIdx.x) * 3 + (warp == 4 ? 2 : warp)) * 9;
-        for (int i = 0; i < 8; ++i)
+        long long* o = p.dbg + (static_cast<size_t>(blockIdx.x) * 3 + (warp == 4 ? 2 : warp)) * 17;
+        for (int i = 0; i < 16; ++i)
             o[i] = dbg_acc[i];
-        o[8] = clock64() - dbg_t0;
+        o[16] = clock64() - dbg_t0;
     }
 #endif
     tc_fence_before();
@@ -1343,7 +1439,11 @@ cudaError_t launch_variant(
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
     cudaLaunchAttribute attr[2];
+#ifdef B200CB_TOOLS
     static const bool use_pdl = getenv("B200CB_NO_PDL") == nullptr;
+#else
+    constexpr bool use_pdl = true;
+#endif
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = use_pdl ? 1 : 0;
     attr[1].id = cudaLaunchAttributeClusterDimension;
@@ -1372,6 +1472,61 @@ cudaError_t launch_variant(
         grid = static_cast<uint32_t>(cluster_tiles) * C;
     cfg.gridDim = dim3(grid, 1, 1);
     return cudaLaunchKernelEx(&cfg, kern, p);
+}
+
+// (device, plan, tensor addresses) -> finished kernel parameters; process-wide, mutex-guarded, bounded
+struct ParamKey {
+    b200cb_plan plan;
+    const void *src, *flt, *bias, *z;
+    void* dst;
+    int dev;
+};
+class ParamCache {
+public:
+    bool lookup(const ParamKey& k, IgemmParams* out) {
+        const uint64_t h = hash(k);
+        std::lock_guard<std::mutex> lk(m_mtx);
+        auto it = m_map.find(h);
+        if (it == m_map.end() || memcmp(&it->second.key, &k, sizeof(k)) != 0)
+            return false;
+        *out = it->second.params;
+        return true;
+    }
+    void store(const ParamKey& k, const IgemmParams& p) {
+        const uint64_t h = hash(k);
+        std::lock_guard<std::mutex> lk(m_mtx);
+        if (m_map.size() >= 4096)
+            m_map.clear();
+        Entry& e = m_map[h];
+        e.key = k;
+        e.params = p;
+    }
+
+private:
+    struct Entry {
+        ParamKey key;
+        IgemmParams params;
+    };
+    static uint64_t hash(const ParamKey& k) {
+        // FNV-1a over the descriptor part of the plan and the addresses
+        uint64_t h = 1469598103934665603ull;
+        auto mix = [&](const void* p, size_t n) {
+            const unsigned char* b = static_cast<const unsigned char*>(p);
+            for (size_t i = 0; i < n; ++i)
+                h = (h ^ b[i]) * 1099511628211ull;
+        };
+        mix(&k.plan.desc, sizeof(k.plan.desc));
+        mix(&k.plan.algo, sizeof(k.plan.algo));
+        mix(k.plan.reserved, sizeof(k.plan.reserved));
+        mix(&k.src, sizeof(void*) * 5 + sizeof(int));
+        return h;
+    }
+    std::mutex m_mtx;
+    std::unordered_map<uint64_t, Entry> m_map;
+};
+ParamCache& param_cache() {
+    static ParamCache c;
+    return c;
 }
 
 // geometry actually fed to the kernel (differs from the descriptor when the conv is W-folded)
@@ -1475,13 +1630,28 @@ uint32_t pick_pair(const b200cb_desc& d, uint32_t block_n, uint32_t m_tiles) {
     const uint32_t in_es = d.src_dtype == B200CB_DT_QS8 ? 1 : 2;
     const uint64_t k_bytes = (uint64_t)d.fh * d.fw * d.ic * in_es;
     (void)block_n;
-    if (m_tiles < 148)
+    // (few M tiles are no reason not to pair: 98 tiles of ResNet-50 layer4 run 10-20 % faster as 49 pairs,
+    // tools/sweep_resnet.py r02)
+    if (m_tiles < 8)
         return 0;
     // measured crossover (tools/sweep_resnet.py): long k-loops always; 1 KiB k-loops only for wide
     // 16-bit tiles without the z stream; shorter ones are epilogue / HBM bound and lose to the pairing
     if (k_bytes >= 2048)
         return 1;
     return (in_es == 2 && k_bytes >= 1024 && !d.has_z && d.oc >= 256) ? 1u : 0u;
+}
+
+// Direct-store epilogue (IgemmParams::direct_store): layers whose k-loop is short are bound by HBM and
+// by the epilogue; there the TMA store's round trip through the (always full) TMA load queue is what
+// the epilogue warps wait for.
+bool pick_direct_store(const b200cb_desc& d, bool nchw4, bool rows) {
+    if (nchw4 || rows)
+        return false;
+    // measured (profiles/r02): with the 16-warp epilogue the TMA store wins on every ResNet-50 / MobileNet
+    // layer (bf16 step 3.47 ms vs 3.51 ms with direct stores everywhere), so the product never picks the
+    // direct path; it stays reachable through the tools build (B200CB_DIRECT=1) and its parity run.
+    (void)d;
+    return false;
 }
 
 uint32_t pick_kb_bytes(uint32_t ic_bytes) {
@@ -1657,7 +1827,7 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     const bool stem = g.stem && block_n == 64;
     const uint32_t kb_bytes = pick_kb_bytes(g.ic * in_es);
     const uint32_t fixed0 =
-            fixed_smem(out32 ? 1 : 2, block_n, d.has_z && !nchw4, (out32 || in_es == 2) ? 128 : 64);
+            fixed_smem(out32 ? 1 : 4, block_n, d.has_z && !nchw4, (out32 || in_es == 2) ? 128 : 64);
     // rows mode: the filter and >= 2 input slabs must fit next to the epilogue buffers
     const RowsGeom rg = rows_geometry(dd, in_es, block_n);
     const bool rows = !nchw4 && !stem && !g.folded && rg.ok &&
@@ -1668,14 +1838,18 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     if (!stem && !rows) {
         const uint32_t m_tiles = (uint32_t)((M + IGEMM_BLOCK_M - 1) / IGEMM_BLOCK_M);
         pair = pick_pair(d, block_n, m_tiles);
-        if (const char* e = getenv("B200CB_PAIR"))  // experiment knobs (tools/)
+#ifdef B200CB_TOOLS  // experiment knobs of the tools build (make tools); the product query is pure
+        if (const char* e = getenv("B200CB_PAIR"))
             pair = atoi(e) != 0;
+#endif
         if (m_tiles < 4)
             pair = 0;
         cluster = pair ? 2 : 1;
+#ifdef B200CB_TOOLS
         if (const char* e = getenv("B200CB_CLUSTER"))
             if (!pair)
                 cluster = (uint32_t)atoi(e);
+#endif
         if (cluster != 1 && cluster != 2 && cluster != 4)
             cluster = 1;
         while (!pair && cluster > 1 && (m_tiles < 2 * cluster || (block_n / cluster) % 8 != 0))
@@ -1700,12 +1874,10 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         const uint32_t zbuf = 128 * ((out32 || in_es == 2) ? 128 : 64);
         const uint32_t num_kb = d.fh * d.fw * ((g.ic * in_es + kb_bytes - 1) / kb_bytes);
         const uint32_t keep = num_kb >= 4 ? 3u : 2u;  // stages the main loop keeps (measured: l3.c3 wants 3)
-        if (stages > keep) {
-            const uint32_t spare = MAX_DYN_SMEM - fixed - keep * stage_b;
-            uint32_t extra = spare / zbuf;
-            if (extra > NZ_MAX - NZ_MIN)
-                extra = NZ_MAX - NZ_MIN;
-            nz = NZ_MIN + extra;
+        // the ring is GROUPS sub-rings (one per epilogue group): 4 chunks (depth 1) or 8 (depth 2)
+        const uint32_t extra = NZ_MAX - NZ_MIN;
+        if (MAX_DYN_SMEM >= fixed + extra * zbuf + keep * stage_b) {
+            nz = NZ_MAX;
             stages = (MAX_DYN_SMEM - fixed - extra * zbuf) / stage_b;
             if (stages > IGEMM_MAX_STAGES)
                 stages = IGEMM_MAX_STAGES;
@@ -1713,6 +1885,25 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         }
     }
 
+#ifdef B200CB_TOOLS
+    if (const char* e = getenv("B200CB_NZ")) {  // force the z ring depth (stages shrink to fit)
+        if (d.has_z && !nchw4 && !stem && !rows) {
+            const uint32_t zbuf = 128 * ((out32 || in_es == 2) ? 128 : 64);
+            const uint32_t want = (uint32_t)atoi(e);
+            if (want == 4 || want == 8) {
+                const uint32_t fixed_nz = fixed - NZ_MIN * zbuf + want * zbuf;
+                stages = (MAX_DYN_SMEM - fixed_nz) / stage_b;
+                if (stages > IGEMM_MAX_STAGES)
+                    stages = IGEMM_MAX_STAGES;
+                if (const char* s2 = getenv("B200CB_STAGES"))
+                    if ((uint32_t)atoi(s2) >= 1 && (uint32_t)atoi(s2) < stages)
+                        stages = (uint32_t)atoi(s2);
+                nz = want;
+                smem_total = fixed_nz + stages * stage_b;
+            }
+        }
+    }
+#endif
     plan->magic = PLAN_MAGIC;
     plan->kernel = KERNEL_IGEMM;
     plan->block_n = block_n;
@@ -1726,6 +1917,12 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         r = 0;
     plan->reserved[0] = static_cast<uint32_t>(kind);
     plan->reserved[1] = out32 ? 1 : 0;
+    // bit 0: debugging override (force the im2col path on pointwise convs); bit 1: direct-store epilogue
+    plan->reserved[2] = pick_direct_store(d, nchw4, rows) ? 2u : 0u;
+#ifdef B200CB_TOOLS
+    if (const char* e = getenv("B200CB_DIRECT"))
+        plan->reserved[2] = (atoi(e) != 0 && !nchw4 && !rows) ? 2u : 0u;
+#endif
     plan->reserved[3] = 0;  // 1: `filter` passed to launch is already packed (weight preprocess)
     plan->reserved[4] = g.folded ? 1 : 0;
     plan->reserved[5] = kb_bytes | (nz << 16);
@@ -1794,7 +1991,7 @@ int igemm_launch(
     const uint32_t row_bytes = epi_n * out_es;
     const uint32_t BN = plan.block_n;
     uint32_t a_mode = plan.a_mode;
-    if (plan.reserved[2] == 1)
+    if (plan.reserved[2] & 1)
         a_mode = 1;  // debugging override: force the im2col path on pointwise convs
 
     if (!src || !filter || !dst || (d.bias_mode != B200CB_BIAS_NONE && !bias) || (d.has_z && !z))
@@ -1841,7 +2038,16 @@ int igemm_launch(
         flt = ws_pack;
     }
 
+    // Kernel parameters (5 encoded tensor maps + scalars) are a pure function of (device, plan, tensor
+    // addresses): a steady-state network launches the same layer on the same buffers every step, so they
+    // are cached (a mutex-guarded CUtensorMap cache keyed by (device, plan)).
     IgemmParams p;
+    ParamKey key;
+    memset(&key, 0, sizeof(key));
+    key.plan = plan;
+    key.src = src, key.flt = flt, key.bias = bias, key.z = z, key.dst = dst;
+    cudaGetDevice(&key.dev);
+    auto build_params = [&]() -> int {
     memset(&p, 0, sizeof(p));
     const uint64_t M = (uint64_t)d.n * d.oh * d.ow;
     const CUtensorMapDataType in_dt =
@@ -1992,6 +2198,7 @@ int igemm_launch(
     p.has_z = d.has_z && !nchw4;
     p.nchw4 = nchw4;
     p.z_direct = d.has_z && nchw4;
+    p.direct_store = (plan.reserved[2] >> 1) & 1;
     p.z = z;
     p.nz = (plan.reserved[5] >> 16) ? (plan.reserved[5] >> 16) : NZ_MIN;
     p.nonline = d.nonline_mode;
@@ -2000,6 +2207,20 @@ int igemm_launch(
     if (const char* e = getenv("B200CB_DBG_PTR"))
         p.dbg = reinterpret_cast<long long*>(strtoull(e, nullptr, 16));
 #endif
+
+    return B200CB_OK;
+    };
+#ifdef B200CB_DEBUG_TIMING
+    const bool cached = false;
+#else
+    const bool cached = param_cache().lookup(key, &p);
+#endif
+    if (!cached) {
+        const int rc = build_params();
+        if (rc != B200CB_OK)
+            return rc;
+        param_cache().store(key, p);
+    }
 
     // the cap on the grid counts M tiles only per N tile: cluster tiles = ceil(m_tiles / C) * n_tiles
     const uint64_t total = (uint64_t)((p.m_tiles + p.cluster - 1) / p.cluster) * p.cluster * p.n_tiles;

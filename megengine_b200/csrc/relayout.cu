@@ -9,6 +9,7 @@
 // Pure HBM traffic: 32 x 32 word tiles through shared memory, both sides 128-byte coalesced.
 // Reference semantics: megdnn RelayoutFormat (dnn/src/cuda/relayout_format/), which the graph
 // optimizer inserts around NCHW4 operators (src/gopt/impl/tensor_reformat.cpp).
+#include <string.h>
 #include "common.h"
 
 namespace b200cb {
@@ -83,7 +84,217 @@ __global__ void __launch_bounds__(256) transpose_u16_kernel(
     }
 }
 
+// NHWC channel padding (gopt's PaddingChannelPass on the network input, src/gopt/impl/padding_channel.cpp):
+// in [p][C] -> out [p][Cpad], zero for c >= C.  One thread per 16 output bytes; E = element type.
+template <typename E>
+__global__ void __launch_bounds__(256) pad_channels_kernel(
+        const E* __restrict__ in, E* __restrict__ out, uint64_t total_out, uint32_t C, uint32_t Cpad) {
+    constexpr uint32_t V = 16 / sizeof(E);
+    const uint64_t nvec = (total_out + V - 1) / V;
+    for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < nvec;
+         t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t i0 = t * V;
+        uint64_t pix = i0 / Cpad;
+        uint32_t c = static_cast<uint32_t>(i0 - pix * Cpad);
+        E v[V];
+#pragma unroll
+        for (uint32_t k = 0; k < V; ++k) {
+            v[k] = (c < C && i0 + k < total_out) ? in[pix * C + c] : E(0);
+            if (++c == Cpad)
+                c = 0, ++pix;
+        }
+        if (i0 + V <= total_out) {
+            *reinterpret_cast<uint4*>(out + i0) = *reinterpret_cast<const uint4*>(v);
+        } else {
+            for (uint32_t k = 0; i0 + k < total_out; ++k)
+                out[i0 + k] = v[k];
+        }
+    }
+}
+
+// Batched transpose of W-byte words through shared memory: in[b][r][s] -> out[b][s][r'], r' < out_ld,
+// zero words for r >= R (channel padding) -- both sides coalesced.  W = 1, 2, 4, 8 or 16 bytes: plain
+// elements (NCHW <-> NHWC) or the 4-element groups of NCHW4 (NCHW4 <-> NHWC).
+template <typename W>
+__global__ void __launch_bounds__(256) transpose_any_kernel(
+        const W* __restrict__ in, W* __restrict__ out, uint32_t R, uint32_t S, uint32_t out_ld) {
+    __shared__ W tile[32][32 + (sizeof(W) >= 4 ? 1 : 4 / sizeof(W))];
+    const uint32_t b = blockIdx.z;
+    const uint32_t s0 = blockIdx.x * 32, r0 = blockIdx.y * 32;
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const W* src = in + static_cast<size_t>(b) * R * S;
+    W zero;
+    memset(&zero, 0, sizeof(W));
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t r = r0 + ty + 8 * i, sidx = s0 + tx;
+        tile[ty + 8 * i][tx] = (r < R && sidx < S) ? src[static_cast<size_t>(r) * S + sidx] : zero;
+    }
+    __syncthreads();
+    W* dst = out + static_cast<size_t>(b) * S * out_ld;
+#pragma unroll
+    for (uint32_t i = 0; i < 4; ++i) {
+        const uint32_t sidx = s0 + ty + 8 * i, r = r0 + tx;
+        if (sidx < S && r < out_ld)
+            dst[static_cast<size_t>(sidx) * out_ld + r] = tile[tx][ty + 8 * i];
+    }
+}
+
+// NCHW <-> NCHW4 and the small-channel NHWC -> NCHW4 case: one thread per (image, channel group, pixel);
+// the plane side is coalesced across the warp, the grouped side is 4 contiguous elements per thread.
+//   DIR 0: (n,c,p) -> (n,c4o,p,4)    DIR 1: (n,c4,p,4) -> (n,co,p)    DIR 2: (n,p,c) -> (n,c4o,p,4)
+template <typename E, int DIR>
+__global__ void __launch_bounds__(256) group4_kernel(
+        const E* __restrict__ in, E* __restrict__ out, uint32_t N, uint32_t C, uint32_t P, uint32_t Cout) {
+    const uint32_t groups = ((DIR == 1 ? C : Cout) + 3) / 4;
+    const uint64_t total = static_cast<uint64_t>(N) * groups * P;
+    for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint32_t p = static_cast<uint32_t>(t % P);
+        const uint32_t g = static_cast<uint32_t>((t / P) % groups);
+        const uint64_t n = t / (static_cast<uint64_t>(P) * groups);
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+            const uint32_t c = g * 4 + k;
+            if (DIR == 0) {
+                out[((n * groups + g) * P + p) * 4 + k] = c < C ? in[(n * C + c) * P + p] : E(0);
+            } else if (DIR == 1) {
+                if (c < Cout)
+                    out[(n * Cout + c) * P + p] = in[((n * groups + g) * P + p) * 4 + k];
+            } else {
+                out[((n * groups + g) * P + p) * 4 + k] = c < C ? in[(n * P + p) * C + c] : E(0);
+            }
+        }
+    }
+}
+
+template <typename W>
+int launch_transpose_any(const void* in, void* out, uint32_t B, uint32_t R, uint32_t S, uint32_t out_ld, cudaStream_t st) {
+    dim3 grid((S + 31) / 32, (out_ld + 31) / 32, B);
+    if (grid.y > 65535 || grid.z > 65535)
+        return B200CB_UNSUPPORTED_SHAPE;
+    transpose_any_kernel<W><<<grid, 256, 0, st>>>(static_cast<const W*>(in), static_cast<W*>(out), R, S, out_ld);
+    return B200CB_OK;
+}
+int transpose_words(uint32_t wbytes, const void* in, void* out, uint32_t B, uint32_t R, uint32_t S, uint32_t out_ld,
+                    cudaStream_t st) {
+    switch (wbytes) {
+        case 1: return launch_transpose_any<uint8_t>(in, out, B, R, S, out_ld, st);
+        case 2: return launch_transpose_any<uint16_t>(in, out, B, R, S, out_ld, st);
+        case 4: return launch_transpose_any<uint32_t>(in, out, B, R, S, out_ld, st);
+        case 8: return launch_transpose_any<uint2>(in, out, B, R, S, out_ld, st);
+        case 16: return launch_transpose_any<uint4>(in, out, B, R, S, out_ld, st);
+        default: return B200CB_UNSUPPORTED_DTYPE;
+    }
+}
+template <int DIR>
+int launch_group4(uint32_t es, const void* in, void* out, uint32_t N, uint32_t C, uint32_t P, uint32_t Cout, cudaStream_t st) {
+    const uint64_t total = static_cast<uint64_t>(N) * (((DIR == 1 ? C : Cout) + 3) / 4) * P;
+    uint64_t blocks = (total + 255) / 256;
+    const uint64_t cap = static_cast<uint64_t>(device_sm_count()) * 32;
+    if (blocks > cap)
+        blocks = cap;
+    const dim3 grid(static_cast<uint32_t>(blocks), 1, 1);
+    if (es == 1)
+        group4_kernel<uint8_t, DIR><<<grid, 256, 0, st>>>(static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), N, C, P, Cout);
+    else if (es == 2)
+        group4_kernel<uint16_t, DIR><<<grid, 256, 0, st>>>(static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), N, C, P, Cout);
+    else if (es == 4)
+        group4_kernel<uint32_t, DIR><<<grid, 256, 0, st>>>(static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), N, C, P, Cout);
+    else
+        return B200CB_UNSUPPORTED_DTYPE;
+    return B200CB_OK;
+}
+
 }  // namespace
+
+// b200cb_relayout: see include/b200cb.h.  Every mode is pure HBM traffic (read src once, write dst once).
+int relayout_generic(
+        uint32_t mode, uint32_t es, uint32_t n, uint32_t c, uint32_t h, uint32_t w, uint32_t c_out, const void* src,
+        void* dst, cudaStream_t stream) {
+    if (es != 1 && es != 2 && es != 4)
+        return B200CB_UNSUPPORTED_DTYPE;
+    const uint64_t p64 = static_cast<uint64_t>(h) * w;
+    if (p64 > 0x7fffffffull)
+        return B200CB_UNSUPPORTED_SHAPE;
+    const uint32_t P = static_cast<uint32_t>(p64);
+    int rc;
+    switch (mode) {
+        case B200CB_RELAYOUT_NCHW_NHWC:   // (n, c, P) -> (n, P, c_out), c_out >= c
+            if (c_out < c)
+                return B200CB_UNSUPPORTED_SHAPE;
+            rc = transpose_words(es, src, dst, n, c, P, c_out, stream);
+            break;
+        case B200CB_RELAYOUT_NHWC_NCHW:   // (n, P, c) -> (n, c_out, P): padded or cropped channel planes
+            rc = transpose_words(es, src, dst, n, P, c, P, stream);
+            if (rc == B200CB_OK && c_out != c)
+                return B200CB_UNSUPPORTED_SHAPE;  // (same channel count only: planes are written whole)
+            break;
+        case B200CB_RELAYOUT_NCHW_NCHW4:
+            if (c_out % 4 || c_out < c)
+                return B200CB_UNSUPPORTED_SHAPE;
+            rc = launch_group4<0>(es, src, dst, n, c, P, c_out, stream);
+            break;
+        case B200CB_RELAYOUT_NCHW4_NCHW:
+            if (c % 4 || c_out > c)
+                return B200CB_UNSUPPORTED_SHAPE;
+            rc = launch_group4<1>(es, src, dst, n, c, P, c_out, stream);
+            break;
+        case B200CB_RELAYOUT_NCHW4_NHWC:  // words of 4 elements: (n, c/4, P) -> (n, P, c_out/4)
+            if (c % 4 || c_out % 4 || c_out < c)
+                return B200CB_UNSUPPORTED_SHAPE;
+            rc = transpose_words(4 * es, src, dst, n, c / 4, P, c_out / 4, stream);
+            break;
+        case B200CB_RELAYOUT_NHWC_NCHW4:
+            if (c_out % 4 || c_out < c)
+                return B200CB_UNSUPPORTED_SHAPE;
+            if (c % 4 == 0 && c_out == c)
+                rc = transpose_words(4 * es, src, dst, n, P, c / 4, P, stream);
+            else
+                rc = launch_group4<2>(es, src, dst, n, c, P, c_out, stream);  // small / ragged channel counts
+            break;
+        case B200CB_RELAYOUT_NHWC_PAD_C:
+            return relayout_pad_channels(src, dst, static_cast<uint64_t>(n) * P, c, c_out, es, stream);
+        default:
+            return B200CB_UNSUPPORTED_PARAM;
+    }
+    if (rc != B200CB_OK)
+        return rc;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("relayout launch", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    return B200CB_OK;
+}
+
+int relayout_pad_channels(
+        const void* in, void* out, uint64_t pixels, uint32_t C, uint32_t Cpad, uint32_t es, cudaStream_t stream) {
+    if (pixels == 0 || C == 0 || Cpad < C || (es != 1 && es != 2 && es != 4))
+        return B200CB_UNSUPPORTED_SHAPE;
+    const uint64_t total = pixels * Cpad;
+    const uint64_t nvec = (total + 16 / es - 1) / (16 / es);
+    uint64_t blocks = (nvec + 255) / 256;
+    const uint64_t cap = static_cast<uint64_t>(device_sm_count()) * 32;
+    if (blocks > cap)
+        blocks = cap;
+    const dim3 grid(static_cast<uint32_t>(blocks), 1, 1);
+    if (es == 1)
+        pad_channels_kernel<uint8_t><<<grid, 256, 0, stream>>>(
+                static_cast<const uint8_t*>(in), static_cast<uint8_t*>(out), total, C, Cpad);
+    else if (es == 2)
+        pad_channels_kernel<uint16_t><<<grid, 256, 0, stream>>>(
+                static_cast<const uint16_t*>(in), static_cast<uint16_t*>(out), total, C, Cpad);
+    else
+        pad_channels_kernel<uint32_t><<<grid, 256, 0, stream>>>(
+                static_cast<const uint32_t*>(in), static_cast<uint32_t*>(out), total, C, Cpad);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("pad_channels launch", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    return B200CB_OK;
+}
 
 int relayout_transpose16(
         const void* in, void* out, uint32_t B, uint32_t R, uint32_t S, uint32_t out_ld, uint64_t in_batch,

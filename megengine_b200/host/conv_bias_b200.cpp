@@ -4,7 +4,9 @@
 
 #include <cstring>
 #include <limits>
+#include <mutex>
 #include <stdexcept>
+#include <unordered_map>
 
 namespace megdnn {
 namespace b200 {
@@ -62,6 +64,24 @@ float dtype_scale(const DType& dt) {
         return dt.param<dtype::QuantizedS32>().scale;
     return 0.f;
 }
+// true when only stride[0] differs from the contiguous layout; *batch_stride = stride[0] then (0 when
+// the tensor is fully contiguous, the C-ABI's "dense" value)
+bool batch_stride_only(const TensorLayout& l, uint64_t* batch_stride) {
+    *batch_stride = 0;
+    if (l.ndim == 0 || l.is_contiguous())
+        return true;
+    ptrdiff_t expect = 1;
+    for (size_t i = l.ndim; i-- > 1;) {
+        if (l.shape[i] != 1 && l.stride[i] != expect)
+            return false;
+        expect *= static_cast<ptrdiff_t>(l.shape[i]);
+    }
+    if (l.stride[0] < expect)
+        return false;
+    *batch_stride = static_cast<uint64_t>(l.stride[0]);
+    return true;
+}
+
 // megdnn_throw / megdnn_assert live in the reference's private dnn/src/common/utils.h; the public
 // hook they end in is ErrorHandler::on_megdnn_error (dnn/include/megdnn/basic_types.h:21-58)
 [[noreturn]] void b200_throw(const std::string& msg) {
@@ -133,17 +153,19 @@ b200cb_desc ConvBiasForwardImpl::make_desc(
         d.bias_mode = bias.eq_shape(dst) ? B200CB_BIAS_FULL : B200CB_BIAS_CHANNEL;
         d.bias_dtype = dtype_code(bias.dtype), d.bias_scale = dtype_scale(bias.dtype);
     }
+    // A non-contiguous BATCH stride must be accepted (dnn/src/cuda/conv_bias/algo.h:32-37); any other
+    // non-contiguity (channel- or W-sliced views forwarded by Subtensor / Concat) passes the reference's
+    // check_exec_allow_noncontiguous and has to be rejected per algorithm, as the reference's CUDA algos
+    // do (`!src_layout->is_contiguous()` -> unavailable): the descriptor is then marked unsupported.
+    bool ok = filter.is_contiguous() && (bias.ndim == 0 || bias.is_contiguous());
+    ok = ok && batch_stride_only(src, &d.src_batch_stride) && batch_stride_only(dst, &d.dst_batch_stride);
     if (z.ndim != 0) {
         d.has_z = 1;
         d.z_dtype = dtype_code(z.dtype), d.z_scale = dtype_scale(z.dtype);
-        if (!z.is_contiguous())
-            d.z_batch_stride = static_cast<uint64_t>(z.stride[0]);
+        ok = ok && batch_stride_only(z, &d.z_batch_stride);
     }
-    // non-contiguous batch stride must be accepted (dnn/src/cuda/conv_bias/algo.h:32-37)
-    if (!src.is_contiguous())
-        d.src_batch_stride = static_cast<uint64_t>(src.stride[0]);
-    if (!dst.is_contiguous())
-        d.dst_batch_stride = static_cast<uint64_t>(dst.stride[0]);
+    if (!ok)
+        d.format = 0xffu;  // b200cb_query: B200CB_UNSUPPORTED_FORMAT -> is_available() == false
     return d;
 }
 
@@ -198,16 +220,69 @@ detail::Algorithm* ConvBiasForwardImpl::get_algorithm_from_desc(const AlgorithmD
     b200_throw("can not find the B200 conv_bias algorithm of this desc");
 }
 
+// The reference resolves an algorithm in three steps -- execution_policy().algo, the process-wide
+// AlgorithmCache (keyed by the serialised layouts + param, dnn/include/megdnn/algorithm_cache.h:12-80,
+// dnn/src/common/algo_chooser.h:24-50), then the heuristic.  Same here: the cache maps the POD descriptor
+// (which carries every field of the layouts and the param that the algorithms look at) + the forced
+// algorithm to the finished plan, so that exec() / get_workspace_in_bytes() of a steady-state network
+// cost one hash lookup instead of a query over the whole algorithm table.
+namespace {
+struct PlanCache {
+    struct Key {
+        b200cb_desc desc;
+        int algo;  // -1: heuristic
+        bool operator==(const Key& o) const { return algo == o.algo && !memcmp(&desc, &o.desc, sizeof(desc)); }
+    };
+    struct Hash {
+        size_t operator()(const Key& k) const {
+            // FNV-1a over the POD (memset-initialised, so padding bytes are deterministic)
+            const unsigned char* p = reinterpret_cast<const unsigned char*>(&k.desc);
+            uint64_t h = 1469598103934665603ull ^ static_cast<uint64_t>(k.algo + 1);
+            for (size_t i = 0; i < sizeof(k.desc); ++i)
+                h = (h ^ p[i]) * 1099511628211ull;
+            return static_cast<size_t>(h);
+        }
+    };
+    std::mutex mtx;
+    std::unordered_map<Key, b200cb_plan, Hash> map;
+    size_t hits = 0, misses = 0;
+};
+PlanCache& plan_cache() {
+    static PlanCache c;
+    return c;
+}
+}  // namespace
+
 void ConvBiasForwardImpl::resolve_plan(const b200cb_desc& desc, b200cb_plan* plan) {
-    int rc;
-    if (execution_policy().algo.valid()) {
-        auto* a = static_cast<AlgoB200*>(get_algorithm_from_desc(execution_policy().algo));
-        rc = b200cb_query_algo(&desc, a->index(), plan);
-    } else {
-        rc = b200cb_query(&desc, plan);
+    PlanCache::Key key;
+    key.desc = desc;
+    key.algo = -1;
+    if (execution_policy().algo.valid())
+        key.algo = static_cast<AlgoB200*>(get_algorithm_from_desc(execution_policy().algo))->index();
+    PlanCache& cache = plan_cache();
+    {
+        std::lock_guard<std::mutex> lk(cache.mtx);
+        auto it = cache.map.find(key);
+        if (it != cache.map.end()) {
+            ++cache.hits;
+            *plan = it->second;
+            return;
+        }
+        ++cache.misses;
     }
+    const int rc = key.algo >= 0 ? b200cb_query_algo(&desc, key.algo, plan) : b200cb_query(&desc, plan);
     if (rc != B200CB_OK)
         throw_rc("query", rc);
+    std::lock_guard<std::mutex> lk(cache.mtx);
+    if (cache.map.size() >= 4096)
+        cache.map.clear();  // bounded like the reference's per-opr caches
+    cache.map.emplace(key, *plan);
+}
+
+void plan_cache_stats(size_t* hits, size_t* misses) {
+    PlanCache& cache = plan_cache();
+    std::lock_guard<std::mutex> lk(cache.mtx);
+    *hits = cache.hits, *misses = cache.misses;
 }
 
 size_t ConvBiasForwardImpl::get_workspace_in_bytes(

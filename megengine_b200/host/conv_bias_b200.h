@@ -78,6 +78,10 @@ private:
     cudaStream_t m_stream;
 };
 
+//! hit / miss counters of the process-wide (descriptor, forced algorithm) -> plan cache (the
+//! AlgorithmCache equivalent, dnn/include/megdnn/algorithm_cache.h:12-80)
+void plan_cache_stats(size_t* hits, size_t* misses);
+
 //! what handle->create_operator<ConvBiasForward>() returns for this backend
 std::unique_ptr<ConvBiasForward> create_conv_bias_forward(Handle* handle, cudaStream_t stream);
 

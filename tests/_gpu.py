@@ -56,7 +56,7 @@ def run_gpu(d, src, flt, bias, z, algo=None, force_im2col=False):
     if rc != 0:
         raise C.B200CBError(rc, "b200cb_query")
     if force_im2col:
-        plan.reserved[2] = 1
+        plan.reserved[2] |= 1
     tsrc, tflt, tbias, tz = to_dev(src), to_dev(flt), to_dev(bias), to_dev(z)
     np_dt = O.NP_STORAGE[d.dst_dtype]
     n_dst = O.dst_elems(d)

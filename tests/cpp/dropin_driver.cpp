@@ -10,6 +10,8 @@
 // Float16 with the reference test's own eps (2e-2 / 2e-2, metric dnn/test/common/utils.h:189-193).
 #include <cuda_runtime.h>
 
+#include <time.h>
+
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -253,6 +255,73 @@ int main() {
         }
         printf("%s %-28s\n", threw ? "PASS" : "FAIL", "unsupported_cell_throws");
         failed += !threw;
+    }
+    // layouts that are non-contiguous in anything but the batch stride pass the reference's
+    // check_exec_allow_noncontiguous and must be reported as "no algorithm available" (the reference's CUDA
+    // algos: `!src_layout->is_contiguous()` -> unavailable), never run as if they were dense.
+    {
+        auto dut = b200::create_conv_bias_forward(host.get(), stream);
+        auto& p = dut->param();
+        p.format = F::NHWC;
+        p.pad_h = p.pad_w = 1;
+        p.compute_mode = param::ConvBias::ComputeMode::FLOAT32;
+        DType bf = dtype::BFloat16();
+        TensorLayout s({2, 14, 14, 64}, bf), f({64, 3, 3, 64}, bf), b({1, 1, 1, 64}, bf), z{bf}, d({2, 14, 14, 64}, bf);
+        const size_t n_dense = dut->get_all_algorithms_info(s, f, b, z, d).size();
+        TensorLayout s_batch = s;   // batch-strided view: must stay available
+        s_batch.stride[0] = s.stride[0] + 4096;
+        const size_t n_batch = dut->get_all_algorithms_info(s_batch, f, b, z, d).size();
+        TensorLayout s_chan = s;    // channel-sliced view of a 128-channel tensor: pixel stride 128
+        s_chan.stride[2] = 128, s_chan.stride[1] = 128 * 14, s_chan.stride[0] = 128 * 14 * 14;
+        const size_t n_chan = dut->get_all_algorithms_info(s_chan, f, b, z, d).size();
+        TensorLayout d_w = d;       // W-sliced dst view
+        d_w.stride[1] = 64 * 20, d_w.stride[0] = 64 * 20 * 14;
+        const size_t n_w = dut->get_all_algorithms_info(s, f, b, z, d_w).size();
+        const bool ok = n_dense >= 1 && n_batch == n_dense && n_chan == 0 && n_w == 0;
+        printf("%s %-28s dense %zu batch-strided %zu channel-sliced %zu w-sliced %zu\n", ok ? "PASS" : "FAIL",
+               "noncontiguous_views", n_dense, n_batch, n_chan, n_w);
+        failed += !ok;
+    }
+    // a14: the plan cache (AlgorithmCache equivalent) must serve the repeated exec / get_workspace_in_bytes
+    // calls of the cases above
+    {
+        size_t hits = 0, misses = 0;
+        b200::plan_cache_stats(&hits, &misses);
+        const bool ok = hits > 0 && misses > 0;
+        printf("%s %-28s hits %zu misses %zu\n", ok ? "PASS" : "FAIL", "plan_cache", hits, misses);
+        failed += !ok;
+    }
+    // host cost of one exec() through the C++ binding (check_exec + descriptor + cached plan + launch),
+    // measured on an enqueue-only loop: the stream is synchronised outside the timed region
+    {
+        auto dut = b200::create_conv_bias_forward(host.get(), stream);
+        auto& p = dut->param();
+        p.format = F::NHWC;
+        p.nonlineMode = NL::RELU;
+        p.compute_mode = param::ConvBias::ComputeMode::FLOAT32;
+        DType bf = dtype::BFloat16();
+        TensorLayout s({8, 14, 14, 256}, bf), f({256, 1, 1, 256}, bf), b({1, 1, 1, 256}, bf), z{bf}, d({8, 14, 14, 256}, bf);
+        DevBuf ds(s.span().dist_byte()), df(f.span().dist_byte()), db(b.span().dist_byte()), dd(d.span().dist_byte());
+        CUDA_OK(cudaMemsetAsync(ds.p, 0, s.span().dist_byte(), stream));
+        CUDA_OK(cudaMemsetAsync(df.p, 0, f.span().dist_byte(), stream));
+        CUDA_OK(cudaMemsetAsync(db.p, 0, b.span().dist_byte(), stream));
+        const size_t ws = dut->get_workspace_in_bytes(s, f, b, z, d, nullptr);
+        DevBuf dws(ws);
+        auto run = [&](int n) {
+            for (int i = 0; i < n; ++i)
+                dut->exec(TensorND(ds.p, s), TensorND(df.p, f), TensorND(db.p, b), TensorND(nullptr, z),
+                          TensorND(dd.p, d), nullptr, Workspace((dt_byte*)dws.p, ws));
+        };
+        run(20);
+        CUDA_OK(cudaStreamSynchronize(stream));
+        const int reps = 2000;
+        timespec t0, t1;
+        clock_gettime(CLOCK_MONOTONIC, &t0);
+        run(reps);
+        clock_gettime(CLOCK_MONOTONIC, &t1);
+        CUDA_OK(cudaStreamSynchronize(stream));
+        const double us = ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 1e3 / reps;
+        printf("INFO host_us_per_exec %.2f (C++ binding, enqueue only, %d execs)\n", us, reps);
     }
     printf("dropin_driver: %d failed\n", failed);
     return failed ? 1 : 0;

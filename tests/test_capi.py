@@ -163,7 +163,7 @@ def test_product_has_no_oracle_or_cpu_fallback():
     pkg = os.path.join(ROOT, "megengine_b200")
     for dirpath, _dn, files in os.walk(pkg):
         for f in files:
-            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", "Makefile")):
+            if f.endswith((".py", ".cu", ".cpp", ".h", ".cuh", ".sh", ".mk", ".txt", "Makefile")):
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 for needle in ("liboracle", "ref_driver", "_oracle", "oracle/", "oracle_convbias", "libmegdnn"):
                     assert needle not in text, (f, needle)

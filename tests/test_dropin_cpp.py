@@ -2,7 +2,8 @@
 megdnn::ConvBiasForward built against the reference's own headers) driven like the reference's
 Checker drives a backend: expected values from the reference's naive operator, every algorithm
 forced through execution_policy(), QuantizedS8 bit-exact, bf16 / fp16 at the reference tests' eps.
-The binaries are built where /root/reference exists (megengine_b200/host/build_host.sh) and travel
+The binaries are built where /root/reference exists (tests/cpp/build_host.sh, into oracle/_ref: the
+binding links the reference's megdnn common layer, so it is not part of the product package) and travel
 to the GPU box with the snapshot."""
 import ctypes
 import os
@@ -11,7 +12,7 @@ import subprocess
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HOST_LIB = os.path.join(ROOT, "megengine_b200", "lib", "libmegdnn_b200.so")
+HOST_LIB = os.path.join(ROOT, "oracle", "_ref", "libmegdnn_b200.so")
 DRIVER = os.path.join(ROOT, "oracle", "_ref", "dropin_driver")
 
 

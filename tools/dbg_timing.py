@@ -8,14 +8,16 @@ import ctypes, os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import torch
-dbg = torch.zeros(148 * 3 * 9, dtype=torch.int64, device="cuda")
+NC = 17  # 16 counters + the role's total
+dbg = torch.zeros(148 * 3 * NC, dtype=torch.int64, device="cuda")
 os.environ["B200CB_DBG_PTR"] = hex(dbg.data_ptr())
 from megengine_b200 import _capi as C
 from tests import _cases as K
 lib = C.load()
 kind = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 only = set(sys.argv[2:])
-names = ["empty", "tempty", "full", "tfull", "zfull", "zempty", "bres", "stwait"]
+names = ["empty", "tempty", "full", "tfull", "zfull", "zempty", "bres", "stwait", "tmem_ld", "body", "store", "zstore_rd",
+         "x12", "x13", "x14", "x15"]
 # "pw" as the only layer name: the MobileNet pointwise table (tools/bench_layers.py) instead of ResNet-50
 if only == {"pw"}:
     from tools.bench_layers import MOBILENET_PW
@@ -42,10 +44,10 @@ for layer, d in work:
                                torch.cuda.current_stream().cuda_stream)
         assert rc == 0
         torch.cuda.synchronize()
-    t = dbg.view(148, 3, 9).double()
-    used = t[:, 0, 8] > 0
+    t = dbg.view(148, 3, NC).double()
+    used = t[:, 1, NC - 1] > 0.5 * t[:, 1, NC - 1].max()  # CTAs whose MMA warp ran (pair: the leaders)
     t = t[used].mean(0)
-    tot = t[:, 8]
-    fmt = lambda role: " ".join("%s %4.1f%%" % (names[i], 100 * t[role, i] / tot[role]) for i in range(8) if t[role, i] > 0.005 * tot[role])
+    tot = t[:, NC - 1]
+    fmt = lambda role: " ".join("%s %4.1f%%" % (names[i], 100 * t[role, i] / tot[role]) for i in range(16) if t[role, i] > 0.005 * tot[role])
     print("%-10s mode %d bn %3d stages %2d  cycles %8.0f | producer: %s | mma: %s | epi(w4): %s" % (
         layer[0], plan.a_mode, plan.block_n, plan.stages, tot[1], fmt(0), fmt(1), fmt(2)))

@@ -59,6 +59,7 @@ def main():
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--only", default="")
     ap.add_argument("--out", default="")
+    ap.add_argument("--verbose", action="store_true")
     a = ap.parse_args()
     lib = C.load()
     rows = []
@@ -81,6 +82,9 @@ def main():
                     continue
                 if pair and not plan.reserved[7]:
                     continue
+                if a.verbose:
+                    print("  %s %s pair %d stages %d smem %d nz %d ..." % (name, nm, pair, plan.stages, plan.smem_bytes,
+                                                                       plan.reserved[5] >> 16), flush=True)
                 ms = time_plan(lib, plan, d, a.reps)
                 res["%s%s" % (nm.split("_")[-1], "p" if pair else "")] = round(ms, 4)
         os.environ.pop("B200CB_PAIR", None)
