@@ -17,6 +17,7 @@ Device memory and streams come from torch (plumbing); all compute goes through t
 (include/b200cb.h) into hand-written sm_100a kernels. There is no fallback path.
 """
 import ctypes
+import threading
 from dataclasses import dataclass, field
 from typing import List, Optional, Tuple
 
@@ -428,11 +429,45 @@ class ConvBiasForward:
     def get_algorithm_set_name():
         return "CONV_BIAS_B200"
 
+    # ------------------------------------------------------------------ algorithm cache
+    # megdnn resolves an algorithm in three steps: execution_policy().algo, the process-wide AlgorithmCache
+    # keyed by the serialised layouts + param (dnn/include/megdnn/algorithm_cache.h:12-80,
+    # dnn/src/common/algo_chooser.h:24-50), then the heuristic.  Same here: steady-state exec() /
+    # get_workspace_in_bytes() calls cost one dictionary lookup instead of check_exec + descriptor + query.
+    _algorithm_cache = {}
+    _algorithm_cache_lock = threading.Lock()
+    cache_hits = 0
+    cache_misses = 0
+
+    @staticmethod
+    def _layout_key(lay: TensorLayout):
+        return (tuple(lay.shape), lay.dtype, None if lay.stride is None else tuple(lay.stride))
+
+    def _cached_plan(self, src, flt, bias, z, dst) -> C.Plan:
+        p = self.param
+        algo = self.execution_policy.algo
+        key = (p.nonlineMode, p.mode, p.sparse, p.format, p.pad_h, p.pad_w, p.stride_h, p.stride_w, p.dilate_h,
+               p.dilate_w, p.compute_mode, -1 if algo is None else algo.algo_id,
+               self._layout_key(src), self._layout_key(flt), self._layout_key(bias), self._layout_key(z),
+               self._layout_key(dst))
+        cls = ConvBiasForward
+        plan = cls._algorithm_cache.get(key)
+        if plan is not None:
+            cls.cache_hits += 1
+            return plan
+        plan = self._plan(self.make_desc(src, flt, bias, z, dst))
+        with cls._algorithm_cache_lock:
+            if len(cls._algorithm_cache) >= 4096:
+                cls._algorithm_cache.clear()
+            cls._algorithm_cache[key] = plan
+            cls.cache_misses += 1
+        return plan
+
     def get_workspace_in_bytes(self, src, flt, bias, z, dst, preprocessed_filter=None) -> int:
-        return int(self._plan(self.make_desc(src, flt, bias, z, dst)).workspace_bytes)
+        return int(self._cached_plan(src, flt, bias, z, dst).workspace_bytes)
 
     def get_plan(self, src, flt, bias, z, dst) -> C.Plan:
-        return self._plan(self.make_desc(src, flt, bias, z, dst))
+        return self._cached_plan(src, flt, bias, z, dst)
 
     # ------------------------------------------------------------------ exec
     def exec(self, src: TensorND, flt: TensorND, bias: TensorND, z: TensorND, dst: TensorND,
@@ -440,11 +475,18 @@ class ConvBiasForward:
         """Enqueue on the handle's stream and return (no synchronisation), like
         cuda::ConvBiasForwardImpl::exec (dnn/src/cuda/conv_bias/opr_impl.cpp:16-28)."""
         if plan is None:
-            plan = self._plan(self.make_desc(src.layout, flt.layout, bias.layout, z.layout, dst.layout))
+            plan = self._cached_plan(src.layout, flt.layout, bias.layout, z.layout, dst.layout)
         ws_bytes = int(plan.workspace_bytes)
         if ws_bytes:
             megdnn_assert(workspace is not None and workspace.numel() * workspace.element_size() >= ws_bytes,
                           "workspace too small: need %d bytes" % ws_bytes)
+        dev = self.handle.device
+        megdnn_assert(src.tensor.device == dev and dst.tensor.device == dev,
+                      "tensors must live on the handle's device %s" % dev)
+        if torch.cuda.current_device() != (dev.index or 0):
+            # the C side keys function attributes / SM count on the current device (ADVICE r1)
+            with torch.cuda.device(dev):
+                return self.exec(src, flt, bias, z, dst, preprocessed_filter, workspace, plan)
         stream = self.handle.stream
         rc = self._lib.b200cb_launch(
             ctypes.byref(plan), src.raw_ptr, flt.raw_ptr,

@@ -63,6 +63,12 @@ struct IgemmParams {
     // stem4: a pixel PAIR is one 16-byte unit (IC * es == 8, e.g. bf16 IC = 4): a single plane, K step =
     // two consecutive pairs (LBO = 16 B), filter rows of 64 bytes (SWIZZLE_64B)
     uint32_t stem4;
+    // stem "row ring" (stem4, one segment per output row): input rows arrive as whole contiguous boxes, two
+    // rows (one even / odd row pair) per box, into a ring of STEM_RING_PAIRS pair slots; consecutive output
+    // rows of an image share all but one pair, and every CTA walks a contiguous range of output rows
+    uint32_t stem_ring;      // 0 = off
+    uint32_t stem_rowb;      // bytes of one staged input row (stem_nj pixel pairs x 16)
+    uint32_t stem_np;        // row pairs one output row needs: ceil((FH + (pad_h & 1)) / 2)
     // rows mode (a_mode 3): stride-1 conv over the padded-linear pixel index m' = oh * PW + ow',
     // PW = OW + FW - 1; a tile = 128 consecutive m' of one image, its input rows resident in smem
     uint32_t PW, tiles_per_img, rows_rh;
@@ -171,6 +177,7 @@ constexpr uint32_t OFF_BRES = 456;     // stem: resident filter barrier
 // more A/B stages
 constexpr uint32_t NZ_MIN = 4, NZ_MAX = 8;  // GROUPS sub-rings of depth 1 or 2 (see the z prefetch warp)
 constexpr uint32_t STEM_NJ_K = 136;    // pixel pairs per staged stem input row (== STEM_NJ on the host)
+constexpr uint32_t STEM_RING_PAIRS = 16, STEM_RING_AHEAD = 4;  // row-pair slots; tiles the producer runs ahead
 constexpr uint32_t OFF_BIAS = 1024;    // 1 KiB: per epilogue group the 64 bias values of its chunk (OUT32: the tile's BN)
 // host mirror of Traits::slabs_bytes
 __host__ __device__ constexpr uint32_t slabs_bytes(uint32_t groups, uint32_t /*bn*/, uint32_t row_bytes) {
@@ -360,6 +367,12 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     const uint32_t cl_id = blockIdx.x / C, cl_num = gridDim.x / C;
     const uint32_t total_ct = ((p.m_tiles + C - 1) / C) * p.n_tiles;
     const uint16_t cmask = static_cast<uint16_t>((1u << C) - 1);
+    // tiles of this CTA (cluster): ct = t_first, t_first + t_step, ... < t_end.  Round robin over the grid,
+    // except for the stem's row ring, where every CTA owns a contiguous range of output rows
+    const bool ring = p.stem_ring != 0;
+    const uint32_t t_first = ring ? static_cast<uint32_t>(static_cast<uint64_t>(blockIdx.x) * total_ct / gridDim.x) : cl_id;
+    const uint32_t t_end = ring ? static_cast<uint32_t>(static_cast<uint64_t>(blockIdx.x + 1) * total_ct / gridDim.x) : total_ct;
+    const uint32_t t_step = ring ? 1u : cl_num;
 
     if (warp == 0 && lane == 0) {
         prefetch_tensormap(&p.tmA);
@@ -410,7 +423,99 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     pdl_launch_dependents();
     pdl_wait();
 
-    if (warp == 0 && stem) {
+    if (warp == 0 && ring) {
+        // ============================ TMA producer, stem row ring ============================
+        // tile = output row (img, oh) of the CTA's contiguous range.  Its window is the last stem_np row
+        // pairs loaded: a tile that continues the previous one's image loads ONE new pair (2 input rows,
+        // one box), the first tile of the range / of an image loads all stem_np.  Pair seq q lives in ring
+        // slot q % STEM_RING_PAIRS; tile t is loaded once tile t - STEM_RING_AHEAD has been consumed, which
+        // keeps every slot it overwrites (seq <= q - 16) clear of the windows still in use (a tile adds at
+        // most stem_np = 4 pairs: 16 >= 4 * STEM_RING_AHEAD).
+        if (elect_one()) {
+            mbar_arrive_expect_tx(bar_bres, bres_bytes);
+            for (uint32_t fh = 0; fh < p.stem_fh; ++fh)
+                tma_load_3d(sBres + fh * BN * stem_rb, &p.tmB, bar_bres, 0, static_cast<int32_t>(fh), 0);
+        }
+        uint32_t stage = 0, phase = 0, pc = 0;
+        for (uint32_t ct = t_first; ct < t_end; ++ct) {
+            const uint32_t img = ct / p.OH, oh = ct % p.OH;
+            const uint32_t nnew = (ct == t_first || oh == 0) ? p.stem_np : 1u;
+            // even row of the window's first pair: 2 * oh - pad_h rounded down to even
+            const int32_t row0 = static_cast<int32_t>(oh) * 2 - p.pad_h - (p.pad_h & 1);
+            TIMED_WAIT(0, bar_empty + 8 * stage, phase ^ 1);
+            if (elect_one()) {
+                const uint32_t full = bar_full + 8 * stage;
+                mbar_arrive_expect_tx(full, nnew * 2 * p.stem_rowb);
+                for (uint32_t k = 0; k < nnew; ++k) {
+                    const uint32_t slot = (pc + k) % STEM_RING_PAIRS;
+                    const int32_t ih = row0 + 2 * static_cast<int32_t>(p.stem_np - nnew + k);
+                    tma_load_3d(sStage + slot * 2 * p.stem_rowb, &p.tmA, full, -2 * p.stem_pad_lo2, ih,
+                                static_cast<int32_t>(img));
+                }
+            }
+            __syncwarp();
+            pc += nnew;
+            if (++stage == STEM_RING_AHEAD) {
+                stage = 0;
+                phase ^= 1;
+            }
+        }
+    } else if (warp == 1 && ring) {
+        // ============================ MMA issuer, stem row ring ============================
+        // as the classic stem issuer, but filter row fh reads ring row 2 * slot + (r & 1) with
+        // r = fh + (pad_h & 1) the row's offset in the window and slot = (window's first pair + r / 2) % 16
+        if (elect_one()) {
+            auto mma_acc = [&](uint32_t taddr, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi) {
+                const uint64_t adesc = (static_cast<uint64_t>(a_hi) << 32) | a_lo;
+                const uint64_t bdesc = (static_cast<uint64_t>(b_hi) << 32) | b_lo;
+                if constexpr (KIND == KIND_S8)
+                    mma_i8_acc(taddr, adesc, bdesc, IDESC);
+                else
+                    mma_f16_acc(taddr, adesc, bdesc, IDESC);
+            };
+            const uint32_t ksteps = (p.stem_fw2 + 1) / 2;   // stem4: one K step (32 bytes) per two tap pairs
+            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, pc = 0;
+            const uint32_t a_hi = desc_hi(128, 0), b_hi = desc_hi(512, 4);
+            const uint32_t a0 = desc_lo(sStage, 16u), b0 = desc_lo(sBres, 16);
+            const uint32_t row16 = p.stem_rowb >> 4, brow = BN * stem_rb / 16u;
+            const uint32_t rodd = static_cast<uint32_t>(p.pad_h) & 1u;
+            TIMED_WAIT(6, bar_bres, 0);
+            for (uint32_t ct = t_first; ct < t_end; ++ct) {
+                const uint32_t oh = ct % p.OH;
+                pc += (ct == t_first || oh == 0) ? p.stem_np : 1u;
+                const uint32_t w0 = pc - p.stem_np;  // seq of the window's first pair
+                TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
+                TIMED_WAIT(2, bar_full + 8 * stage, phase);
+                tc_fence_after();
+                const uint32_t taddr = tmem_base + acc * BN;
+                uint32_t b_lo = b0;
+                for (uint32_t fh = 0; fh < p.stem_fh; ++fh) {
+                    const uint32_t r = fh + rodd;
+                    const uint32_t a_lo = a0 + ((((w0 + (r >> 1)) % STEM_RING_PAIRS) << 1) + (r & 1u)) * row16;
+                    if (fh == 0) {
+                        mma_issue<KIND>(taddr, a_lo, a_hi, b_lo, b_hi, IDESC, 0);  // overwrites the accumulator
+                        for (uint32_t t2 = 1; t2 < ksteps; ++t2)
+                            mma_acc(taddr, a_lo + t2 * 2, a_hi, b_lo + 2 * t2, b_hi);
+                    } else {
+                        for (uint32_t t2 = 0; t2 < ksteps; ++t2)
+                            mma_acc(taddr, a_lo + t2 * 2, a_hi, b_lo + 2 * t2, b_hi);
+                    }
+                    b_lo += brow;
+                }
+                mma_commit(bar_empty + 8 * stage);
+                mma_commit(bar_tfull + 8 * acc);
+                if (++stage == STEM_RING_AHEAD) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+                if (++acc == NACC) {
+                    acc = 0;
+                    acc_phase ^= 1;
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 0 && stem) {
         // ============================ TMA producer, stem mode ============================
         // the whole (packed) filter once, then per tile the FH input rows it needs, de-interleaved
         // into even / odd pixel planes: [parity][fh][pixel pair][16 bytes], no swizzle
@@ -420,7 +525,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 tma_load_3d(sBres + fh * BN * stem_rb, &p.tmB, bar_bres, 0, static_cast<int32_t>(fh), 0);
         }
         uint32_t stage = 0, phase = 0;
-        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+        for (uint32_t ct = t_first; ct < t_end; ct += t_step) {
             const uint32_t tile = ct;  // C == 1 in this mode
             const uint32_t seg = tile % p.nseg, row3 = tile / p.nseg;  // row3 = img * OH + oh
             const uint32_t img = row3 / p.OH, oh = row3 % p.OH;
@@ -467,7 +572,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             const uint32_t stage16 = stage_bytes >> 4, brow = BN * stem_rb / 16u;
             uint32_t soff = 0;
             TIMED_WAIT(6, bar_bres, 0);
-            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+            for (uint32_t ct = t_first; ct < t_end; ct += t_step) {
                 TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
                 TIMED_WAIT(2, bar_full + 8 * stage, phase);
                 tc_fence_after();
@@ -526,7 +631,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                             static_cast<int32_t>(kc * p.kb_elems), static_cast<int32_t>(tap), 0);
         }
         uint32_t stage = 0, phase = 0;
-        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+        for (uint32_t ct = t_first; ct < t_end; ct += t_step) {
             const uint32_t tile = ct;  // C == 1 in this mode
             const uint32_t img = tile / p.tiles_per_img, t = tile % p.tiles_per_img;
             const uint32_t r0 = (t * IGEMM_BLOCK_M) / p.PW;  // first (padded) input row of the slab
@@ -573,7 +678,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 }
             };
             TIMED_WAIT(6, bar_bres, 0);
-            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+            for (uint32_t ct = t_first; ct < t_end; ct += t_step) {
                 const uint32_t t = ct % p.tiles_per_img;  // C == 1 in this mode: ct is the tile
                 const uint32_t off0 = (t * IGEMM_BLOCK_M) % p.PW;
                 TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
@@ -621,7 +726,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     } else if (warp == 0) {
         // ============================ TMA producer (A, B) ============================
         uint32_t stage = 0, phase = 0;
-        for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+        for (uint32_t ct = t_first; ct < t_end; ct += t_step) {
             // a phantom tile (M tiles not a multiple of C) re-loads the last valid tile: every CTA of the
             // cluster must run the same k-loop because the filter slices are exchanged in lock step
             const uint32_t m_raw = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
@@ -733,7 +838,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             const uint32_t stage16 = stage_bytes >> 4;     // descriptor units are 16 bytes
             const uint32_t a0 = desc_lo(sStage, 16), b0 = desc_lo(sStage + a_bytes, 16);
             uint32_t soff = 0;
-            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num) {
+            for (uint32_t ct = t_first; ct < t_end; ct += t_step) {
                 TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * BN;
@@ -795,7 +900,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             const uint32_t ZD = nz / T::GROUPS;
             uint32_t zcnt = 0, zph = 0;  // per group: 4-bit slot counters / 1-bit phases, packed
             uint32_t first = 0;
-            for (uint32_t ct = cl_id; ct < total_ct; ct += cl_num, first = (first + NUM_CHUNKS) % T::GROUPS) {
+            for (uint32_t ct = t_first; ct < t_end; ct += t_step, first = (first + NUM_CHUNKS) % T::GROUPS) {
                 const uint32_t m_blk = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
                 if (m_blk >= p.m_tiles)
                     continue;  // phantom tile
@@ -867,8 +972,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         };
         // (m, n) tile indices advance incrementally: a division per tile is a ~25-instruction MUFU chain on
         // the critical path of short tiles (10 % of the low-K pointwise layers' samples)
-        uint32_t tq = cl_id / p.n_tiles, tr = cl_id % p.n_tiles;
-        const uint32_t dq = cl_num / p.n_tiles, dr = cl_num % p.n_tiles, ntl = p.n_tiles;
+        uint32_t tq = t_first / p.n_tiles, tr = t_first % p.n_tiles;
+        const uint32_t dq = t_step / p.n_tiles, dr = t_step % p.n_tiles, ntl = p.n_tiles;
         auto next_tile = [&]() {
             tq += dq, tr += dr;
             if (tr >= ntl)
@@ -879,8 +984,8 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         constexpr uint32_t BIAS_COLS = T::GROUPS > 1 ? T::EPI_N : BN;
         // group of the tile's chunk 0: (tile sequence number * NUM_CHUNKS) % GROUPS
         uint32_t first = 0;
-        for (uint32_t ct = cl_id; ct < total_ct;
-             ct += cl_num, next_tile(), next_acc(), first = (first + NUM_CHUNKS) % T::GROUPS) {
+        for (uint32_t ct = t_first; ct < t_end;
+             ct += t_step, next_tile(), next_acc(), first = (first + NUM_CHUNKS) % T::GROUPS) {
             const uint32_t m_blk = tq * C + crank, n_blk = tr;
             const uint32_t n0 = n_blk * BN;
             // the chunks of this tile the group owns: c_own, c_own + GROUPS, ... (with 4 groups: at most one)

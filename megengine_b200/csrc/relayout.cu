@@ -226,9 +226,9 @@ int relayout_generic(
             rc = transpose_words(es, src, dst, n, c, P, c_out, stream);
             break;
         case B200CB_RELAYOUT_NHWC_NCHW:   // (n, P, c) -> (n, c_out, P): padded or cropped channel planes
-            rc = transpose_words(es, src, dst, n, P, c, P, stream);
-            if (rc == B200CB_OK && c_out != c)
+            if (c_out != c)
                 return B200CB_UNSUPPORTED_SHAPE;  // (same channel count only: planes are written whole)
+            rc = transpose_words(es, src, dst, n, P, c, P, stream);
             break;
         case B200CB_RELAYOUT_NCHW_NCHW4:
             if (c_out % 4 || c_out < c)

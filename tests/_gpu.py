@@ -1,5 +1,6 @@
 """GPU-side helpers for the parity tests: run one b200cb_desc through the C-ABI on cuda:0."""
 import ctypes
+import os
 
 import numpy as np
 import torch
@@ -20,8 +21,25 @@ def to_dev(a):
     return torch.from_numpy(a).cuda()
 
 
-def plan_for(d, algo=None):
-    lib = C.load()
+TOOLS_LIB = os.path.join(os.path.dirname(C.LIB_PATH), "libb200cb_tools.so")
+_tools = None
+
+
+def tools_lib():
+    """the tools build of the same sources (make tools): identical kernels plus the experiment knobs read
+    from the environment (B200CB_PAIR, B200CB_DIRECT, ...), used to force kernel variants in parity runs."""
+    global _tools
+    if _tools is None:
+        lib = ctypes.CDLL(TOOLS_LIB)
+        for name, res, args in C.SYMBOLS:
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _tools = lib
+    return _tools
+
+
+def plan_for(d, algo=None, lib=None):
+    lib = lib or C.load()
     plan = C.Plan()
     if algo is None:
         rc = lib.b200cb_query(ctypes.byref(d), ctypes.byref(plan))
@@ -40,8 +58,8 @@ def available_algos(d):
     return out
 
 
-def launch(plan, tsrc, tflt, tbias, tz, tdst, tws=None, stream=None):
-    lib = C.load()
+def launch(plan, tsrc, tflt, tbias, tz, tdst, tws=None, stream=None, lib=None):
+    lib = lib or C.load()
     s = stream if stream is not None else torch.cuda.current_stream()
     p = lambda t: t.data_ptr() if t is not None else None
     rc = lib.b200cb_launch(ctypes.byref(plan), p(tsrc), p(tflt), p(tbias), p(tz), p(tdst), p(tws),
@@ -50,9 +68,9 @@ def launch(plan, tsrc, tflt, tbias, tz, tdst, tws=None, stream=None):
         raise C.B200CBError(rc, "b200cb_launch")
 
 
-def run_gpu(d, src, flt, bias, z, algo=None, force_im2col=False):
+def run_gpu(d, src, flt, bias, z, algo=None, force_im2col=False, lib=None):
     """Returns the dst tensor as a numpy array of raw storage (uint16 bits for fp16/bf16)."""
-    rc, plan = plan_for(d, algo)
+    rc, plan = plan_for(d, algo, lib)
     if rc != 0:
         raise C.B200CBError(rc, "b200cb_query")
     if force_im2col:
@@ -63,7 +81,7 @@ def run_gpu(d, src, flt, bias, z, algo=None, force_im2col=False):
     tdst = torch.full((n_dst,), 0x55, dtype=_TORCH_STORAGE[np.dtype(np_dt)], device="cuda") \
         if np_dt != np.float32 else torch.full((n_dst,), float("nan"), device="cuda")
     tws = torch.empty(int(plan.workspace_bytes), dtype=torch.uint8, device="cuda") if plan.workspace_bytes else None
-    launch(plan, tsrc, tflt, tbias, tz, tdst, tws)
+    launch(plan, tsrc, tflt, tbias, tz, tdst, tws, lib=lib)
     torch.cuda.synchronize()
     out = tdst.cpu().numpy()
     if np_dt == np.uint16:

@@ -4,6 +4,7 @@ error |x-y|/max(|x|,|y|,1) against the fp32 oracle (BASELINE.json north_star; me
 dnn/test/common/utils.h:189-193).  Case generators mirror dnn/test/cuda/conv_bias.cpp:83-124,
 234-265,650-714,1390-1439 and dnn/test/cuda/conv_bias_int8.cpp:798-835.
 """
+import os
 import zlib
 
 import numpy as np
@@ -17,13 +18,13 @@ from .gpu_diag import stage_cases
 pytestmark = pytest.mark.gpu
 
 
-def _check(d, opt=None, seed=1234):
+def _check(d, opt=None, seed=1234, lib=None):
     from . import _gpu as G
     opt = opt or {}
     src, flt, bias, z = K.gen_inputs(d, seed, int_range=opt.get("int_range", 8), bias_range=opt.get("bias_range", 50))
     want = O.oracle_convbias(d, src, flt, bias, z)
     want_f32 = K.fp32_reference(d, src, flt, bias, z) if d.dst_dtype in (C.DT_BF16, C.DT_F16) else None
-    got, plan = G.run_gpu(d, src, flt, bias, z, algo=opt.get("algo"), force_im2col=opt.get("im2col", False))
+    got, plan = G.run_gpu(d, src, flt, bias, z, algo=opt.get("algo"), force_im2col=opt.get("im2col", False), lib=lib)
     ok, info = G.compare(d, got, want, want_f32)
     assert ok, (K.desc_str(d), info)
     return plan, info
@@ -320,3 +321,162 @@ def test_gpu_matches_golden_reference_outputs(meta, want):
         want_f32 = K.fp32_reference(d, src, flt, bias, z) if d.dst_dtype != C.DT_F32 else None
         ok, info = G.compare(d, got, want, want_f32)
         assert ok, info
+
+
+# ------------------------------------------------------------------ forced kernel variants (tools build)
+_VARIANT_CASES = (stage_cases("gemm_tiled") + stage_cases("conv") + stage_cases("int8"))
+
+
+@pytest.fixture
+def knob(monkeypatch):
+    def set_(name, value):
+        monkeypatch.setenv(name, str(value))
+    return set_
+
+
+@pytest.mark.parametrize("name,d,opt", _VARIANT_CASES, ids=_ids(_VARIANT_CASES))
+def test_cta_pair_forced_on_every_case(name, d, opt, knob):
+    """cta_group::2 tiles forced wherever the kernel can pair (>= 4 M tiles), whatever the heuristic says:
+    same parity bar.  Runs the tools build of the same sources (B200CB_PAIR is its knob)."""
+    from . import _gpu as G
+    if not os.path.exists(G.TOOLS_LIB):
+        pytest.skip("tools build (make -C megengine_b200/csrc tools) not present")
+    knob("B200CB_PAIR", 1)
+    _check(d, opt, lib=G.tools_lib())
+
+
+@pytest.mark.parametrize("name,d,opt", _VARIANT_CASES, ids=_ids(_VARIANT_CASES))
+def test_direct_store_epilogue_forced_on_every_case(name, d, opt, knob):
+    """the st.global epilogue (instead of the TMA store) on every case: same parity bar."""
+    from . import _gpu as G
+    if not os.path.exists(G.TOOLS_LIB):
+        pytest.skip("tools build not present")
+    knob("B200CB_DIRECT", 1)
+    _check(d, opt, lib=G.tools_lib())
+
+
+@pytest.mark.parametrize("kind", ["bf16", "f16", "qs8"])
+@pytest.mark.parametrize("layer", [l for l in K.RESNET50_LAYERS if l[0] in ("l2.bN.c2", "l3.c3", "l4.bN.c1")],
+                         ids=["l2.bN.c2", "l3.c3", "l4.bN.c1"])
+def test_pair_tiles_at_n8_against_full_oracle(layer, kind, knob):
+    """N = 8 is the smallest batch at which the ResNet-50 layers have enough M tiles to pair: forced pairs
+    against the full oracle (phantom tiles: 8 * 7 * 7 = 392 pixels = 3.06 M tiles on 2 CTAs)."""
+    from . import _gpu as G
+    if not os.path.exists(G.TOOLS_LIB):
+        pytest.skip("tools build not present")
+    knob("B200CB_PAIR", 1)
+    d = K.resnet50_desc(layer, kind, 8, ic_pad=16 if kind == "qs8" else 8)
+    plan, _info = _check(d, {"int_range": 127, "bias_range": 5000} if kind == "qs8" else None, lib=G.tools_lib())
+    assert plan.reserved[7] == 1
+
+
+@pytest.mark.parametrize("kind", ["bf16", "f16", "qs8"])
+def test_full_size_residual_layer_repeated_and_sampled(kind):
+    """ResNet-50 l1.c3 at N = 256 (802816 x 256 outputs, residual z, one k-block per tile): the layer whose
+    z ring hung / faulted in round 2 when a ring slot was shared by two epilogue groups.  40 back-to-back
+    launches must complete, agree with each other bit for bit, and match the oracle on 4096 samples."""
+    import torch
+    from . import _gpu as G
+    layer = [l for l in K.RESNET50_LAYERS if l[0] == "l1.c3"][0]
+    d = K.resnet50_desc(layer, kind, 256)
+    src, flt, bias, z = K.gen_inputs(d, 23, int_range=127, bias_range=5000)
+    rc, plan = G.plan_for(d)
+    assert rc == 0
+    tsrc, tflt, tbias, tz = G.to_dev(src), G.to_dev(flt), G.to_dev(bias), G.to_dev(z)
+    outs = [torch.zeros(O.dst_elems(d), dtype=torch.int8 if kind == "qs8" else torch.int16, device="cuda") for _ in range(2)]
+    for i in range(40):
+        G.launch(plan, tsrc, tflt, tbias, tz, outs[i & 1])
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1])
+    got = outs[0].cpu().numpy()
+    idx = np.random.default_rng(5).integers(0, got.size, 4096).astype(np.uint64)
+    if kind == "qs8":
+        want = O.oracle_convbias_sample(d, src, flt, bias, z, idx)
+        assert np.array_equal(got[idx.astype(np.int64)], want)
+    else:
+        d32 = d.copy()
+        d32.src_dtype = d32.filter_dtype = d32.dst_dtype = d32.bias_dtype = d32.z_dtype = C.DT_F32
+        d32.compute_mode = C.COMPUTE_DEFAULT
+        up = lambda a: O.to_f32(a, d.src_dtype)
+        want = O.oracle_convbias_sample(d32, up(src), up(flt), up(bias), up(z), idx)
+        err = O.megdnn_rel_err(O.to_f32(got.view(np.uint16), d.dst_dtype)[idx.astype(np.int64)], want)
+        assert err.max() <= (1e-2 if kind == "bf16" else 2e-3), err.max()
+
+
+# ------------------------------------------------------------------ host-buffer entry point
+@pytest.mark.parametrize("kind,has_z", [("bf16", True), ("qs8", True), ("f16", False)])
+def test_exec_host_matches_device_path(kind, has_z):
+    """b200cb_exec_host (include/b200cb.h): host src / filter / bias / z in, host dst out, device scratch
+    owned by the caller -- the same bytes as b200cb_launch on device tensors."""
+    import ctypes
+    import torch
+    from . import _gpu as G
+    lib = C.load()
+    d = K.make_desc(kind, 3, 64, 14, 14, 128, 3, pad=1, nonline=C.NL_RELU, has_z=has_z, scales=(0.37, 0.71, None, 1.9, 23.0))
+    src, flt, bias, z = K.gen_inputs(d, 3, int_range=127, bias_range=5000)
+    want, plan = G.run_gpu(d, src, flt, bias, z)
+    need = lib.b200cb_host_scratch_bytes(ctypes.byref(plan))
+    assert need >= src.nbytes + flt.nbytes + want.nbytes
+    scratch = torch.empty(need, dtype=torch.uint8, device="cuda")
+    got = np.zeros_like(want)
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p) if a is not None else None
+    s = torch.cuda.current_stream().cuda_stream
+    assert lib.b200cb_exec_host(ctypes.byref(plan), p(src), p(flt), p(bias), p(z), p(got), scratch.data_ptr(), need, s) == 0
+    assert np.array_equal(got, want)
+    # too little scratch / missing buffers are reported, not executed
+    assert lib.b200cb_exec_host(ctypes.byref(plan), p(src), p(flt), p(bias), p(z), p(got), scratch.data_ptr(), need - 1, s) == -3
+    assert lib.b200cb_exec_host(ctypes.byref(plan), None, p(flt), p(bias), p(z), p(got), scratch.data_ptr(), need, s) == -5
+
+
+# ------------------------------------------------------------------ first-class relayout operators (8f rank 1)
+def _np_relayout(mode, x, n, c, h, w, c_out):
+    """numpy statement of megdnn RelayoutFormat for the modes of include/b200cb.h (zero channel padding)."""
+    def padc(a, axis, to):
+        pad = [(0, 0)] * a.ndim
+        pad[axis] = (0, to - a.shape[axis])
+        return np.pad(a, pad)
+    if mode == C.RELAYOUT_NCHW_NHWC:
+        return padc(x.reshape(n, c, h, w).transpose(0, 2, 3, 1), 3, c_out)
+    if mode == C.RELAYOUT_NHWC_NCHW:
+        return x.reshape(n, h, w, c).transpose(0, 3, 1, 2)
+    if mode == C.RELAYOUT_NCHW_NCHW4:
+        return padc(x.reshape(n, c, h, w), 1, c_out).reshape(n, c_out // 4, 4, h, w).transpose(0, 1, 3, 4, 2)
+    if mode == C.RELAYOUT_NCHW4_NCHW:
+        return x.reshape(n, c // 4, h, w, 4).transpose(0, 1, 4, 2, 3).reshape(n, c, h, w)[:, :c_out]
+    if mode == C.RELAYOUT_NCHW4_NHWC:
+        return padc(x.reshape(n, c // 4, h, w, 4).transpose(0, 2, 3, 1, 4).reshape(n, h, w, c), 3, c_out)
+    if mode == C.RELAYOUT_NHWC_NCHW4:
+        return padc(x.reshape(n, h, w, c), 3, c_out).reshape(n, h, w, c_out // 4, 4).transpose(0, 3, 1, 2, 4)
+    return padc(x.reshape(n, h, w, c), 3, c_out)
+
+
+RELAYOUT_CASES = [
+    # mode, elem bytes, n, c, h, w, c_out
+    (C.RELAYOUT_NCHW_NHWC, 2, 3, 20, 9, 11, 24), (C.RELAYOUT_NCHW_NHWC, 4, 2, 3, 17, 5, 3), (C.RELAYOUT_NCHW_NHWC, 1, 2, 64, 7, 7, 64),
+    (C.RELAYOUT_NHWC_NCHW, 2, 3, 40, 9, 11, 40), (C.RELAYOUT_NHWC_NCHW, 4, 2, 7, 5, 33, 7), (C.RELAYOUT_NHWC_NCHW, 1, 2, 96, 14, 14, 96),
+    (C.RELAYOUT_NCHW_NCHW4, 1, 2, 3, 30, 30, 4), (C.RELAYOUT_NCHW_NCHW4, 1, 3, 22, 9, 11, 24), (C.RELAYOUT_NCHW_NCHW4, 2, 2, 8, 6, 7, 8),
+    (C.RELAYOUT_NCHW4_NCHW, 1, 2, 24, 9, 11, 22), (C.RELAYOUT_NCHW4_NCHW, 4, 2, 8, 5, 5, 8),
+    (C.RELAYOUT_NCHW4_NHWC, 1, 3, 32, 9, 11, 32), (C.RELAYOUT_NCHW4_NHWC, 1, 2, 4, 30, 30, 16), (C.RELAYOUT_NCHW4_NHWC, 2, 2, 36, 7, 7, 40),
+    (C.RELAYOUT_NHWC_NCHW4, 1, 2, 3, 30, 30, 4), (C.RELAYOUT_NHWC_NCHW4, 1, 3, 64, 9, 11, 64), (C.RELAYOUT_NHWC_NCHW4, 2, 2, 10, 5, 6, 12),
+    (C.RELAYOUT_NHWC_PAD_C, 2, 2, 3, 224, 224, 4), (C.RELAYOUT_NHWC_PAD_C, 1, 3, 3, 31, 17, 8), (C.RELAYOUT_NHWC_PAD_C, 4, 1, 5, 9, 9, 8),
+    (C.RELAYOUT_NHWC_PAD_C, 2, 1, 24, 13, 3, 32),
+]
+
+
+@pytest.mark.parametrize("case", RELAYOUT_CASES, ids=["m%d_e%d_n%d_c%d_%dx%d_co%d" % c for c in RELAYOUT_CASES])
+def test_relayout_modes_match_numpy(case):
+    """b200cb_relayout: NCHW <-> NHWC <-> NCHW4 and channel padding, byte-exact against the numpy statement
+    of megdnn's RelayoutFormat (dnn/src/naive/relayout_format/opr_impl.cpp semantics: pure permutation with
+    zero-filled channel padding)."""
+    import torch
+    mode, es, n, c, h, w, c_out = case
+    lib = C.load()
+    npdt = {1: np.int8, 2: np.int16, 4: np.int32}[es]
+    x = np.random.default_rng(mode * 7 + es).integers(-100, 100, n * c * h * w).astype(npdt)
+    want = np.ascontiguousarray(_np_relayout(mode, x, n, c, h, w, c_out))
+    tx = torch.from_numpy(x).cuda()
+    ty = torch.full((want.size,), 0x55, dtype=tx.dtype, device="cuda")
+    rc = lib.b200cb_relayout(mode, es, n, c, h, w, c_out, tx.data_ptr(), ty.data_ptr(), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0, C.strerror(rc)
+    torch.cuda.synchronize()
+    assert np.array_equal(ty.cpu().numpy(), want.reshape(-1))
