@@ -474,45 +474,52 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     mma_f16_acc(taddr, adesc, bdesc, IDESC);
             };
             const uint32_t ksteps = (p.stem_fw2 + 1) / 2;   // stem4: one K step (32 bytes) per two tap pairs
-            uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, pc = 0;
             const uint32_t a_hi = desc_hi(128, 0), b_hi = desc_hi(512, 4);
             const uint32_t a0 = desc_lo(sStage, 16u), b0 = desc_lo(sBres, 16);
             const uint32_t row16 = p.stem_rowb >> 4, brow = BN * stem_rb / 16u;
             const uint32_t rodd = static_cast<uint32_t>(p.pad_h) & 1u;
-            TIMED_WAIT(6, bar_bres, 0);
-            for (uint32_t ct = t_first; ct < t_end; ++ct) {
-                const uint32_t oh = ct % p.OH;
-                pc += (ct == t_first || oh == 0) ? p.stem_np : 1u;
-                const uint32_t w0 = pc - p.stem_np;  // seq of the window's first pair
-                TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
-                TIMED_WAIT(2, bar_full + 8 * stage, phase);
-                tc_fence_after();
-                const uint32_t taddr = tmem_base + acc * BN;
-                uint32_t b_lo = b0;
-                for (uint32_t fh = 0; fh < p.stem_fh; ++fh) {
-                    const uint32_t r = fh + rodd;
-                    const uint32_t a_lo = a0 + ((((w0 + (r >> 1)) % STEM_RING_PAIRS) << 1) + (r & 1u)) * row16;
-                    if (fh == 0) {
-                        mma_issue<KIND>(taddr, a_lo, a_hi, b_lo, b_hi, IDESC, 0);  // overwrites the accumulator
-                        for (uint32_t t2 = 1; t2 < ksteps; ++t2)
-                            mma_acc(taddr, a_lo + t2 * 2, a_hi, b_lo + 2 * t2, b_hi);
-                    } else {
-                        for (uint32_t t2 = 0; t2 < ksteps; ++t2)
+            constexpr uint32_t RING_ROWS = 2 * STEM_RING_PAIRS;  // ring row of window row r: (2 * w0 + r) % 32
+            auto run = [&](auto KS_) {
+                constexpr uint32_t KS = decltype(KS_)::value;
+                uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0, pc = 0;
+                TIMED_WAIT(6, bar_bres, 0);
+                for (uint32_t ct = t_first; ct < t_end; ++ct) {
+                    const uint32_t oh = ct % p.OH;
+                    pc += (ct == t_first || oh == 0) ? p.stem_np : 1u;
+                    uint32_t rr = (2 * (pc - p.stem_np) + rodd) % RING_ROWS;  // ring row of filter row 0
+                    TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
+                    TIMED_WAIT(2, bar_full + 8 * stage, phase);
+                    tc_fence_after();
+                    const uint32_t taddr = tmem_base + acc * BN;
+                    uint32_t a_lo = a0 + rr * row16, b_lo = b0;
+                    mma_issue<KIND>(taddr, a_lo, a_hi, b_lo, b_hi, IDESC, 0);  // overwrites the accumulator
+#pragma unroll
+                    for (uint32_t t2 = 1; t2 < KS; ++t2)
+                        mma_acc(taddr, a_lo + t2 * 2, a_hi, b_lo + 2 * t2, b_hi);
+                    for (uint32_t fh = 1; fh < p.stem_fh; ++fh) {
+                        rr = (rr + 1) % RING_ROWS;
+                        a_lo = a0 + rr * row16;
+                        b_lo += brow;
+#pragma unroll
+                        for (uint32_t t2 = 0; t2 < KS; ++t2)
                             mma_acc(taddr, a_lo + t2 * 2, a_hi, b_lo + 2 * t2, b_hi);
                     }
-                    b_lo += brow;
+                    mma_commit(bar_empty + 8 * stage);
+                    mma_commit(bar_tfull + 8 * acc);
+                    if (++stage == STEM_RING_AHEAD) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                    if (++acc == NACC) {
+                        acc = 0;
+                        acc_phase ^= 1;
+                    }
                 }
-                mma_commit(bar_empty + 8 * stage);
-                mma_commit(bar_tfull + 8 * acc);
-                if (++stage == STEM_RING_AHEAD) {
-                    stage = 0;
-                    phase ^= 1;
-                }
-                if (++acc == NACC) {
-                    acc = 0;
-                    acc_phase ^= 1;
-                }
-            }
+            };
+            if (ksteps == 1)
+                run(std::integral_constant<uint32_t, 1>{});
+            else
+                run(std::integral_constant<uint32_t, 2>{});
         }
         __syncwarp();
     } else if (warp == 0 && stem) {
@@ -1643,6 +1650,9 @@ struct Geometry {
     bool folded;
     bool stem;            // a_mode 2: resident filter + one input-row slab per tile
     bool stem4;           // ... with a pixel pair per 16-byte unit (IC * es == 8)
+    bool ring;            // ... staged as whole rows into the row ring (IgemmParams::stem_ring)
+    uint32_t ring_nj;     // pixel pairs per staged row
+    uint32_t ring_np;     // row pairs per output row
 };
 constexpr uint32_t STEM_NJ = STEM_NJ_K;  // 128 output pixels + up to 4 tap pairs - 1, rounded up to 8
 
@@ -1672,6 +1682,8 @@ Geometry make_geometry(const b200cb_desc& d, uint32_t in_es, bool allow_fold = t
     g.folded = false;
     g.stem = false;
     g.stem4 = false;
+    g.ring = false;
+    g.ring_nj = g.ring_np = 0;
     if (allow_fold && d.stride_w == 2 && d.dilate_w == 1 && d.iw % 2 == 0 && d.ic * in_es <= 16 &&
         d.mode == B200CB_MODE_CROSS_CORRELATION && d.src_batch_stride == 0) {
         // window of output ow covers pixels [2*ow - pad, 2*ow - pad + FW); extend it to an even start
@@ -1694,6 +1706,22 @@ Geometry make_geometry(const b200cb_desc& d, uint32_t in_es, bool allow_fold = t
             g.stem = true;
             g.stem4 = d.ic * in_es == 8;
             g.fw_packed = 4;
+            // row ring: one 128-pixel segment covers the output row, a staged row (OW + FW2 - 1 pixel pairs
+            // of 16 bytes) fits one TMA box of <= 256 8-byte elements, <= 4 row pairs per output row
+            // (rows of 8 pixel pairs = 128 bytes: a TMA box must land on a 128-byte aligned address)
+            const uint32_t nj = (d.ow + fw2 - 1 + 7) / 8 * 8, np = (d.fh + (d.pad_h & 1) + 1) / 2;
+            // (16-bit kinds: conv1 0.214 -> 0.159 ms; the int8 stem is epilogue bound and measured 15 % slower
+            // on contiguous row ranges, profiles/r02)
+            bool ring_ok = g.stem4 && in_es == 2 && d.ow <= IGEMM_BLOCK_M && nj <= 128 && np <= 4 && d.has_z == 0;
+#ifdef B200CB_TOOLS
+            if (const char* e = getenv("B200CB_RING"))
+                ring_ok = ring_ok && atoi(e) != 0;
+#endif
+            if (ring_ok) {
+                g.ring = true;
+                g.ring_nj = nj;
+                g.ring_np = np;
+            }
         }
     }
     return g;
@@ -1966,6 +1994,9 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
                                     : (IGEMM_BLOCK_M + (pair ? block_n / 2 : block_n)) * kb_bytes;
     const uint32_t fixed = fixed0 + (stem ? d.fh * block_n * stem_rb : rows ? rg.bres : 0);
     uint32_t stages = (MAX_DYN_SMEM - fixed) / stage_b;
+    // stem row ring: 16 row pairs + slack for the descriptor rows past OW (read, never stored)
+    const bool ring = stem && g.ring;
+    const uint32_t ring_bytes = ring ? STEM_RING_PAIRS * 2 * g.ring_nj * 16 + 4096 : 0;
     if (rows && stages > 3)
         stages = 3;
     if (stages > IGEMM_MAX_STAGES)
@@ -1975,6 +2006,12 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     // z ring depth: layers with a short k-loop are bound by the z / dst streams; give them z chunks
     // (prefetched a tile or more ahead) instead of a third A/B stage
     uint32_t nz = NZ_MIN, smem_total = fixed + stages * stage_b;
+    if (ring) {
+        if (fixed + ring_bytes > MAX_DYN_SMEM)
+            return B200CB_UNSUPPORTED_SHAPE;
+        stages = STEM_RING_AHEAD;
+        smem_total = fixed + ring_bytes;
+    }
     if (d.has_z && !nchw4 && !stem && !rows) {
         const uint32_t zbuf = 128 * ((out32 || in_es == 2) ? 128 : 64);
         const uint32_t num_kb = d.fh * d.fw * ((g.ic * in_es + kb_bytes - 1) / kb_bytes);
@@ -2029,7 +2066,7 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         plan->reserved[2] = (atoi(e) != 0 && !nchw4 && !rows) ? 2u : 0u;
 #endif
     plan->reserved[3] = 0;  // 1: `filter` passed to launch is already packed (weight preprocess)
-    plan->reserved[4] = g.folded ? 1 : 0;
+    plan->reserved[4] = (g.folded ? 1u : 0u) | (ring ? 2u : 0u);  // bit 0: W-folded (packed filter), bit 1: row ring
     plan->reserved[5] = kb_bytes | (nz << 16);
     plan->reserved[6] = cluster;
     plan->reserved[7] = pair;
@@ -2174,6 +2211,15 @@ int igemm_launch(
         cr = encode_tiled(
                 &p.tmA, in_dt, 4, src, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
+    } else if (stem && (plan.reserved[4] & 2)) {
+        // row ring: rows as contiguous runs of 8-byte elements (a pixel of IC * es == 8 bytes), boxes of one
+        // row pair; left / right / top / bottom padding by out-of-bounds zero fill
+        uint64_t dims[3] = {(uint64_t)d.iw * d.ic * in_es / 8, d.ih, d.n};
+        uint64_t strides[2] = {(uint64_t)d.iw * d.ic * in_es, src_bstride * in_es};
+        uint32_t box[3] = {2 * g.ring_nj, 2, 1};
+        cr = encode_tiled(
+                &p.tmA, CU_TENSOR_MAP_DATA_TYPE_UINT64, 3, src, dims, strides, box, nullptr,
+                CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B);
     } else if (stem) {
         // even / odd input pixels as two (C, W/2, H, N) tensors whose W stride is one pixel pair
         // (stem4: one tensor whose innermost 16 bytes are the pixel pair itself)
@@ -2286,6 +2332,12 @@ int igemm_launch(
     p.stem_fw2 = g.fw;
     p.stem_pad_lo2 = g.pad_w_lo;
     p.stem4 = (stem && g.stem4) ? 1 : 0;
+    if (stem && (plan.reserved[4] & 2)) {
+        p.stem_ring = 1;
+        p.stem_nj = g.ring_nj;
+        p.stem_rowb = g.ring_nj * 16;
+        p.stem_np = g.ring_np;
+    }
     if (stem)
         p.m_tiles = d.n * d.oh * p.nseg;
     if (rows) {

@@ -480,3 +480,28 @@ def test_relayout_modes_match_numpy(case):
     assert rc == 0, C.strerror(rc)
     torch.cuda.synchronize()
     assert np.array_equal(ty.cpu().numpy(), want.reshape(-1))
+
+
+# ------------------------------------------------------------------ stem row ring (8-byte pixels)
+STEM_RING_CASES = [
+    # name, kind, n, ic, h, w, oc, f, pad          (stride 2; bf16 / fp16 IC = 4, int8 IC = 8: 8-byte pixels)
+    ("bf16_7x7_224_n4", "bf16", 4, 4, 224, 224, 64, 7, 3),    # 448 output rows: 3 per CTA, image changes mid-range
+    ("qs8_7x7_224_n2", "qs8", 2, 8, 224, 224, 64, 7, 3),
+    ("f16_7x7_odd_rows", "f16", 3, 4, 74, 62, 64, 7, 3),
+    ("bf16_3x3_p1", "bf16", 5, 4, 66, 40, 32, 3, 1),          # 2 row pairs per window
+    ("qs8_5x5_p2", "qs8", 3, 8, 50, 100, 48, 5, 2),           # even padding: 3 row pairs, last row unused
+    ("bf16_7x7_one_row_per_cta", "bf16", 1, 4, 30, 30, 64, 7, 3),
+    ("bf16_7x7_ow125", "bf16", 2, 4, 20, 250, 64, 7, 3),      # widest row that still fits one box
+    ("bf16_7x7_ow129_classic", "bf16", 2, 4, 20, 258, 64, 7, 3),  # one pixel too wide: classic stem path
+]
+
+
+@pytest.mark.parametrize("case", STEM_RING_CASES, ids=[c[0] for c in STEM_RING_CASES])
+def test_stem_row_ring(case):
+    """network stems with 8-byte pixels: whole input rows staged into the row ring, contiguous output-row
+    ranges per CTA (first / last rows of an image, image changes inside a range, padding rows)."""
+    _name, kind, n, ic, h, w, oc, f, pd = case
+    d = K.make_desc(kind, n, ic, h, w, oc, f, stride=2, pad=pd, nonline=C.NL_RELU, scales=(0.37, 0.71, None, 1.9, 23.0))
+    plan, _info = _check(d, {"int_range": 127, "bias_range": 5000} if kind == "qs8" else None, seed=61 + h)
+    assert plan.a_mode == 2
+    assert ((plan.reserved[4] >> 1) & 1) == (0 if ("classic" in _name or kind == "qs8") else 1)
