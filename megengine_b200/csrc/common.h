@@ -69,6 +69,9 @@ int relayout_generic(
         uint32_t mode, uint32_t es, uint32_t n, uint32_t c, uint32_t h, uint32_t w, uint32_t c_out, const void* src,
         void* dst, cudaStream_t stream);
 
+// fp32 [P][C] -> bf16 [P][3*Cp] operand split of the Float32 ConvBias path (relayout.cu)
+int relayout_split3(const void* in, void* out, uint64_t P, uint32_t C, uint32_t Cp, int filter_side, cudaStream_t stream);
+
 int device_sm_count();
 
 inline uint32_t dtype_size(uint32_t dt) {

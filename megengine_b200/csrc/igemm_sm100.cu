@@ -84,6 +84,10 @@ struct IgemmParams {
     // a z chunk costs a whole queue drain (thousands of clocks when the layer is HBM bound); plain
     // stores free the staging memory as soon as the warp has read it back.
     uint32_t direct_store;
+    // OUT32 kernels: 0 = QuantizedS32 dst (int32 accumulator + bias), 1 = Float32 dst: float(acc) * acc_scale
+    // (QuantizedS8 inputs) or the fp32 accumulator (bf16 inputs) + fp32 bias [+ fp32 z], activation
+    uint32_t out_f32;
+    float acc_scale;
     const void* z;
     RequantParams rq;
     long long* dbg;   // -DB200CB_DEBUG_TIMING builds only: 148 x 3 roles x 17 counters
@@ -1026,7 +1030,9 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 for (uint32_t i = quad * 32 + lane; i < BIAS_COLS; i += 128) {
                     uint32_t v = 0;
                     if (p.has_bias && b0 + i < p.OC) {
-                        if constexpr (KIND == KIND_S8) {
+                        if (OUT32 && p.out_f32) {
+                            v = reinterpret_cast<const uint32_t*>(p.bias)[b0 + i];  // Float32 bias
+                        } else if constexpr (KIND == KIND_S8) {
                             v = static_cast<uint32_t>(reinterpret_cast<const int32_t*>(p.bias)[b0 + i]);
                         } else if constexpr (KIND == KIND_BF16) {
                             v = static_cast<uint32_t>(
@@ -1111,7 +1117,36 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     const uint32_t* bcol = sbias + (T::GROUPS > 1 ? 0u : c * T::EPI_N) + h * 32;
                     constexpr uint32_t COLS_PER_16B = 16 / T::OUT_ES;
                     constexpr uint32_t PIECES = 32 / COLS_PER_16B;  // 16-byte pieces per 32 columns
-                    if constexpr (KIND == KIND_S8 && OUT32) {
+                    if constexpr (OUT32) {
+                      if (p.out_f32) {
+                        // Float32 destination: x = acc (int8: dequantised with s_src * s_flt) + bias [+ z],
+                        // activation, stored as fp32 (the fp32 ConvBias path and QuantizedS8 -> Float32)
+#pragma unroll
+                        for (uint32_t j = 0; j < PIECES; ++j) {
+                            const uint32_t off = (h * PIECES + j) ^ (lane & 7);
+                            const uint4 bv = *reinterpret_cast<const uint4*>(bcol + j * 4);
+                            const uint32_t bb[4] = {bv.x, bv.y, bv.z, bv.w};
+                            uint32_t zz[4] = {0, 0, 0, 0};
+                            if (p.has_z) {
+                                const uint4 zv = *reinterpret_cast<const uint4*>(zrow + off * 16);
+                                zz[0] = zv.x, zz[1] = zv.y, zz[2] = zv.z, zz[3] = zv.w;
+                            }
+                            uint32_t ov[4];
+#pragma unroll
+                            for (uint32_t k = 0; k < 4; ++k) {
+                                float x;
+                                if constexpr (KIND == KIND_S8)
+                                    x = __fmul_rn(__int2float_rn(static_cast<int32_t>(r[j * 4 + k])), p.acc_scale);
+                                else
+                                    x = __uint_as_float(r[j * 4 + k]);
+                                x = __fadd_rn(x, __uint_as_float(bb[k]));
+                                if (p.has_z)
+                                    x = __fadd_rn(x, __uint_as_float(zz[k]));
+                                ov[k] = __float_as_uint(act_f(x, p.nonline));
+                            }
+                            *reinterpret_cast<uint4*>(drow + off * 16) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                        }
+                      } else {
                         // QuantizedS32 destination: dst = acc + bias (IDENTITY, no z)
 #pragma unroll
                         for (uint32_t j = 0; j < PIECES; ++j) {
@@ -1124,6 +1159,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                             const uint32_t off = (h * PIECES + j) ^ (lane & 7);
                             *reinterpret_cast<uint4*>(drow + off * 16) = ov;
                         }
+                      }
                     } else if constexpr (KIND == KIND_S8) {
                       if (p.nchw4) {
                         // this thread's output pixel (stem tiles are 128-pixel segments of one output row)
@@ -1853,6 +1889,42 @@ int igemm_selftest(int which, cudaStream_t stream, uint64_t* mismatches) {
 }
 
 // --------------------------------------------------------------------------- host side
+// The dense convolution one kernel launch computes for descriptor `d` (already NHWC):
+//  * GROUP (non-depthwise): one launch per group over channel-sliced views of src / dst / z -- what the
+//    reference's AlgoGroupConvGeneral does with sub-operators (dnn/src/cuda/conv_bias/group_conv.cpp:1-190):
+//    ic / oc become the per-group counts, *ld_src / *ld_dst keep the parent tensors' channel counts (the
+//    pixel pitch of the views);
+//  * BiasMode::BIAS (dst-shaped bias, dnn/src/common/conv_bias.cpp:38-49): bias + [no z] is the same
+//    arithmetic as no bias + z = bias (both are added in fp32 before the activation), so the full bias
+//    travels through the z ring (*bias_as_z).
+// Returns B200CB_OK or the reason the cell is not supported.
+int igemm_normalise(const b200cb_desc& d, b200cb_desc* out, uint32_t* ld_src, uint32_t* ld_dst, bool* bias_as_z) {
+    *out = d;
+    *ld_src = d.ic, *ld_dst = d.oc;
+    *bias_as_z = false;
+    if (d.group == 0 || d.ic % d.group || d.oc % d.group)
+        return B200CB_UNSUPPORTED_SHAPE;
+    if (d.group > 1) {
+        if (d.sparse != B200CB_SPARSE_GROUP || d.format != B200CB_FORMAT_NHWC)
+            return B200CB_UNSUPPORTED_PARAM;
+        if (d.src_batch_stride || d.dst_batch_stride || d.z_batch_stride)
+            return B200CB_UNSUPPORTED_SHAPE;  // grouped views of batch-strided tensors: not implemented
+        out->ic = d.ic / d.group, out->oc = d.oc / d.group;
+        out->group = 1, out->sparse = B200CB_SPARSE_DENSE;
+    } else if (d.sparse != B200CB_SPARSE_DENSE) {
+        return B200CB_UNSUPPORTED_PARAM;
+    }
+    if (d.bias_mode == B200CB_BIAS_FULL) {
+        const bool fl = d.src_dtype == B200CB_DT_BF16 || d.src_dtype == B200CB_DT_F16;
+        if (!fl || d.has_z || d.bias_dtype != d.dst_dtype || d.format != B200CB_FORMAT_NHWC)
+            return B200CB_UNSUPPORTED_PARAM;  // (with z as well: two dst-shaped streams, not implemented)
+        out->bias_mode = B200CB_BIAS_NONE, out->bias_dtype = B200CB_DT_NONE;
+        out->has_z = 1, out->z_dtype = d.bias_dtype, out->z_batch_stride = 0;
+        *bias_as_z = true;
+    }
+    return B200CB_OK;
+}
+
 int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     const bool nchw4 = d0.format == B200CB_FORMAT_NCHW4;
     if (d0.format != B200CB_FORMAT_NHWC && !nchw4)
@@ -1867,9 +1939,15 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         if (d0.src_batch_stride != 0 && (d0.src_batch_stride < simg || d0.src_batch_stride % 4 != 0))
             return B200CB_UNSUPPORTED_ALIGNMENT;
     }
-    const b200cb_desc d = nchw4 ? nchw4_equivalent(d0) : d0;
-    if (d.sparse != B200CB_SPARSE_DENSE || d.group != 1)
-        return B200CB_UNSUPPORTED_PARAM;
+    b200cb_desc d;
+    uint32_t ld_src, ld_dst;
+    bool bias_as_z;
+    {
+        const int rc = igemm_normalise(nchw4 ? nchw4_equivalent(d0) : d0, &d, &ld_src, &ld_dst, &bias_as_z);
+        if (rc != B200CB_OK)
+            return rc;
+    }
+    const bool grouped = d0.group > 1;
     int kind;
     if (d.src_dtype == B200CB_DT_BF16)
         kind = KIND_BF16;
@@ -1881,8 +1959,17 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         return B200CB_UNSUPPORTED_DTYPE;
     if (d.filter_dtype != d.src_dtype)
         return B200CB_UNSUPPORTED_DTYPE;
-    bool out32 = false;
-    if (kind == KIND_S8) {
+    bool out32 = false, out_f32 = false;
+    if (d.dst_dtype == B200CB_DT_F32 && (kind == KIND_S8 || kind == KIND_BF16)) {
+        // Float32 destination: QuantizedS8 -> Float32 (naive DISPATCH(QuantizedS8, Float32),
+        // dnn/src/naive/conv_bias/opr_impl.cpp:248-275: Float32 bias and z) and the bf16 -> fp32 accumulate
+        // kernel the Float32 ConvBias path runs on its split operands (capi.cpp)
+        if ((d.bias_mode != B200CB_BIAS_NONE && d.bias_dtype != B200CB_DT_F32) || (d.has_z && d.z_dtype != B200CB_DT_F32))
+            return B200CB_UNSUPPORTED_DTYPE;
+        if (nchw4)
+            return B200CB_UNSUPPORTED_DTYPE;
+        out32 = out_f32 = true;
+    } else if (kind == KIND_S8) {
         if (d.dst_dtype == B200CB_DT_QS32) {
             // raw int32 accumulator + bias; the oracle writes sfb straight into dst
             // (naive/conv_bias/opr_impl.cpp:223-228) only for IDENTITY without z
@@ -1910,8 +1997,6 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         if (kind == KIND_F16 && d.compute_mode != B200CB_COMPUTE_FLOAT32)
             return B200CB_UNSUPPORTED_PARAM;
     }
-    if (d.bias_mode == B200CB_BIAS_FULL)
-        return B200CB_UNSUPPORTED_PARAM;
     if (block_n != 64 && block_n != 128 && block_n != 256)
         return B200CB_UNSUPPORTED_ALGO;
     const uint32_t in_es = kind == KIND_S8 ? 1 : 2;
@@ -1920,6 +2005,8 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     // (8-byte pixels are legal when the W-fold turns a pixel pair into one 16-byte unit: checked below)
     if (((d.ic * in_es) % 16 != 0 && d.ic * in_es != 8) || (!nchw4 && (d.oc * out_es) % 16 != 0))
         return B200CB_UNSUPPORTED_ALIGNMENT;
+    if (grouped && (d.ic * in_es) % 16 != 0)
+        return B200CB_UNSUPPORTED_ALIGNMENT;  // every group's channel slice must start on a 16-byte boundary
     if (d.n == 0 || d.oh == 0 || d.ow == 0 || d.fh == 0 || d.fw == 0)
         return B200CB_UNSUPPORTED_SHAPE;
     if (d.stride_h == 0 || d.stride_w == 0 || d.stride_h > 8 || d.stride_w > 8)
@@ -1952,7 +2039,7 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         dd.src_batch_stride = 0;
     // NCHW4 runs the generic modes only (no W-fold / stem / rows: their filter packing and output
     // paths are NHWC-specific); its z is read in place by the epilogue, not through the TMA ring
-    const Geometry g = make_geometry(dd, in_es, !nchw4 || dd.ic == 8);
+    const Geometry g = make_geometry(dd, in_es, !grouped && !out_f32 && (!nchw4 || dd.ic == 8));
     if ((g.ic * in_es) % 16 != 0)
         return B200CB_UNSUPPORTED_ALIGNMENT;
     if (g.folded && (g.pad_w_hi - (int32_t)(g.fw - 1) < -128 || g.pad_w_lo > 127))
@@ -1963,7 +2050,7 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
             fixed_smem(out32 ? 1 : 4, block_n, d.has_z && !nchw4, (out32 || in_es == 2) ? 128 : 64);
     // rows mode: the filter and >= 2 input slabs must fit next to the epilogue buffers
     const RowsGeom rg = rows_geometry(dd, in_es, block_n);
-    const bool rows = !nchw4 && !stem && !g.folded && rg.ok &&
+    const bool rows = !nchw4 && !grouped && !out32 && !stem && !g.folded && rg.ok &&
                       fixed0 + rg.bres + 2 * rg.a_stage <= MAX_DYN_SMEM;
     // generic modes: CTA pair (cta_group::2, 256 x BN tile, filter rows split between the two CTAs) or
     // a thread-block cluster sharing each filter tile by TMA multicast
@@ -2058,7 +2145,7 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     for (auto& r : plan->reserved)
         r = 0;
     plan->reserved[0] = static_cast<uint32_t>(kind);
-    plan->reserved[1] = out32 ? 1 : 0;
+    plan->reserved[1] = (out32 ? 1u : 0u) | (out_f32 ? 2u : 0u);
     // bit 0: debugging override (force the im2col path on pointwise convs); bit 1: direct-store epilogue
     plan->reserved[2] = pick_direct_store(d, nchw4, rows) ? 2u : 0u;
 #ifdef B200CB_TOOLS
@@ -2119,14 +2206,56 @@ int igemm_pack_filter(const b200cb_plan& plan, const void* filter, void* packed,
     return B200CB_OK;
 }
 
+namespace {
+int launch_dense(
+        const b200cb_plan& plan, const b200cb_desc& d, uint32_t ld_src, uint32_t ld_dst, const void* src,
+        const void* filter, const void* bias, const void* z, void* dst, void* workspace, cudaStream_t stream);
+}
+
 int igemm_launch(
         const b200cb_plan& plan, const void* src, const void* filter, const void* bias,
         const void* z, void* dst, void* workspace, size_t /*workspace_bytes*/,
         cudaStream_t stream) {
     const bool nchw4 = plan.desc.format == B200CB_FORMAT_NCHW4;
-    const b200cb_desc d = nchw4 ? nchw4_equivalent(plan.desc) : plan.desc;
+    b200cb_desc d;
+    uint32_t ld_src, ld_dst;
+    bool bias_as_z;
+    if (igemm_normalise(nchw4 ? nchw4_equivalent(plan.desc) : plan.desc, &d, &ld_src, &ld_dst, &bias_as_z) != B200CB_OK)
+        return B200CB_ERR_BAD_PLAN;
+    if (!src || !filter || !dst || (plan.desc.bias_mode != B200CB_BIAS_NONE && !bias) || (plan.desc.has_z && !z))
+        return B200CB_ERR_NULL;
+    if (bias_as_z) {
+        z = bias;
+        bias = nullptr;
+    }
+    const uint32_t groups = plan.desc.group;
+    if (groups <= 1)
+        return launch_dense(plan, d, ld_src, ld_dst, src, filter, bias, z, dst, workspace, stream);
+    // one dense launch per group on channel-sliced views (pixel pitch = the parent's channel count)
+    const uint32_t es = dtype_size(d.src_dtype), oes = dtype_size(d.dst_dtype);
+    const size_t flt_g = (size_t)d.oc * d.fh * d.fw * d.ic * es;
+    for (uint32_t g = 0; g < groups; ++g) {
+        const int rc = launch_dense(
+                plan, d, ld_src, ld_dst, static_cast<const uint8_t*>(src) + (size_t)g * d.ic * es,
+                static_cast<const uint8_t*>(filter) + g * flt_g,
+                bias ? static_cast<const uint8_t*>(bias) + (size_t)g * d.oc * dtype_size(d.bias_dtype) : nullptr,
+                z ? static_cast<const uint8_t*>(z) + (size_t)g * d.oc * dtype_size(d.z_dtype) : nullptr,
+                static_cast<uint8_t*>(dst) + (size_t)g * d.oc * oes, workspace, stream);
+        if (rc != B200CB_OK)
+            return rc;
+    }
+    return B200CB_OK;
+}
+
+namespace {
+int launch_dense(
+        const b200cb_plan& plan, const b200cb_desc& d, uint32_t ld_src, uint32_t ld_dst, const void* src,
+        const void* filter, const void* bias, const void* z, void* dst, void* workspace, cudaStream_t stream) {
+    const bool nchw4 = plan.desc.format == B200CB_FORMAT_NCHW4;
+    const bool grouped = plan.desc.group > 1;
     const int kind = static_cast<int>(plan.reserved[0]);
-    const bool out32 = plan.reserved[1] != 0;
+    const bool out32 = (plan.reserved[1] & 1) != 0;
+    const bool out_f32 = (plan.reserved[1] & 2) != 0;
     const uint32_t in_es = kind == KIND_S8 ? 1 : 2;
     const uint32_t out_es = out32 ? 4 : in_es;
     const uint32_t epi_n = out32 ? 32 : 64;
@@ -2156,10 +2285,10 @@ int igemm_launch(
     }
 
     b200cb_desc dd = d;
-    const uint64_t src_img = (uint64_t)d.ih * d.iw * d.ic;
+    const uint64_t src_img = (uint64_t)d.ih * d.iw * ld_src;  // elements between images of a dense parent tensor
     if (d.src_batch_stride == src_img)
         dd.src_batch_stride = 0;
-    const Geometry g = make_geometry(dd, in_es, !nchw4 || dd.ic == 8);
+    const Geometry g = make_geometry(dd, in_es, !grouped && !out_f32 && (!nchw4 || dd.ic == 8));
     const uint32_t kb_bytes = pick_kb_bytes(g.ic * in_es);
     const uint32_t kb_elems = kb_bytes / in_es;
     const CUtensorMapSwizzle in_swz = kb_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
@@ -2237,15 +2366,16 @@ int igemm_launch(
                     box, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     } else if (a_mode == 0) {
         uint64_t dims[2] = {d.ic, M};
-        uint64_t strides[1] = {(uint64_t)d.ic * in_es};
+        uint64_t strides[1] = {(uint64_t)ld_src * in_es};
         uint32_t box[2] = {kb_elems, IGEMM_BLOCK_M};
         cr = encode_tiled(
                 &p.tmA, in_dt, 2, src, dims, strides, box, nullptr, in_swz,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     } else {
+        // (grouped views are never W-folded: g.ic == d.ic there and the pixel pitch is the parent's)
+        const uint64_t pix = g.folded ? (uint64_t)g.ic : (uint64_t)ld_src;
         uint64_t dims[4] = {g.ic, g.iw, d.ih, d.n};
-        uint64_t strides[3] = {
-                (uint64_t)g.ic * in_es, (uint64_t)g.iw * g.ic * in_es, src_bstride * in_es};
+        uint64_t strides[3] = {pix * in_es, (uint64_t)g.iw * pix * in_es, src_bstride * in_es};
         int lower[2] = {-g.pad_w_lo, -(int)d.pad_h};
         int upper[2] = {
                 g.pad_w_hi - (int)((g.fw - 1) * d.dilate_w),
@@ -2289,7 +2419,7 @@ int igemm_launch(
         const CUtensorMapSwizzle swz = row_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B;
         // stem tiles are row segments: dst / z as (OC, OW, N*OH) so that a tile's tail is clipped
         uint64_t dims[3] = {d.oc, (stem || rows) ? (uint64_t)d.ow : M, (uint64_t)d.n * d.oh};
-        uint64_t strides[2] = {(uint64_t)d.oc * out_es, (uint64_t)d.ow * d.oc * out_es};
+        uint64_t strides[2] = {(uint64_t)ld_dst * out_es, (uint64_t)d.ow * ld_dst * out_es};
         uint32_t box_d[3] = {epi_n, 32, 1};
         uint32_t box_z[3] = {epi_n, IGEMM_BLOCK_M, 1};
         const uint32_t rank = (stem || rows) ? 3 : 2;
@@ -2355,7 +2485,9 @@ int igemm_launch(
     p.has_z = d.has_z && !nchw4;
     p.nchw4 = nchw4;
     p.z_direct = d.has_z && nchw4;
-    p.direct_store = (plan.reserved[2] >> 1) & 1;
+    p.direct_store = ((plan.reserved[2] >> 1) & 1) && ld_dst == d.oc;  // (the st.global path assumes a dense dst)
+    p.out_f32 = out_f32 ? 1 : 0;
+    p.acc_scale = d.src_scale * d.filter_scale;
     p.z = z;
     p.nz = (plan.reserved[5] >> 16) ? (plan.reserved[5] >> 16) : NZ_MIN;
     p.nonline = d.nonline_mode;
@@ -2392,7 +2524,9 @@ int igemm_launch(
         default: break;                                                                       \
     }
     if (p.pair) {
-        if (kind == KIND_BF16) {
+        if (kind == KIND_BF16 && out32) {
+            B200CB_DISPATCH(KIND_BF16, 1, 1)
+        } else if (kind == KIND_BF16) {
             B200CB_DISPATCH(KIND_BF16, 0, 1)
         } else if (kind == KIND_F16) {
             B200CB_DISPATCH(KIND_F16, 0, 1)
@@ -2401,6 +2535,8 @@ int igemm_launch(
         } else {
             B200CB_DISPATCH(KIND_S8, 1, 1)
         }
+    } else if (kind == KIND_BF16 && out32) {
+        B200CB_DISPATCH(KIND_BF16, 1, 0)
     } else if (kind == KIND_BF16) {
         B200CB_DISPATCH(KIND_BF16, 0, 0)
     } else if (kind == KIND_F16) {
@@ -2417,5 +2553,6 @@ int igemm_launch(
     }
     return B200CB_OK;
 }
+}  // namespace
 
 }  // namespace b200cb

@@ -206,7 +206,51 @@ int launch_group4(uint32_t es, const void* in, void* out, uint32_t N, uint32_t C
     return B200CB_OK;
 }
 
+// Float32 ConvBias operand split (capi.cpp, f32 adapter): x = x0 + x1 + r with x0 = bf16(x), x1 = bf16(x - x0),
+// |r| <= 2^-17 |x|.  in [p][C] fp32 -> out [p][3 * Cp] bf16, channel blocks (x0, x0, x1) for the activations
+// and (x0, x1, x0) for the filter, so that the bf16 dot product over 3 * Cp channels is
+// sum a0 b0 + a0 b1 + a1 b0 = sum a b (1 + O(2^-16)), accumulated in fp32 by the tensor core.
+__global__ void __launch_bounds__(256) split3_kernel(
+        const float* __restrict__ in, uint16_t* __restrict__ out, uint64_t P, uint32_t C, uint32_t Cp, int filter_side) {
+    const uint64_t total = P * Cp;
+    for (uint64_t t = blockIdx.x * static_cast<uint64_t>(blockDim.x) + threadIdx.x; t < total;
+         t += static_cast<uint64_t>(gridDim.x) * blockDim.x) {
+        const uint64_t p = t / Cp;
+        const uint32_t c = static_cast<uint32_t>(t - p * Cp);
+        const float x = c < C ? in[p * C + c] : 0.f;
+        const uint32_t xb = __float_as_uint(x);
+        // round to nearest even on the top 16 bits (finite inputs; inf / nan keep their class)
+        const uint32_t r0 = ((xb & 0x7f800000u) == 0x7f800000u) ? xb : xb + 0x7fffu + ((xb >> 16) & 1u);
+        const uint16_t h0 = static_cast<uint16_t>(r0 >> 16);
+        const float rem = x - __uint_as_float(static_cast<uint32_t>(h0) << 16);
+        const uint32_t rb = __float_as_uint(rem);
+        const uint32_t r1 = ((rb & 0x7f800000u) == 0x7f800000u) ? rb : rb + 0x7fffu + ((rb >> 16) & 1u);
+        const uint16_t h1 = static_cast<uint16_t>(r1 >> 16);
+        uint16_t* o = out + p * 3 * Cp + c;
+        o[0] = h0;
+        o[Cp] = filter_side ? h1 : h0;
+        o[2 * Cp] = filter_side ? h0 : h1;
+    }
+}
+
 }  // namespace
+
+int relayout_split3(const void* in, void* out, uint64_t P, uint32_t C, uint32_t Cp, int filter_side, cudaStream_t stream) {
+    if (P == 0 || C == 0 || Cp < C)
+        return B200CB_UNSUPPORTED_SHAPE;
+    uint64_t blocks = (P * Cp + 255) / 256;
+    const uint64_t cap = static_cast<uint64_t>(device_sm_count()) * 32;
+    if (blocks > cap)
+        blocks = cap;
+    split3_kernel<<<static_cast<uint32_t>(blocks), 256, 0, stream>>>(
+            static_cast<const float*>(in), static_cast<uint16_t*>(out), P, C, Cp, filter_side);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error("split3 launch", cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    return B200CB_OK;
+}
 
 // b200cb_relayout: see include/b200cb.h.  Every mode is pure HBM traffic (read src once, write dst once).
 int relayout_generic(

@@ -38,9 +38,9 @@ def make_desc(kind, n, ic, ih, iw, oc, fh, fw=None, stride=1, pad=0, dilate=1, g
     dt = KIND_DT[kind]
     d.src_dtype = d.filter_dtype = dt
     if kind == "qs8":
-        ddt = {None: C.DT_QS8, "qs8": C.DT_QS8, "qs32": C.DT_QS32}[dst_kind]
+        ddt = {None: C.DT_QS8, "qs8": C.DT_QS8, "qs32": C.DT_QS32, "f32": C.DT_F32}[dst_kind]
         d.dst_dtype = ddt
-        d.bias_dtype = C.DT_QS32
+        d.bias_dtype = C.DT_F32 if ddt == C.DT_F32 else C.DT_QS32   # naive DISPATCH(QuantizedS8, Float32): fp32 bias / z
         d.z_dtype = ddt if has_z else C.DT_NONE
         d.src_scale, d.filter_scale = f32(scales[0]), f32(scales[1])
         d.bias_scale = f32(d.src_scale * d.filter_scale) if scales[2] is None else f32(scales[2])
@@ -82,9 +82,13 @@ def gen_inputs(d, seed, int_range=8, bias_range=50, float_like="resnet"):
         src = rng.integers(-int_range, int_range + 1, n_src, dtype=np.int8)
         flt = rng.integers(-int_range, int_range + 1, n_flt, dtype=np.int8)
         bias = rng.integers(-bias_range, bias_range + 1, n_bias).astype(np.int32) if n_bias else None
+        if n_bias and d.bias_dtype == C.DT_F32:
+            bias = rng.uniform(-0.5, 0.5, n_bias).astype(np.float32)
         z = None
         if d.has_z:
-            if d.z_dtype == C.DT_QS8:
+            if d.z_dtype == C.DT_F32:
+                z = rng.standard_normal(n_dst, dtype=np.float32)
+            elif d.z_dtype == C.DT_QS8:
                 z = rng.integers(-127, 128, n_dst, dtype=np.int8)
             else:
                 z = rng.integers(-5000, 5001, n_dst).astype(np.int32)

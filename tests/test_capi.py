@@ -100,21 +100,46 @@ def test_unsupported_cells_are_rejected_not_silently_wrong(lib):
     assert _query(lib, ok)[0] == 0
     cases = []
     d = ok.copy(); d.format = 2; cases.append(d)                                   # format (NHWCD4)
-    d = K.make_desc("f32", 2, 64, 14, 14, 64, 3, pad=1, fmt=C.FORMAT_NCHW); cases.append(d)  # NCHW fp32: not on this path
+    d = K.make_desc("f32", 2, 64, 14, 14, 62, 3, pad=1, fmt=C.FORMAT_NCHW); cases.append(d)  # fp32 path: OC % 4
     d = K.make_desc("bf16", 2, 64, 14, 14, 60, 3, pad=1, fmt=C.FORMAT_NCHW); cases.append(d)  # NCHW adapter needs OC % 8
-    d = ok.copy(); d.src_dtype = d.filter_dtype = C.DT_F32; d.dst_dtype = d.bias_dtype = C.DT_F32; cases.append(d)
+    d = ok.copy(); d.src_dtype = d.filter_dtype = C.DT_F32; d.dst_dtype = C.DT_F32; cases.append(d)  # fp32 conv, bf16 bias
     d = ok.copy(); d.ic = 60; cases.append(d)                                      # 16-byte channel alignment
-    d = ok.copy(); d.bias_mode = C.BIAS_FULL; cases.append(d)
+    d = ok.copy(); d.bias_mode = C.BIAS_FULL; d.has_z = 1; d.z_dtype = d.dst_dtype; cases.append(d)  # full bias AND z
+    d = K.make_desc("qs8", 2, 64, 14, 14, 64, 3, pad=1, bias_mode=C.BIAS_FULL); cases.append(d)  # QS32 full bias
     d = ok.copy(); d.filter_dtype = C.DT_F16; cases.append(d)                      # src/filter mismatch
     d = ok.copy(); d.oh += 1; cases.append(d)                                      # inconsistent output extent
     d = ok.copy(); d.stride_h = 0; cases.append(d)
     d = K.make_desc("qs8", 2, 64, 14, 14, 64, 3, pad=1, nonline=C.NL_SIGMOID); cases.append(d)
     d = K.make_desc("qs8", 2, 64, 14, 14, 64, 3, pad=1, dst_kind="qs32", nonline=C.NL_RELU); cases.append(d)
-    d = K.make_desc("bf16", 2, 64, 14, 14, 64, 3, pad=1, group=2); cases.append(d)  # general group conv
+    d = K.make_desc("bf16", 2, 24, 14, 14, 64, 3, pad=1, group=2); cases.append(d)  # group slices of 24 bytes
+    d = K.make_desc("qs8", 2, 64, 14, 14, 64, 3, pad=1, dst_kind="f32"); d.bias_dtype = C.DT_QS32; cases.append(d)
     for d in cases:
         rc, _p = _query(lib, d)
         assert rc > 0, K.desc_str(d)
         assert lib.b200cb_strerror(rc) not in (b"ok", b"unknown error")
+
+
+def test_new_cells_of_round2_are_available(lib):
+    """a13 cells closed in round 2: general GROUP conv (one dense launch per group on channel-sliced views),
+    BiasMode::BIAS through the z ring, QuantizedS8 -> Float32, Float32 NHWC / NCHW through the bf16 x 3 split."""
+    d = K.make_desc("bf16", 2, 64, 14, 14, 128, 3, pad=1, group=4, nonline=C.NL_RELU, has_z=True)
+    rc, p = _query(lib, d)
+    assert rc == 0 and lib.b200cb_plan_num_launches(ctypes.byref(p)) == 4
+    assert p.flops == 2 * 2 * 128 * 14 * 14 * 16 * 9
+    rc, p = _query(lib, K.make_desc("f16", 2, 64, 14, 14, 64, 3, pad=1, bias_mode=C.BIAS_FULL))
+    assert rc == 0 and p.workspace_bytes == 0
+    rc, p = _query(lib, K.make_desc("qs8", 2, 64, 14, 14, 64, 3, pad=1, dst_kind="f32", has_z=True, nonline=C.NL_H_SWISH))
+    assert rc == 0
+    for fmt, nl in ((C.FORMAT_NHWC, 2), (C.FORMAT_NCHW, 6)):
+        d = K.make_desc("f32", 2, 20, 14, 14, 64, 3, pad=1, fmt=fmt, has_z=True, nonline=C.NL_RELU)
+        rc, p = _query(lib, d)
+        assert rc == 0, lib.b200cb_strerror(rc)
+        a = lambda v: (v + 255) & ~255
+        assert p.workspace_bytes >= a(2 * 14 * 14 * 72 * 2) + a(64 * 9 * 72 * 2)   # 3 x 24 bf16 channels
+        assert lib.b200cb_plan_num_launches(ctypes.byref(p)) == nl + 1
+    # BASELINE configs[0]: every ResNet-18 fp32 NCHW layer has a plan
+    for layer in K.RESNET18_LAYERS:
+        assert _query(lib, K.resnet18_desc(layer, 8))[0] == 0, layer[0]
 
 
 def test_nchw_16bit_plans_carry_the_relayout_workspace(lib):

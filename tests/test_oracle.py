@@ -103,6 +103,10 @@ def _sweep_cases():
                 out.append(K.make_desc(kind, 1, 8, 7, 7, 12, 3, pad=1, group=4, fmt=fmt))
                 out.append(K.make_desc(kind, 1, 4, 7, 7, 4, 3, pad=1, mode=1, fmt=fmt))
                 out.append(K.make_desc(kind, 1, 4, 9, 9, 4, 3, pad=2, dilate=2, fmt=fmt, has_z=True))
+            if kind == "qs8" and fmt != C.FORMAT_NCHW4:
+                # QuantizedS8 -> Float32 (fp32 bias / z, dequantised products accumulated in fp32)
+                out.append(K.make_desc("qs8", 2, 16, 7, 7, 16, 3, pad=1, fmt=fmt, nonline=1, has_z=True, dst_kind="f32"))
+                out.append(K.make_desc("qs8", 1, 8, 5, 6, 12, 1, fmt=fmt, nonline=3, dst_kind="f32"))
             # depthwise 3x3 as the GPU parity cases run it (get_chanwise_args, dnn/test/cuda/conv_bias.cpp:650-714):
             # channel counts that are not vector multiples, stride 2 on odd extents, no padding, z
             if fmt == C.FORMAT_NHWC and kind in ("f16", "bf16"):

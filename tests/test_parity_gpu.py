@@ -505,3 +505,81 @@ def test_stem_row_ring(case):
     plan, _info = _check(d, {"int_range": 127, "bias_range": 5000} if kind == "qs8" else None, seed=61 + h)
     assert plan.a_mode == 2
     assert ((plan.reserved[4] >> 1) & 1) == (0 if ("classic" in _name or kind == "qs8") else 1)
+
+
+# ------------------------------------------------------------------ a13 cells closed in round 2
+GROUP_CASES = [
+    # name, kind, n, ic, h, w, oc, f, stride, pad, group, nonline, has_z   (dnn/test/cuda/conv_bias.cpp:234-265 group args)
+    ("bf16_g2_3x3_z", "bf16", 2, 64, 14, 14, 128, 3, 1, 1, 2, C.NL_RELU, True),
+    ("f16_g4_1x1", "f16", 3, 64, 9, 9, 64, 1, 1, 0, 4, C.NL_IDENTITY, False),
+    ("bf16_g32_resnext", "bf16", 2, 256, 14, 14, 256, 3, 1, 1, 32, C.NL_RELU, False),
+    ("qs8_g2_3x3_s2_z", "qs8", 2, 64, 15, 15, 64, 3, 2, 1, 2, C.NL_RELU, True),
+    ("qs8_g4_5x5_hswish", "qs8", 1, 128, 12, 12, 64, 5, 1, 2, 4, C.NL_H_SWISH, False),
+]
+
+
+@pytest.mark.parametrize("case", GROUP_CASES, ids=[c[0] for c in GROUP_CASES])
+def test_general_group_conv(case):
+    """param::Sparse::GROUP with icpg, ocpg > 1: one dense launch per group on channel-sliced views of src / z /
+    dst (replaces dnn/src/cuda/conv_bias/group_conv.cpp)."""
+    _n, kind, n, ic, h, w, oc, f, s, pd, grp, nl, has_z = case
+    d = K.make_desc(kind, n, ic, h, w, oc, f, stride=s, pad=pd, group=grp, nonline=nl, has_z=has_z,
+                    scales=(0.37, 0.71, None, 1.9, 23.0))
+    plan, _info = _check(d, {"int_range": 127, "bias_range": 5000} if kind == "qs8" else None, seed=71 + grp)
+    assert C.load().b200cb_algo_name(plan.algo).decode().startswith("B200_IGEMM")
+
+
+@pytest.mark.parametrize("kind,f,nl", [("bf16", 3, C.NL_RELU), ("f16", 1, C.NL_IDENTITY), ("bf16", 1, C.NL_H_SWISH)])
+def test_full_shape_bias(kind, f, nl):
+    """BiasMode::BIAS (dst-shaped bias, dnn/src/common/conv_bias.cpp:38-49) through the z ring."""
+    d = K.make_desc(kind, 3, 64, 10, 12, 128, f, pad=f // 2, nonline=nl, bias_mode=C.BIAS_FULL)
+    _check(d, seed=81 + f)
+
+
+QS8_F32_CASES = [
+    ("3x3_z_relu", 2, 64, 14, 14, 128, 3, 1, 1, C.NL_RELU, True),
+    ("1x1_identity", 3, 32, 9, 9, 64, 1, 1, 0, C.NL_IDENTITY, False),
+    ("5x5_s2_hswish_z", 2, 16, 17, 17, 36, 5, 2, 2, C.NL_H_SWISH, True),
+    ("7x7_s2_ic16", 1, 16, 30, 30, 64, 7, 2, 3, C.NL_RELU, False),
+]
+
+
+@pytest.mark.parametrize("case", QS8_F32_CASES, ids=[c[0] for c in QS8_F32_CASES])
+def test_qs8_to_float32(case):
+    """QuantizedS8 x QuantizedS8 -> Float32 (naive DISPATCH(QuantizedS8, Float32): fp32 bias / z).  The oracle
+    accumulates dequantised products in fp32, the GPU scales the exact int32 sum once: Float32 tolerance 1e-3."""
+    _n, n, ic, h, w, oc, f, s, pd, nl, has_z = case
+    d = K.make_desc("qs8", n, ic, h, w, oc, f, stride=s, pad=pd, nonline=nl, has_z=has_z, dst_kind="f32",
+                    scales=(0.037, 0.071, None, 1.0, 1.0))
+    _check(d, {"int_range": 127}, seed=91 + ic)
+
+
+F32_CASES = [
+    # name, fmt, n, ic, h, w, oc, f, stride, pad, nonline, has_z      (dnn/test/cuda/conv_bias.cpp:83-100 eps 1e-3)
+    ("nhwc_3x3_z_relu", C.FORMAT_NHWC, 2, 64, 14, 14, 128, 3, 1, 1, C.NL_RELU, True),
+    ("nhwc_1x1_ic20", C.FORMAT_NHWC, 3, 20, 9, 11, 64, 1, 1, 0, C.NL_IDENTITY, False),
+    ("nchw_3x3_z_relu", C.FORMAT_NCHW, 2, 32, 14, 14, 64, 3, 1, 1, C.NL_RELU, True),
+    ("nchw_7x7_s2_ic3_stem", C.FORMAT_NCHW, 2, 3, 62, 62, 64, 7, 2, 3, C.NL_RELU, False),
+    ("nchw_5x5_s2_oc36_hswish", C.FORMAT_NCHW, 2, 12, 17, 17, 36, 5, 2, 2, C.NL_H_SWISH, False),
+    ("nchw_1x1_s2_sigmoid_z", C.FORMAT_NCHW, 2, 24, 12, 12, 40, 1, 2, 0, C.NL_SIGMOID, True),
+]
+
+
+@pytest.mark.parametrize("case", F32_CASES, ids=[c[0] for c in F32_CASES])
+def test_float32_through_bf16_split(case):
+    """Float32 NHWC / NCHW ConvBias on the tensor-core path: operands split into bf16 pieces (x = x0 + x1 +
+    O(2^-17)), three products accumulated in fp32, Float32 epilogue -- the reference test's own eps 1e-3."""
+    _n, fmt, n, ic, h, w, oc, f, s, pd, nl, has_z = case
+    d = K.make_desc("f32", n, ic, h, w, oc, f, stride=s, pad=pd, fmt=fmt, nonline=nl, has_z=has_z)
+    plan, info = _check(d, seed=101 + ic)
+    assert info["max_rel"] < 2e-4, info     # the split leaves ~2^-16 per product: far inside 1e-3
+
+
+@pytest.mark.parametrize("layer", K.RESNET18_LAYERS, ids=[l[0] for l in K.RESNET18_LAYERS])
+def test_resnet18_fp32_nchw_on_the_gpu_path(layer):
+    """BASELINE.json configs[0] (ResNet-18, fp32 NCHW, bias + ReLU) on the GPU path against the naive oracle;
+    conv1 on a reduced image for the oracle's sake."""
+    d = K.resnet18_desc(layer, 2)
+    if layer[0] == "conv1":
+        d = K.make_desc("f32", 2, 3, 96, 96, 64, 7, stride=2, pad=3, fmt=C.FORMAT_NCHW, nonline=C.NL_RELU)
+    _check(d, seed=111)
