@@ -374,22 +374,46 @@ struct Dw3Common {
     uint32_t flip, has_bias, has_z, nonline;
 };
 
+// Float32 rides the same kernels: one fp32 channel is one 32-bit word, i.e. the "pair" (c, c + 1) of 16-bit
+// half-channels of a tensor with 2 C half-channels; the second lane of every packed operation is a zero
+// (the kernels are HBM bound: instructions per byte are the same as for the 16-bit kinds).
 template <int KIND>
 __device__ __forceinline__ float2 unpack2(uint32_t w) {
     if constexpr (KIND == B200CB_DT_BF16)
         return make_float2(bf16lo(w), bf16hi(w));
+    else if constexpr (KIND == B200CB_DT_F32)
+        return make_float2(__uint_as_float(w), 0.f);
     else
         return make_float2(f16lo(w), f16hi(w));
 }
 template <int KIND>
-__device__ __forceinline__ float elem_f32(const void* p, size_t idx) {
+__device__ __forceinline__ uint32_t pack2(float2 v) {
     if constexpr (KIND == B200CB_DT_BF16)
+        return pack_bf16x2(v.x, v.y);
+    else if constexpr (KIND == B200CB_DT_F32)
+        return __float_as_uint(v.x);
+    else
+        return pack_f16x2(v.x, v.y);
+}
+template <int KIND>
+__device__ __forceinline__ float elem_f32(const void* p, size_t idx) {
+    if constexpr (KIND == B200CB_DT_F32)
+        return reinterpret_cast<const float*>(p)[idx];
+    else if constexpr (KIND == B200CB_DT_BF16)
         return __uint_as_float(static_cast<uint32_t>(reinterpret_cast<const unsigned short*>(p)[idx]) << 16);
     else
         return __half2float(reinterpret_cast<const __half*>(p)[idx]);
 }
 template <int KIND>
 __device__ __forceinline__ void load_weights(const Dw3Common& p, uint32_t c, float2 (&w)[9], float2& bias) {
+    if constexpr (KIND == B200CB_DT_F32) {
+        const uint32_t ch = c / 2;  // half-channel index -> fp32 channel
+#pragma unroll
+        for (int tap = 0; tap < 9; ++tap)
+            w[tap] = make_float2(reinterpret_cast<const float*>(p.filter)[(size_t)ch * 9 + (p.flip ? 8 - tap : tap)], 0.f);
+        bias = make_float2(p.has_bias ? reinterpret_cast<const float*>(p.bias)[ch] : 0.f, 0.f);
+        return;
+    }
 #pragma unroll
     for (int tap = 0; tap < 9; ++tap) {
         const int ft = p.flip ? 8 - tap : tap;
@@ -474,7 +498,7 @@ __device__ __forceinline__ void dw3_slide(
             }
             if (store_ok && ow0 + t2 < p.OW)
                 dst[orow + static_cast<size_t>(t2) * p.CP] =
-                        KIND == B200CB_DT_BF16 ? pack_bf16x2(acc.x, acc.y) : pack_f16x2(acc.x, acc.y);
+                        pack2<KIND>(acc);
         }
     };
     using I0 = std::integral_constant<int, 0>;
@@ -586,7 +610,7 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
     __syncthreads();
     // programmatic dependent launch: the next kernel's CTAs may take this SM as soon as it is free; this
     // one touches activations (src / z / dst) only after the kernel before it has completed
-    pdl_launch_dependents();
+    ptx::pdl_launch_dependents();
     // gridDim.x is a multiple of cblks: this CTA's channel block never changes
     const uint32_t cblk = blockIdx.x % q.cblks;
     const uint32_t sp0 = blockIdx.x / q.cblks, sp_step = gridDim.x / q.cblks;
@@ -618,8 +642,10 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
     const uint32_t c = cblk * CB + cpl * 2;
     const bool ch_ok = c < p.C;
     float2 w[9], bias;
-    load_weights<KIND>(p, ch_ok ? c : 0, w, bias);   // constants: read before the dependency wait
-    pdl_wait();
+    // (filter / bias are stream-ordered inputs like any other: a previous kernel of the stream may have
+    // written them -- dynamic filters, on-device weight updates -- so they are read after the dependency wait)
+    ptx::pdl_wait();
+    load_weights<KIND>(p, ch_ok ? c : 0, w, bias);
     const uint32_t u = warp * SUBS + sub;          // this thread's unit in every tile
     const bool has_unit = u < q.units;
     const uint32_t strip = u % q.strips, span = (u / q.strips) % q.spans, img = u / (q.strips * q.spans);
@@ -701,8 +727,7 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
 #pragma unroll
                 for (int t2 = 0; t2 < TW; ++t2)
                     if ((cmask >> t2) & 1)
-                        drow[t2 * cstride] = KIND == B200CB_DT_BF16 ? pack_bf16x2(acc[t2].x, acc[t2].y)
-                                                                    : pack_f16x2(acc[t2].x, acc[t2].y);
+                        drow[t2 * cstride] = pack2<KIND>(acc[t2]);
                 drow += rstride;
             };
             using I0 = std::integral_constant<int, 0>;
@@ -793,7 +818,7 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1) dw3x3_bulk_ke
         }
     }
     __syncthreads();
-    pdl_launch_dependents();
+    ptx::pdl_launch_dependents();
     if (warp == DW3_COMPUTE_WARPS) {
         pdl_wait();
         uint32_t st = 0, ph = 0;
@@ -824,8 +849,8 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1) dw3x3_bulk_ke
     const uint32_t cp = threadIdx.x % p.CP, u0 = threadIdx.x / p.CP;
     const bool active = u0 < q.U;
     float2 w[9], bias;
+    ptx::pdl_wait();  // (weights are stream-ordered inputs too: read after the dependency wait)
     load_weights<KIND>(p, cp * 2, w, bias);
-    pdl_wait();
     const uint32_t units = q.strips * q.spans;
     const float act_lo = p.nonline == B200CB_NL_RELU ? 0.f : -INFINITY;
     const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
@@ -911,8 +936,7 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1) dw3x3_bulk_ke
 #pragma unroll
                     for (int t2 = 0; t2 < TW; ++t2)
                         if ((cmask >> t2) & 1)
-                            drow[t2 * cstride] = KIND == B200CB_DT_BF16 ? pack_bf16x2(acc[t2].x, acc[t2].y)
-                                                                        : pack_f16x2(acc[t2].x, acc[t2].y);
+                            drow[t2 * cstride] = pack2<KIND>(acc[t2]);
                     drow += rstride;
                 };
                 using I0 = std::integral_constant<int, 0>;
@@ -945,6 +969,406 @@ __global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1) dw3x3_bulk_ke
     }
 }
 
+// ------------------------------------------------------------------------------------------------
+// 3x3 depthwise, QuantizedS8 (replaces dnn/src/cuda/conv_bias/chanwise_8x8x32.cpp + the TypeCvt / Elemwise
+// passes behind it): a window kernel on 4-channel words.
+//   thread   = one 32-bit word of the NHWC row (4 channels) x TW adjacent output columns x a vertical span;
+//   warp     = consecutive channel words: loads / stores touch whole 128-byte lines;
+//   math     = DP4A ACROSS TAPS: the 6 pixel words of an input row are byte-transposed (PRMT) into
+//              per-channel words [p0 p1 p2 p3] / [p2 p3 p4 p5]; one dp4a with the filter row packed as
+//              [w0 w1 w2 0] or [0 w0 w1 w2] is one output's whole filter row (3 MACs), so an output costs
+//              3 dp4a instead of 9 multiply-adds + 9 byte extractions;
+//   window   = the transposed rows slide down in registers (one new input row per output row at stride 1);
+//   epilogue = bias (accumulator init), z, activation and the bit-exact requantize of epilogue.cuh fused.
+struct DwS8Params {
+    const uint32_t* src;
+    const int8_t* filter;
+    const int32_t* bias;
+    const uint32_t* z;
+    uint32_t* dst;
+    uint32_t N, C, IH, IW, OH, OW, CW;  // CW = C / 4 words per pixel
+    int32_t pad_h, pad_w;
+    uint64_t src_bwords, z_bwords, dst_bwords;
+    uint32_t strips, spans, RH;
+    uint64_t total_items;
+    uint32_t flip, has_bias, has_z, nonline;
+    RequantParams rq;
+};
+
+__device__ __forceinline__ int32_t sx8(uint32_t w, int b) {
+    return static_cast<int32_t>(static_cast<int8_t>((w >> (8 * b)) & 0xffu));
+}
+
+// MODE: 0 = generic requantize (any activation / scale), 1 = fast IDENTITY, 2 = fast RELU (epilogue.cuh);
+// the variants are separate kernels so that the row loop holds exactly one epilogue (a run-time choice
+// inside the unrolled loop quadrupled the code and ran out of the instruction cache)
+template <int S, int MODE, bool HAS_Z>
+__global__ void __launch_bounds__(256, 2) dw3x3_s8_kernel(const DwS8Params p) {
+    constexpr int TW = S == 1 ? 4 : 2;
+    const uint64_t item = static_cast<uint64_t>(blockIdx.x) * 256 + threadIdx.x;
+    if (item >= p.total_items)
+        return;
+    const uint32_t cw = static_cast<uint32_t>(item % p.CW);
+    uint64_t t = item / p.CW;
+    const uint32_t strip = static_cast<uint32_t>(t % p.strips);
+    t /= p.strips;
+    const uint32_t span = static_cast<uint32_t>(t % p.spans);
+    const uint32_t n = static_cast<uint32_t>(t / p.spans);
+    const uint32_t ow0 = strip * TW, oh0 = span * p.RH;
+    const uint32_t oh1 = oh0 + p.RH < p.OH ? oh0 + p.RH : p.OH;
+    ptx::pdl_launch_dependents();
+    ptx::pdl_wait();
+
+    // filter rows packed for dp4a: wa = [w0 w1 w2 0] (bytes 0..3), wb = [0 w0 w1 w2].  The 4 channels' 36
+    // filter bytes are 9 aligned words
+    uint32_t wa[4][3], wb[4][3];
+    int32_t bias[4];
+    {
+        uint32_t fw[9];
+        const uint32_t* f32p = reinterpret_cast<const uint32_t*>(p.filter) + static_cast<size_t>(cw) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            fw[i] = __ldg(f32p + i);
+        auto fbyte = [&](int idx) { return (fw[idx >> 2] >> (8 * (idx & 3))) & 0xffu; };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    const int tap = r * 3 + x;
+                    w |= (p.flip ? fbyte(k * 9 + 8 - tap) : fbyte(k * 9 + tap)) << (8 * x);
+                }
+                wa[k][r] = w, wb[k][r] = w << 8;
+            }
+            bias[k] = p.has_bias ? p.bias[cw * 4 + k] : 0;
+        }
+    }
+    const uint32_t* img = p.src + n * p.src_bwords + cw;
+    const int32_t iw0 = static_cast<int32_t>(ow0) * S - p.pad_w;
+    // raw pixel words of one input row (the 6 this thread needs), and their byte transpose into per-channel
+    // words A[k] = pixels 0..3, B[k] = pixels 2..5
+    auto fetch_row = [&](int32_t ih, uint32_t (&px)[6]) {
+#pragma unroll
+        for (int j = 0; j < 6; ++j) {
+            const int32_t iw = iw0 + j;
+            px[j] = (static_cast<uint32_t>(ih) < p.IH && static_cast<uint32_t>(iw) < p.IW)
+                            ? __ldg(img + (static_cast<size_t>(ih) * p.IW + iw) * p.CW)
+                            : 0u;
+        }
+    };
+    auto transpose_row = [&](const uint32_t (&px)[6], uint32_t (&A)[4], uint32_t (&B)[4]) {
+        const uint32_t l01 = __byte_perm(px[0], px[1], 0x5140), h01 = __byte_perm(px[0], px[1], 0x7362);
+        const uint32_t l23 = __byte_perm(px[2], px[3], 0x5140), h23 = __byte_perm(px[2], px[3], 0x7362);
+        const uint32_t l45 = __byte_perm(px[4], px[5], 0x5140), h45 = __byte_perm(px[4], px[5], 0x7362);
+        A[0] = __byte_perm(l01, l23, 0x5410), A[1] = __byte_perm(l01, l23, 0x7632);
+        A[2] = __byte_perm(h01, h23, 0x5410), A[3] = __byte_perm(h01, h23, 0x7632);
+        B[0] = __byte_perm(l23, l45, 0x5410), B[1] = __byte_perm(l23, l45, 0x7632);
+        B[2] = __byte_perm(h23, h45, 0x5410), B[3] = __byte_perm(h23, h45, 0x7632);
+    };
+    uint32_t A[3][4], B[3][4];
+    uint32_t nx[S][6];  // the next output row's new input row(s), in flight while this row is computed
+    const int32_t ih_top = static_cast<int32_t>(oh0) * S - p.pad_h;
+    {
+        uint32_t px[6];
+        fetch_row(ih_top, px);
+        transpose_row(px, A[0], B[0]);
+        if (S == 1) {
+            fetch_row(ih_top + 1, px);
+            transpose_row(px, A[1], B[1]);
+        }
+    }
+    // new rows of output row oh0: ih_top + 2 (stride 1) / ih_top + 1, + 2 (stride 2)
+#pragma unroll
+    for (int k = 0; k < S; ++k)
+        fetch_row(ih_top + 3 - S + k, nx[k]);
+    const RequantPacked kp = make_requant_packed(p.rq);
+#pragma unroll 1
+    for (uint32_t oh = oh0; oh < oh1; ++oh) {
+        const int32_t ih = static_cast<int32_t>(oh) * S - p.pad_h;
+        if (S == 1) {
+            transpose_row(nx[0], A[2], B[2]);
+        } else {
+            transpose_row(nx[0], A[1], B[1]);
+            transpose_row(nx[S - 1], A[2], B[2]);
+        }
+        if (oh + 1 < oh1) {
+#pragma unroll
+            for (int k = 0; k < S; ++k)
+                fetch_row(ih + S + 3 - S + k, nx[k]);
+        }
+        const size_t orow = (static_cast<size_t>(oh) * p.OW + ow0) * p.CW + cw;
+        uint32_t zw[TW];
+#pragma unroll
+        for (int t2 = 0; t2 < TW; ++t2)
+            zw[t2] = (HAS_Z && ow0 + t2 < p.OW) ? __ldg(p.z + n * p.z_bwords + orow + static_cast<size_t>(t2) * p.CW) : 0u;
+#pragma unroll
+        for (int t2 = 0; t2 < TW; ++t2) {
+            int32_t acc[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                int32_t a = bias[k];
+#pragma unroll
+                for (int r = 0; r < 3; ++r) {
+                    uint32_t x, w;
+                    if (S == 1) {
+                        x = (t2 < 2) ? A[r][k] : B[r][k];
+                        w = (t2 & 1) ? wb[k][r] : wa[k][r];
+                    } else {
+                        x = t2 == 0 ? A[r][k] : B[r][k];
+                        w = wa[k][r];
+                    }
+                    a = __dp4a(static_cast<int32_t>(x), static_cast<int32_t>(w), a);
+                }
+                acc[k] = a;
+            }
+            uint32_t o;
+            if constexpr (MODE != 0) {
+                const uint32_t zx = zw[t2] ^ 0x80808080u;
+                uint32_t ub[4];
+#pragma unroll
+                for (int b = 0; b < 4; b += 2) {
+                    const uint32_t z0 = __byte_perm(zx, 0x4B000000u, 0x7540u | b);
+                    const uint32_t z1 = __byte_perm(zx, 0x4B000000u, 0x7540u | (b + 1));
+                    if constexpr (MODE == 2)
+                        requant_pair_nonneg<HAS_Z>(acc[b], acc[b + 1], z0, z1, kp, ub[b], ub[b + 1]);
+                    else
+                        requant_pair_signed<HAS_Z>(acc[b], acc[b + 1], z0, z1, kp, ub[b], ub[b + 1]);
+                }
+                o = pack_low_bytes(ub[0], ub[1], ub[2], ub[3]);
+            } else {
+                o = 0;
+#pragma unroll
+                for (int b = 0; b < 4; ++b)
+                    o |= (static_cast<uint32_t>(requant_s8(acc[b], HAS_Z ? sx8(zw[t2], b) : 0, p.nonline, p.rq)) & 0xffu) << (8 * b);
+            }
+            if (ow0 + t2 < p.OW)
+                p.dst[n * p.dst_bwords + orow + static_cast<size_t>(t2) * p.CW] = o;
+        }
+        // slide the window down
+        if (S == 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                A[0][k] = A[1][k], B[0][k] = B[1][k];
+                A[1][k] = A[2][k], B[1][k] = B[2][k];
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                A[0][k] = A[2][k], B[0][k] = B[2][k];
+        }
+    }
+}
+
+// The same window math behind the TMA front end of the 16-bit kernels (dw3x3_tma_kernel): input tiles staged
+// in shared memory by a producer warp, 3-4 tiles in flight per SM whatever the occupancy.  The int8 tensor
+// is seen as 16-bit "channels" (C / 2 of them), so tile geometry and tensor map are launch_dw3_tma's; a lane
+// owns one 32-bit word = 4 int8 channels.  IDENTITY / RELU with ordinary scales only (MODE 1 / 2).
+struct Dw3S8TmaParams {
+    Dw3TmaParams t;
+    RequantParams rq;
+};
+
+template <int S, int MODE, bool HAS_Z, int CPB>
+__global__ void __launch_bounds__((DW3_COMPUTE_WARPS + 1) * 32, 1)
+        dw3x3_s8_tma_kernel(const __grid_constant__ Dw3S8TmaParams qq) {
+    constexpr int TW = S == 1 ? 4 : 2;
+    constexpr int IN = (TW - 1) * S + 3;     // 6 (stride 1) or 5 (stride 2) pixel words per row
+    constexpr uint32_t PIX = CPB * 4;        // bytes per pixel in the tile
+    constexpr uint32_t CB = CPB * 2;
+    using namespace ptx;
+    const Dw3TmaParams& q = qq.t;
+    const Dw3Common& p = q.c;
+    extern __shared__ __align__(128) uint8_t dsm[];
+    const uint32_t sbase = smem_u32(dsm);
+    const uint32_t bar_full = sbase, bar_empty = sbase + 64;
+    const uint32_t stage0 = sbase + 128;
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        prefetch_tensormap(&q.tmS);
+        for (uint32_t i = 0; i < q.stages; ++i) {
+            mbar_init(bar_full + 8 * i, 1);
+            mbar_init(bar_empty + 8 * i, DW3_COMPUTE_WARPS);
+        }
+        fence_mbar_init();
+    }
+    __syncthreads();
+    pdl_launch_dependents();
+    const uint32_t cblk = blockIdx.x % q.cblks;
+    const uint32_t sp0 = blockIdx.x / q.cblks, sp_step = gridDim.x / q.cblks;
+    if (warp == DW3_COMPUTE_WARPS) {
+        pdl_wait();
+        uint32_t st = 0, ph = 0;
+        for (uint32_t sp = sp0; sp < q.spatial_tiles; sp += sp_step) {
+            const uint32_t tw = sp % q.tiles_w, r = sp / q.tiles_w;
+            const uint32_t th = r % q.tiles_h, n = r / q.tiles_h;
+            mbar_wait(bar_empty + 8 * st, ph ^ 1);
+            if (elect_one()) {
+                mbar_arrive_expect_tx(bar_full + 8 * st, q.tile_bytes);
+                tma_load_4d(
+                        stage0 + st * q.stage_bytes, &q.tmS, bar_full + 8 * st,
+                        static_cast<int32_t>(cblk * CB), static_cast<int32_t>(tw * q.TWT) * S - p.pad_w,
+                        static_cast<int32_t>(th * q.TH) * S - p.pad_h, static_cast<int32_t>(n * q.NB));
+            }
+            __syncwarp();
+            if (++st == q.stages) {
+                st = 0;
+                ph ^= 1;
+            }
+        }
+        return;
+    }
+    const uint32_t cpl = lane % CPB, sub = lane / CPB;
+    constexpr uint32_t SUBS = 32 / CPB;
+    const uint32_t c = cblk * CB + cpl * 2;  // first 16-bit "channel" of the lane's word
+    const bool ch_ok = c < p.C;
+    const uint32_t cw = ch_ok ? c / 2 : 0;   // word of the pixel = 4 int8 channels
+    pdl_wait();
+    uint32_t wa[4][3];
+    int32_t bias[4];
+    {
+        uint32_t fw[9];
+        const uint32_t* f32p = reinterpret_cast<const uint32_t*>(p.filter) + static_cast<size_t>(cw) * 9;
+#pragma unroll
+        for (int i = 0; i < 9; ++i)
+            fw[i] = __ldg(f32p + i);
+        auto fbyte = [&](int idx) { return (fw[idx >> 2] >> (8 * (idx & 3))) & 0xffu; };
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+                uint32_t w = 0;
+#pragma unroll
+                for (int x = 0; x < 3; ++x) {
+                    const int tap = r * 3 + x;
+                    w |= (p.flip ? fbyte(k * 9 + 8 - tap) : fbyte(k * 9 + tap)) << (8 * x);
+                }
+                wa[k][r] = w;
+            }
+            bias[k] = p.has_bias ? reinterpret_cast<const int32_t*>(p.bias)[cw * 4 + k] : 0;
+        }
+    }
+    const RequantPacked kp = make_requant_packed(qq.rq);
+    const uint32_t u = warp * SUBS + sub;
+    const bool has_unit = u < q.units;
+    const uint32_t strip = u % q.strips, span = (u / q.strips) % q.spans, img = u / (q.strips * q.spans);
+    const uint32_t srow = q.IWT * PIX;
+    const uint32_t unit_off = ((img * q.IHT + span * q.RS * S) * q.IWT + strip * TW * S) * PIX + cpl * 4;
+    const uint32_t cstride = p.CP, rstride = p.OW * p.CP;
+    uint32_t st = 0, ph = 0;
+    for (uint32_t sp = sp0; sp < q.spatial_tiles; sp += sp_step) {
+        const uint32_t tw = sp % q.tiles_w, r = sp / q.tiles_w;
+        const uint32_t th = r % q.tiles_h, n = (r / q.tiles_h) * q.NB + img;
+        mbar_wait(bar_full + 8 * st, ph);
+        const uint32_t oh0 = th * q.TH + span * q.RS;
+        uint32_t oh1 = oh0 + q.RS;
+        if (oh1 > (th + 1) * q.TH)
+            oh1 = (th + 1) * q.TH;
+        if (oh1 > p.OH)
+            oh1 = p.OH;
+        const uint32_t ow0 = tw * q.TWT + strip * TW;
+        if (has_unit && oh0 < oh1 && ow0 < p.OW && n < q.N) {
+            const uint8_t* a = dsm + 128 + st * q.stage_bytes + unit_off;
+            uint32_t cmask = 0;
+#pragma unroll
+            for (int t2 = 0; t2 < TW; ++t2)
+                cmask |= (ch_ok && ow0 + t2 < p.OW ? 1u : 0u) << t2;
+            uint32_t* drow = p.dst + n * p.dst_bwords + (static_cast<size_t>(oh0) * p.OW + ow0) * p.CP + c / 2;
+            const uint32_t* zrow = p.z + n * p.z_bwords + (static_cast<size_t>(oh0) * p.OW + ow0) * p.CP + c / 2;
+            uint32_t A[3][4], B[3][4];
+            // one staged row -> per-channel words A[k] = pixels 0..3, B[k] = pixels 2..5
+            auto lds_row = [&](uint32_t (&Ar)[4], uint32_t (&Br)[4]) {
+                uint32_t px[6];
+#pragma unroll
+                for (int j = 0; j < 6; ++j)
+                    px[j] = j < IN ? *reinterpret_cast<const uint32_t*>(a + j * PIX) : 0u;
+                a += srow;
+                const uint32_t l01 = __byte_perm(px[0], px[1], 0x5140), h01 = __byte_perm(px[0], px[1], 0x7362);
+                const uint32_t l23 = __byte_perm(px[2], px[3], 0x5140), h23 = __byte_perm(px[2], px[3], 0x7362);
+                const uint32_t l45 = __byte_perm(px[4], px[5], 0x5140), h45 = __byte_perm(px[4], px[5], 0x7362);
+                Ar[0] = __byte_perm(l01, l23, 0x5410), Ar[1] = __byte_perm(l01, l23, 0x7632);
+                Ar[2] = __byte_perm(h01, h23, 0x5410), Ar[3] = __byte_perm(h01, h23, 0x7632);
+                Br[0] = __byte_perm(l23, l45, 0x5410), Br[1] = __byte_perm(l23, l45, 0x7632);
+                Br[2] = __byte_perm(h23, h45, 0x5410), Br[3] = __byte_perm(h23, h45, 0x7632);
+            };
+            lds_row(A[0], B[0]);
+            if constexpr (S == 1)
+                lds_row(A[1], B[1]);
+#pragma unroll 1
+            for (uint32_t rows = oh1 - oh0; rows > 0; --rows) {
+                if constexpr (S == 2)
+                    lds_row(A[1], B[1]);
+                lds_row(A[2], B[2]);
+                uint32_t zw[TW];
+#pragma unroll
+                for (int t2 = 0; t2 < TW; ++t2)
+                    zw[t2] = (HAS_Z && ((cmask >> t2) & 1)) ? __ldg(zrow + t2 * cstride) : 0u;
+#pragma unroll
+                for (int t2 = 0; t2 < TW; ++t2) {
+                    int32_t acc[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        int32_t av = bias[k];
+#pragma unroll
+                        for (int rr = 0; rr < 3; ++rr) {
+                            uint32_t x, w;
+                            if (S == 1) {
+                                x = (t2 < 2) ? A[rr][k] : B[rr][k];
+                                w = (t2 & 1) ? (wa[k][rr] << 8) : wa[k][rr];
+                            } else {
+                                x = t2 == 0 ? A[rr][k] : B[rr][k];
+                                w = wa[k][rr];
+                            }
+                            av = __dp4a(static_cast<int32_t>(x), static_cast<int32_t>(w), av);
+                        }
+                        acc[k] = av;
+                    }
+                    const uint32_t zx = zw[t2] ^ 0x80808080u;
+                    uint32_t ub[4];
+#pragma unroll
+                    for (int b = 0; b < 4; b += 2) {
+                        const uint32_t z0 = __byte_perm(zx, 0x4B000000u, 0x7540u | b);
+                        const uint32_t z1 = __byte_perm(zx, 0x4B000000u, 0x7540u | (b + 1));
+                        if constexpr (MODE == 2)
+                            requant_pair_nonneg<HAS_Z>(acc[b], acc[b + 1], z0, z1, kp, ub[b], ub[b + 1]);
+                        else
+                            requant_pair_signed<HAS_Z>(acc[b], acc[b + 1], z0, z1, kp, ub[b], ub[b + 1]);
+                    }
+                    if ((cmask >> t2) & 1)
+                        drow[t2 * cstride] = pack_low_bytes(ub[0], ub[1], ub[2], ub[3]);
+                }
+                drow += rstride;
+                zrow += rstride;
+                if constexpr (S == 1) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        A[0][k] = A[1][k], B[0][k] = B[1][k];
+                        A[1][k] = A[2][k], B[1][k] = B[2][k];
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        A[0][k] = A[2][k], B[0][k] = B[2][k];
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0)
+            mbar_arrive(bar_empty + 8 * st);
+        if (++st == q.stages) {
+            st = 0;
+            ph ^= 1;
+        }
+    }
+}
+
+bool dw3_s8_applicable(const b200cb_desc& d) {
+    return d.src_dtype == B200CB_DT_QS8 && d.dst_dtype == B200CB_DT_QS8 && d.fh == 3 && d.fw == 3 &&
+           d.stride_h == d.stride_w && (d.stride_h == 1 || d.stride_h == 2) && d.dilate_h == 1 && d.dilate_w == 1 &&
+           d.ic % 4 == 0 && d.src_batch_stride % 4 == 0 && d.dst_batch_stride % 4 == 0 && d.z_batch_stride % 4 == 0;
+}
+
 // experiment knobs (tools/): integer environment override with a default
 int env_flag(const char* name, int dflt) {
 #ifdef B200CB_TOOLS  // the product library never reads the environment
@@ -974,6 +1398,18 @@ cudaError_t launch_pdl(Kern kern, uint32_t grid, uint32_t threads, uint32_t smem
     return cudaLaunchKernelEx(&cfg, kern, q);
 }
 
+// Float32 3x3: the same problem seen as 16-bit half-channels (ic = oc = 2 C; element strides double)
+bool dw3_f32(const b200cb_desc& d) {
+    return d.src_dtype == B200CB_DT_F32 && d.fh == 3 && d.fw == 3 && d.stride_h == d.stride_w &&
+           (d.stride_h == 1 || d.stride_h == 2) && d.dilate_h == 1 && d.dilate_w == 1;
+}
+b200cb_desc dw3_f32_view(const b200cb_desc& d) {
+    b200cb_desc v = d;
+    v.src_dtype = v.filter_dtype = v.dst_dtype = B200CB_DT_BF16;  // (16-bit element counting only)
+    v.ic = v.oc = v.group = 2 * d.ic;
+    v.src_batch_stride *= 2, v.dst_batch_stride *= 2, v.z_batch_stride *= 2;
+    return v;
+}
 bool dw3_applicable(const b200cb_desc& d) {
     return (d.src_dtype == B200CB_DT_BF16 || d.src_dtype == B200CB_DT_F16) && d.fh == 3 && d.fw == 3 &&
            d.stride_h == d.stride_w && (d.stride_h == 1 || d.stride_h == 2) && d.dilate_h == 1 &&
@@ -1100,9 +1536,34 @@ cudaError_t launch_dw3_tma_variant(const Dw3TmaParams& q, uint32_t grid, uint32_
     return launch_pdl(kern, grid, (DW3_COMPUTE_WARPS + 1) * 32, smem, stream, q);
 }
 
-// tile geometry + tensor map of the TMA front end
+template <int S, int MODE, bool HAS_Z, int CPB>
+cudaError_t launch_s8_tma_variant(const Dw3S8TmaParams& qq, uint32_t grid, uint32_t smem, cudaStream_t stream) {
+    auto kern = dw3x3_s8_tma_kernel<S, MODE, HAS_Z, CPB>;
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)MAX_DYN_SMEM);
+        if (e != cudaSuccess)
+            return e;
+        attr_set[dev] = true;
+    }
+    return launch_pdl(kern, grid, (DW3_COMPUTE_WARPS + 1) * 32, smem, stream, qq);
+}
+template <int S, int CPB>
+cudaError_t launch_s8_tma(const Dw3S8TmaParams& qq, int mode, bool has_z, uint32_t grid, uint32_t smem, cudaStream_t st) {
+    if (mode == 2)
+        return has_z ? launch_s8_tma_variant<S, 2, true, CPB>(qq, grid, smem, st)
+                     : launch_s8_tma_variant<S, 2, false, CPB>(qq, grid, smem, st);
+    return has_z ? launch_s8_tma_variant<S, 1, true, CPB>(qq, grid, smem, st)
+                 : launch_s8_tma_variant<S, 1, false, CPB>(qq, grid, smem, st);
+}
+
+// tile geometry + tensor map of the TMA front end (KIND == QuantizedS8: `d` is the 16-bit view of the int8
+// tensors, `rq8` / `mode8` select the int8 window kernel)
 template <int KIND>
-int launch_dw3_tma(const b200cb_desc& d, const Dw3Common& c, const void* src, cudaStream_t stream) {
+int launch_dw3_tma(const b200cb_desc& d, const Dw3Common& c, const void* src, cudaStream_t stream,
+                   const RequantParams* rq8 = nullptr, int mode8 = 0) {
     Dw3TmaParams q;
     memset(&q, 0, sizeof(q));
     q.c = c;
@@ -1171,7 +1632,7 @@ int launch_dw3_tma(const b200cb_desc& d, const Dw3Common& c, const void* src, cu
     uint64_t strides[3] = {(uint64_t)d.ic * 2, (uint64_t)d.iw * d.ic * 2, src_b * 2};
     uint32_t box[4] = {CB, q.IWT, q.IHT, q.NB};
     CUresult cr = encode_tiled(
-            &q.tmS, KIND == B200CB_DT_BF16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 4,
+            &q.tmS, KIND == B200CB_DT_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4,
             src, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     if (cr != CUDA_SUCCESS) {
         char buf[64];
@@ -1189,7 +1650,17 @@ int launch_dw3_tma(const b200cb_desc& d, const Dw3Common& c, const void* src, cu
     const uint32_t grid = (uint32_t)per * q.cblks;
     const uint32_t smem = 128 + q.stages * q.stage_bytes;
     cudaError_t e;
-    if (S == 1)
+    if constexpr (KIND == B200CB_DT_QS8) {
+        Dw3S8TmaParams qq;
+        qq.t = q;
+        qq.rq = *rq8;
+        if (S == 1)
+            e = CPB == 32 ? launch_s8_tma<1, 32>(qq, mode8, c.has_z != 0, grid, smem, stream)
+                          : launch_s8_tma<1, 16>(qq, mode8, c.has_z != 0, grid, smem, stream);
+        else
+            e = CPB == 32 ? launch_s8_tma<2, 32>(qq, mode8, c.has_z != 0, grid, smem, stream)
+                          : launch_s8_tma<2, 16>(qq, mode8, c.has_z != 0, grid, smem, stream);
+    } else if (S == 1)
         e = CPB == 32 ? launch_dw3_tma_variant<KIND, 1, 4, 32>(q, grid, smem, stream)
                       : launch_dw3_tma_variant<KIND, 1, 4, 16>(q, grid, smem, stream);
     else
@@ -1265,8 +1736,9 @@ int dwconv_query(const b200cb_desc& d, b200cb_plan* plan) {
         return B200CB_UNSUPPORTED_PARAM;
     const uint32_t vec = dw_vec(dt);
     const uint32_t es = dtype_size(dt);
-    // the 3x3 16-bit bandwidth kernel works on channel pairs; everything else on 16-byte vectors
-    if (!dw3_applicable(d)) {
+    // the 3x3 bandwidth kernels work on 32-bit words (16-bit channel pairs / one fp32 channel); everything
+    // else on 16-byte vectors
+    if (!dw3_applicable(d) && !dw3_f32(d) && !dw3_s8_applicable(d)) {
         if (d.ic % vec != 0)
             return B200CB_UNSUPPORTED_ALIGNMENT;
         if ((d.src_batch_stride * es) % 16 || (d.dst_batch_stride * es) % 16 || (d.z_batch_stride * es) % 16)
@@ -1300,7 +1772,9 @@ int dwconv_query(const b200cb_desc& d, b200cb_plan* plan) {
 int dwconv_launch(
         const b200cb_plan& plan, const void* src, const void* filter, const void* bias,
         const void* z, void* dst, cudaStream_t stream) {
-    const b200cb_desc& d = plan.desc;
+    const bool f32_dw3 = dw3_f32(plan.desc);
+    // (Float32 3x3: the half-channel view of the same tensors, see dw3_f32_view)
+    const b200cb_desc d = f32_dw3 ? dw3_f32_view(plan.desc) : plan.desc;
     if (!src || !filter || !dst || (d.bias_mode != B200CB_BIAS_NONE && !bias) || (d.has_z && !z))
         return B200CB_ERR_NULL;
     if (dw3_applicable(d)) {
@@ -1317,14 +1791,16 @@ int dwconv_launch(
         c.has_z = d.has_z;
         c.nonline = d.nonline_mode;
         if (dw3_tma_applicable(d) && plan.reserved[2] != 2) {  // reserved[2] == 2: force the register front end
-            int rc = d.src_dtype == B200CB_DT_BF16 ? launch_dw3_tma<B200CB_DT_BF16>(d, c, src, stream)
-                                                   : launch_dw3_tma<B200CB_DT_F16>(d, c, src, stream);
+            int rc = f32_dw3                          ? launch_dw3_tma<B200CB_DT_F32>(d, c, src, stream)
+                     : d.src_dtype == B200CB_DT_BF16 ? launch_dw3_tma<B200CB_DT_BF16>(d, c, src, stream)
+                                                     : launch_dw3_tma<B200CB_DT_F16>(d, c, src, stream);
             if (rc != B200CB_UNSUPPORTED_SHAPE)
                 return rc;
         }
         if (dw3_bulk_applicable(d) && plan.reserved[2] != 2 && env_flag("B200CB_DW_BULK", 1)) {
-            int rc = d.src_dtype == B200CB_DT_BF16 ? launch_dw3_bulk<B200CB_DT_BF16>(d, c, src, stream)
-                                                   : launch_dw3_bulk<B200CB_DT_F16>(d, c, src, stream);
+            int rc = f32_dw3                          ? launch_dw3_bulk<B200CB_DT_F32>(d, c, src, stream)
+                     : d.src_dtype == B200CB_DT_BF16 ? launch_dw3_bulk<B200CB_DT_BF16>(d, c, src, stream)
+                                                     : launch_dw3_bulk<B200CB_DT_F16>(d, c, src, stream);
             if (rc != B200CB_UNSUPPORTED_SHAPE)
                 return rc;
         }
@@ -1333,13 +1809,93 @@ int dwconv_launch(
         q.c = c;
         q.src = static_cast<const uint32_t*>(src);
         q.src_bwords = (d.src_batch_stride ? d.src_batch_stride : (uint64_t)d.ih * d.iw * d.ic) / 2;
-        cudaError_t e3 = d.src_dtype == B200CB_DT_BF16 ? launch_dw3<B200CB_DT_BF16>(d, q, stream)
-                                                      : launch_dw3<B200CB_DT_F16>(d, q, stream);
+        cudaError_t e3 = f32_dw3                          ? launch_dw3<B200CB_DT_F32>(d, q, stream)
+                         : d.src_dtype == B200CB_DT_BF16 ? launch_dw3<B200CB_DT_BF16>(d, q, stream)
+                                                         : launch_dw3<B200CB_DT_F16>(d, q, stream);
         if (e3 != cudaSuccess) {
             set_last_error("dw3x3 launch", cudaGetErrorString(e3));
             return B200CB_ERR_CUDA;
         }
         return B200CB_OK;
+    }
+    if (dw3_s8_applicable(d) && plan.reserved[2] != 2 && d.ic % 16 == 0) {
+        // TMA-staged window kernel: the int8 tensors as C / 2 16-bit channels (fast IDENTITY / RELU only)
+        const RequantParams rq = make_requant(d);
+        const bool fast = rq.fast_div == 2 && (d.nonline_mode == B200CB_NL_RELU || d.nonline_mode == B200CB_NL_IDENTITY);
+        b200cb_desc v = d;
+        v.src_dtype = v.filter_dtype = v.dst_dtype = B200CB_DT_BF16;  // (16-bit element counting only)
+        v.ic = v.oc = v.group = d.ic / 2;
+        v.src_batch_stride /= 2, v.dst_batch_stride /= 2, v.z_batch_stride /= 2;
+        if (fast && dw3_tma_applicable(v) && d.src_batch_stride % 2 == 0 && d.dst_batch_stride % 4 == 0 &&
+            d.z_batch_stride % 4 == 0) {
+            Dw3Common c;
+            memset(&c, 0, sizeof(c));
+            c.filter = filter, c.bias = bias;
+            c.z = static_cast<const uint32_t*>(z), c.dst = static_cast<uint32_t*>(dst);
+            c.N = d.n, c.C = v.ic, c.IH = d.ih, c.IW = d.iw, c.OH = d.oh, c.OW = d.ow, c.CP = d.ic / 4;
+            c.pad_h = d.pad_h, c.pad_w = d.pad_w;
+            c.dst_bwords = (d.dst_batch_stride ? d.dst_batch_stride : (uint64_t)d.oh * d.ow * d.oc) / 4;
+            c.z_bwords = (d.z_batch_stride ? d.z_batch_stride : (uint64_t)d.oh * d.ow * d.oc) / 4;
+            c.flip = d.mode == B200CB_MODE_CONVOLUTION;
+            c.has_bias = d.bias_mode != B200CB_BIAS_NONE, c.has_z = d.has_z, c.nonline = d.nonline_mode;
+            const int rc = launch_dw3_tma<B200CB_DT_QS8>(v, c, src, stream, &rq, d.nonline_mode == B200CB_NL_RELU ? 2 : 1);
+            if (rc != B200CB_UNSUPPORTED_SHAPE)
+                return rc;
+        }
+    }
+    if (dw3_s8_applicable(d) && plan.reserved[2] != 2) {
+        DwS8Params q;
+        memset(&q, 0, sizeof(q));
+        q.src = static_cast<const uint32_t*>(src), q.filter = static_cast<const int8_t*>(filter);
+        q.bias = static_cast<const int32_t*>(bias), q.z = static_cast<const uint32_t*>(z);
+        q.dst = static_cast<uint32_t*>(dst);
+        q.N = d.n, q.C = d.ic, q.IH = d.ih, q.IW = d.iw, q.OH = d.oh, q.OW = d.ow, q.CW = d.ic / 4;
+        q.pad_h = d.pad_h, q.pad_w = d.pad_w;
+        q.src_bwords = (d.src_batch_stride ? d.src_batch_stride : (uint64_t)d.ih * d.iw * d.ic) / 4;
+        q.dst_bwords = (d.dst_batch_stride ? d.dst_batch_stride : (uint64_t)d.oh * d.ow * d.oc) / 4;
+        q.z_bwords = (d.z_batch_stride ? d.z_batch_stride : (uint64_t)d.oh * d.ow * d.oc) / 4;
+        q.flip = d.mode == B200CB_MODE_CONVOLUTION;
+        q.has_bias = d.bias_mode != B200CB_BIAS_NONE, q.has_z = d.has_z, q.nonline = d.nonline_mode;
+        q.rq = make_requant(d);
+        const uint32_t tw = d.stride_h == 1 ? 4 : 2;
+        q.strips = (d.ow + tw - 1) / tw;
+        // vertical span: long enough to amortise the halo rows, short enough to fill the machine
+        uint32_t rh = 16;
+        auto items = [&](uint32_t r) { return (uint64_t)q.CW * q.strips * ((d.oh + r - 1) / r) * d.n; };
+        while (rh > 2 && items(rh) < 148ull * 4096)
+            rh /= 2;
+        q.RH = rh;
+        q.spans = (d.oh + rh - 1) / rh;
+        q.total_items = items(rh);
+        const uint64_t blocks = (q.total_items + 255) / 256;
+        if (blocks <= 0x7fffffffull) {
+            const bool fast = q.rq.fast_div == 2 && (d.nonline_mode == B200CB_NL_RELU || d.nonline_mode == B200CB_NL_IDENTITY);
+            const int mode = !fast ? 0 : (d.nonline_mode == B200CB_NL_RELU ? 2 : 1);
+            cudaError_t e8 = cudaErrorInvalidValue;
+#define B200CB_DW8(S_, M_, Z_) e8 = launch_pdl(dw3x3_s8_kernel<S_, M_, Z_>, (uint32_t)blocks, 256, 0, stream, q)
+#define B200CB_DW8_S(S_)                                              \
+    if (d.has_z) {                                                     \
+        if (mode == 2) B200CB_DW8(S_, 2, true);                        \
+        else if (mode == 1) B200CB_DW8(S_, 1, true);                   \
+        else B200CB_DW8(S_, 0, true);                                  \
+    } else {                                                           \
+        if (mode == 2) B200CB_DW8(S_, 2, false);                       \
+        else if (mode == 1) B200CB_DW8(S_, 1, false);                  \
+        else B200CB_DW8(S_, 0, false);                                 \
+    }
+            if (d.stride_h == 1) {
+                B200CB_DW8_S(1)
+            } else {
+                B200CB_DW8_S(2)
+            }
+#undef B200CB_DW8_S
+#undef B200CB_DW8
+            if (e8 != cudaSuccess) {
+                set_last_error("dw3x3 s8 launch", cudaGetErrorString(e8));
+                return B200CB_ERR_CUDA;
+            }
+            return B200CB_OK;
+        }
     }
     const bool spec = dw_specialised(d);
     const uint32_t vec = dw_vec(d.src_dtype);

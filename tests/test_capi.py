@@ -90,7 +90,8 @@ def test_query_shufflenet_depthwise_channel_counts(lib):
             assert p.workspace_bytes == 0 and lib.b200cb_plan_num_launches(ctypes.byref(p)) == 1
             assert p.bytes == 2 * 256 * c * (h * w + (h // s) * (w // s)) + 2 * c * 9 + 2 * c
     assert _query(lib, K.dw_desc("qs8", 256, 58, 28, 28, 1))[0] > 0
-    assert _query(lib, K.dw_desc("f32", 256, 58, 28, 28, 1))[0] > 0
+    assert _query(lib, K.dw_desc("f32", 256, 58, 28, 28, 1))[0] == 0   # fp32 3x3: one channel per 32-bit word
+    assert _query(lib, K.dw_desc("f32", 256, 58, 28, 28, 1, f=5))[0] > 0  # other filters: 16-byte vectors
     assert _query(lib, K.dw_desc("bf16", 256, 57, 28, 28, 1))[0] > 0   # odd channel count: no channel pairs
 
 

@@ -583,3 +583,50 @@ def test_resnet18_fp32_nchw_on_the_gpu_path(layer):
     if layer[0] == "conv1":
         d = K.make_desc("f32", 2, 3, 96, 96, 64, 7, stride=2, pad=3, fmt=C.FORMAT_NCHW, nonline=C.NL_RELU)
     _check(d, seed=111)
+
+
+F32_DW_CASES = [
+    # name, n, c, h, w, stride, pad, nonline, has_z       (3x3: the TMA / bulk-row / global bandwidth kernels)
+    ("c32_s1_tma", 3, 32, 14, 14, 1, 1, C.NL_RELU, False),
+    ("c96_s2_tma_z", 2, 96, 28, 28, 2, 1, C.NL_RELU, True),
+    ("c144_s1_56", 2, 144, 56, 56, 1, 1, C.NL_IDENTITY, False),
+    ("c58_s1_bulk", 3, 58, 9, 8, 1, 1, C.NL_RELU, False),
+    ("c36_s2_nopad_z", 2, 36, 11, 16, 2, 0, C.NL_H_SWISH, True),
+    ("c960_7x7_multi_image", 5, 960, 7, 7, 1, 1, C.NL_RELU, False),
+    ("c6_tiny", 2, 6, 5, 5, 1, 1, C.NL_RELU, True),
+]
+
+
+@pytest.mark.parametrize("case", F32_DW_CASES, ids=[c[0] for c in F32_DW_CASES])
+def test_float32_depthwise_3x3_bandwidth_kernels(case):
+    """Float32 depthwise 3x3 on the bandwidth kernels of the 16-bit kinds (one fp32 channel = one 32-bit word):
+    fp32 arithmetic in a different summation order than the oracle, eps 1e-3 (dnn/test/cuda/conv_bias.cpp:650-714)."""
+    _n, n, c, h, w, s, pd, nl, has_z = case
+    d = K.make_desc("f32", n, c, h, w, c, 3, stride=s, pad=pd, group=c, nonline=nl, has_z=has_z)
+    _plan, info = _check(d, seed=121 + c)
+    assert info["max_rel"] < 1e-5, info
+
+
+S8_DW_CASES = [
+    # name, n, c, h, w, stride, pad, nonline, has_z, mode      (3x3 QuantizedS8: the DP4A window kernel)
+    ("c32_s1_relu", 3, 32, 14, 14, 1, 1, C.NL_RELU, False, 0),
+    ("c96_s2_relu_z", 2, 96, 28, 28, 2, 1, C.NL_RELU, True, 0),
+    ("c144_s1_identity_z", 2, 144, 56, 56, 1, 1, C.NL_IDENTITY, True, 0),
+    ("c24_s2_word_channels", 3, 24, 17, 19, 2, 1, C.NL_RELU, False, 0),
+    ("c116_s1_hswish", 2, 116, 14, 14, 1, 1, C.NL_H_SWISH, True, 0),
+    ("c36_s2_nopad", 2, 36, 11, 16, 2, 0, C.NL_RELU, True, 0),
+    ("c960_7x7", 5, 960, 7, 7, 1, 1, C.NL_RELU, False, 0),
+    ("c64_s1_flipped", 2, 64, 9, 13, 1, 1, C.NL_IDENTITY, False, 1),
+    ("c8_w3_narrow", 2, 8, 6, 3, 1, 1, C.NL_RELU, True, 0),
+]
+
+
+@pytest.mark.parametrize("case", S8_DW_CASES, ids=[c[0] for c in S8_DW_CASES])
+def test_int8_depthwise_3x3_window_kernel(case):
+    """QuantizedS8 depthwise 3x3 (C % 4 == 0) on the DP4A window kernel: 0 mismatching bytes, saturation,
+    z, every activation, mode CONVOLUTION (flipped filter)."""
+    _n, n, c, h, w, s, pd, nl, has_z, mode = case
+    d = K.make_desc("qs8", n, c, h, w, c, 3, stride=s, pad=pd, group=c, nonline=nl, has_z=has_z, mode=mode,
+                    scales=(0.37, 0.71, None, 1.9, 23.0))
+    _plan, info = _check(d, {"int_range": 127, "bias_range": 5000}, seed=131 + c)
+    assert info["mismatch"] == 0
