@@ -72,7 +72,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+// B200CB_WAIT_HINT_NS (experiment, tools builds): suspend-time hint of the potentially blocking try_wait --
+// a waiting warp then re-issues the poll less often and leaves the issue slots to the working warps
+#ifndef B200CB_WAIT_HINT_NS
+#define B200CB_WAIT_HINT_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#if B200CB_WAIT_HINT_NS > 0
+    asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+            "@P1 bra DONE;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity), "r"(static_cast<uint32_t>(B200CB_WAIT_HINT_NS))
+            : "memory");
+#else
     asm volatile(
             "{\n"
             ".reg .pred P1;\n"
@@ -84,6 +102,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
             "}\n" ::"r"(bar),
             "r"(parity)
             : "memory");
+#endif
 }
 
 // ---------------------------------------------------------------- proxies / fences
