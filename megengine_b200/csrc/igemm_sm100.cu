@@ -338,7 +338,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 
     const bool stem = p.a_mode == 2;
     const bool rows = p.a_mode == 3;
-    const uint32_t plane_bytes = rows ? p.rows_rh * p.PW * 128u   // rows: one 64-channel block of the slab
+    const uint32_t plane_bytes = rows ? p.rows_rh * p.PW * p.kb_bytes   // rows: one channel block (128 / 64 B) of the slab
                                       : p.stem_fh * p.stem_nj * 16; // stem: one pixel parity, all filter rows
     const uint32_t a_bytes = stem ? (p.stem4 ? plane_bytes : 2 * plane_bytes)
                              : rows ? p.num_kc * plane_bytes
@@ -348,7 +348,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     constexpr bool pair = PAIR != 0;
     const uint32_t b_rows = pair ? BN / 2 : BN;
     const uint32_t stage_bytes = (stem || rows) ? a_bytes : a_bytes + b_rows * p.kb_bytes;
-    const uint32_t bres_bytes = stem ? p.stem_fh * BN * stem_rb : rows ? p.num_taps * p.num_kc * BN * 128u : 0u;
+    const uint32_t bres_bytes = stem ? p.stem_fh * BN * stem_rb : rows ? p.num_taps * p.num_kc * BN * p.kb_bytes : 0u;
     const uint32_t sZ = smem_base + OFF_SZ;
     constexpr uint32_t NSLAB = T::nslab(BN);
     const uint32_t nz = p.nz;
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             for (uint32_t tap = 0; tap < p.num_taps; ++tap)
                 for (uint32_t kc = 0; kc < p.num_kc; ++kc)
                     tma_load_3d(
-                            sBres + (tap * p.num_kc + kc) * BN * 128u, &p.tmB, bar_bres,
+                            sBres + (tap * p.num_kc + kc) * BN * p.kb_bytes, &p.tmB, bar_bres,
                             static_cast<int32_t>(kc * p.kb_elems), static_cast<int32_t>(tap), 0);
         }
         uint32_t stage = 0, phase = 0;
@@ -665,21 +665,24 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     } else if (warp == 1 && rows) {
         // ============================ MMA issuer, rows mode ============================
         // tap (fh, fw) of output m' reads slab entry m' - r0*PW + fh*PW + fw: a pure row shift of the
-        // A descriptor (128-byte rows, SWIZZLE_128B keyed on absolute smem address bits).  The slab row
-        // a tap starts on is usually not a multiple of 8: the swizzle is keyed on absolute address bits
-        // (as TMA wrote it), so a plain row-shifted start address is correct (base-offset field 0;
-        // verified on B200 against the oracle).  One thread issues; the four MMAs of a (tap, channel
-        // block) are unrolled with immediate offsets and a constant accumulate predicate.
+        // A descriptor (RB-byte rows, RB = 128 / 64 with SWIZZLE_128B / 64B keyed on absolute smem address
+        // bits).  The slab row a tap starts on is usually not a multiple of 8: the swizzle is keyed on
+        // absolute address bits (as TMA wrote it), so a plain row-shifted start address is correct
+        // (base-offset field 0; verified on B200 against the oracle).  One thread issues; the RB / 32 MMAs
+        // of a (tap, channel block) are unrolled with immediate offsets and a constant accumulate predicate.
         if (elect_one()) {
+            auto run = [&](auto NM_) {
+            constexpr uint32_t NM = decltype(NM_)::value;   // MMAs (32 bytes of K) per (tap, channel block)
+            constexpr uint32_t RB = NM * 32;                // bytes per slab / filter row
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
-            const uint32_t ab_hi = desc_hi(1024, 2);
-            const uint32_t plane16 = plane_bytes >> 4, stage16 = stage_bytes >> 4, brow = BN * 128u / 16u;
+            const uint32_t ab_hi = desc_hi(8 * RB, NM == 4 ? 2u : 4u);
+            const uint32_t plane16 = plane_bytes >> 4, stage16 = stage_bytes >> 4, brow = BN * RB / 16u;
             const uint32_t a0 = desc_lo(sStage, 16), b0 = desc_lo(sBres, 16);
-            const uint32_t FH = p.num_taps / p.FW, roww = p.PW * 8;
+            const uint32_t FH = p.num_taps / p.FW, roww = p.PW * (RB / 16);
             uint32_t soff = 0;
             auto mma4 = [&](uint32_t taddr, uint32_t a_lo, uint32_t b_lo) {
 #pragma unroll
-                for (uint32_t k = 0; k < 4; ++k) {
+                for (uint32_t k = 0; k < NM; ++k) {
                     const uint64_t adesc = (static_cast<uint64_t>(ab_hi) << 32) | (a_lo + 2 * k);
                     const uint64_t bdesc = (static_cast<uint64_t>(ab_hi) << 32) | (b_lo + 2 * k);
                     if constexpr (KIND == KIND_S8)
@@ -696,12 +699,12 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 TIMED_WAIT(2, bar_full + 8 * stage, phase);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * BN;
-                uint32_t row_lo = a0 + soff + off0 * 8;  // tap (fh, 0); 128-byte rows = 8 units
+                uint32_t row_lo = a0 + soff + off0 * (RB / 16);  // tap (fh, 0); RB-byte rows = RB / 16 units
                 uint32_t b_lo = b0;
                 // the very first MMA of the tile overwrites the accumulator
                 mma_issue<KIND>(taddr, row_lo, ab_hi, b_lo, ab_hi, IDESC, 0);
 #pragma unroll
-                for (uint32_t k = 1; k < 4; ++k)
+                for (uint32_t k = 1; k < NM; ++k)
                     mma_issue<KIND>(taddr, row_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC, 1);
                 bool skip = true;  // (fh, fw, kc) == (0, 0, 0) is done
                 for (uint32_t fh = 0; fh < FH; ++fh) {
@@ -715,7 +718,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                             a_lo += plane16;
                             b_lo += brow;
                         }
-                        tap_lo += 8;  // next pixel: 128 bytes
+                        tap_lo += RB / 16;  // next pixel
                     }
                     row_lo += roww;  // next input row
                 }
@@ -732,6 +735,11 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                     acc_phase ^= 1;
                 }
             }
+            };
+            if (p.kb_bytes == 128)
+                run(std::integral_constant<uint32_t, 4>{});
+            else
+                run(std::integral_constant<uint32_t, 2>{});
         }
         __syncwarp();
     } else if (warp == 0) {
@@ -1775,7 +1783,9 @@ RowsGeom rows_geometry(const b200cb_desc& d, uint32_t in_es, uint32_t block_n) {
         return r;
     if (d.fh * d.fw == 1 || d.mode != B200CB_MODE_CROSS_CORRELATION || d.has_z)
         return r;
-    if ((d.ic * in_es) % 128 != 0 || d.oc > block_n)
+    // channel rows of 128 bytes (SWIZZLE_128B), or of 64 bytes (SWIZZLE_64B: QuantizedS8 IC = 64, ResNet l1 3x3)
+    const uint32_t rb = (d.ic * in_es) % 128 == 0 ? 128u : 64u;
+    if ((rb == 64 && d.ic * in_es != 64) || d.oc > block_n)
         return r;
     r.pw = d.iw + 2 * d.pad_w;
     if (r.pw != d.ow + d.fw - 1 || r.pw > 256)
@@ -1783,10 +1793,10 @@ RowsGeom rows_geometry(const b200cb_desc& d, uint32_t in_es, uint32_t block_n) {
     r.rh = (r.pw - 1 + (d.fh - 1) * r.pw + d.fw - 1 + 127) / r.pw + 1;
     if (r.rh > 256)
         return r;
-    r.num_kc = d.ic * in_es / 128;
+    r.num_kc = d.ic * in_es / rb;
     r.tiles_per_img = (d.oh * r.pw + IGEMM_BLOCK_M - 1) / IGEMM_BLOCK_M;
-    r.a_stage = r.num_kc * r.rh * r.pw * 128;
-    r.bres = d.fh * d.fw * r.num_kc * block_n * 128;
+    r.a_stage = r.num_kc * r.rh * r.pw * rb;
+    r.bres = d.fh * d.fw * r.num_kc * block_n * rb;
     r.ok = true;
     return r;
 }
@@ -2115,6 +2125,11 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     }
 
 #ifdef B200CB_TOOLS
+    if (const char* s2 = getenv("B200CB_STAGES"))  // pipeline-depth sensitivity (generic modes)
+        if (!getenv("B200CB_NZ") && !stem && !rows && (uint32_t)atoi(s2) >= 2 && (uint32_t)atoi(s2) < stages) {
+            smem_total -= (stages - (uint32_t)atoi(s2)) * stage_b;
+            stages = (uint32_t)atoi(s2);
+        }
     if (const char* e = getenv("B200CB_NZ")) {  // force the z ring depth (stages shrink to fit)
         if (d.has_z && !nchw4 && !stem && !rows) {
             const uint32_t zbuf = 128 * ((out32 || in_es == 2) ? 128 : 64);
@@ -2338,7 +2353,7 @@ int launch_dense(
                 (uint64_t)d.ic * in_es, (uint64_t)d.iw * d.ic * in_es, src_bstride * in_es};
         uint32_t box[4] = {kb_elems, rg.pw, rg.rh, 1};
         cr = encode_tiled(
-                &p.tmA, in_dt, 4, src, dims, strides, box, nullptr, CU_TENSOR_MAP_SWIZZLE_128B,
+                &p.tmA, in_dt, 4, src, dims, strides, box, nullptr, in_swz,
                 CU_TENSOR_MAP_L2_PROMOTION_L2_128B);
     } else if (stem && (plan.reserved[4] & 2)) {
         // row ring: rows as contiguous runs of 8-byte elements (a pixel of IC * es == 8 bytes), boxes of one

@@ -76,6 +76,8 @@ def stage_cases(stage):
                 ("rows_c3_bf16_padh0", md("bf16", 2, 64, 12, 17, 64, 3, pad=0, pad_w=1), {}),
                 ("rows_c1x3_bf16", md("bf16", 2, 64, 9, 30, 64, 1, fw=3, pad=0, pad_w=1, nonline=1), {}),
                 ("rows_c3_bf16_ic128_oc16", md("bf16", 1, 128, 10, 10, 16, 3, pad=1), {}),
+                ("rows64_c3_bf16_ic32", md("bf16", 2, 32, 28, 28, 64, 3, pad=1, nonline=1), {}),
+                ("rows64_c3_f16_ic32_oc48", md("f16", 3, 32, 9, 11, 48, 3, pad=1, nonline=3), {}),
                 ("nofold_c3_bf16_ic8_oddw", md("bf16", 2, 8, 17, 17, 64, 3, stride=2, pad=1), {})]
     if stage == "int8":
         sc = (1.2, 1.3, None, 0.7, 19.99)
@@ -98,7 +100,14 @@ def stage_cases(stage):
                 ("q_c3_ic64_sw64_oc512", md("qs8", 2, 64, 14, 14, 512, 3, pad=1, nonline=3, has_z=True,
                                             scales=(0.11, 0.23, None, 0.37, 0.41)), {"int_range": 127}),
                 ("q_pw_oc192_tail", md("qs8", 3, 128, 7, 7, 192, 1, nonline=1, has_z=True, scales=sc), {"algo": 1}),
-                ("q_denormal_dst_scale", md("qs8", 1, 64, 7, 7, 64, 1, scales=(0.1, 0.2, None, 0.3, 1e-39)), {})]
+                ("q_denormal_dst_scale", md("qs8", 1, 64, 7, 7, 64, 1, scales=(0.1, 0.2, None, 0.3, 1e-39)), {}),
+                # rows mode with 64-byte channel rows (SWIZZLE_64B slabs): QuantizedS8 IC = 64 (ResNet-50 l1 3x3)
+                ("q_rows64_c3_56", md("qs8", 2, 64, 56, 56, 64, 3, pad=1, nonline=1, scales=sc), {"int_range": 127}),
+                ("q_rows64_c3_7x7_n3_hswish", md("qs8", 3, 64, 7, 7, 64, 3, pad=1, nonline=3,
+                                                 scales=(0.11, 0.23, None, 0.37, 0.41)), {"int_range": 127}),
+                ("q_rows64_c5_oc32", md("qs8", 2, 64, 20, 13, 32, 5, pad=2, nonline=0, scales=sc), {}),
+                ("q_rows64_c1x3_padw", md("qs8", 2, 64, 9, 30, 64, 1, fw=3, pad=0, pad_w=1, nonline=1, scales=sc), {}),
+                ("q_rows128_c3_ic128", md("qs8", 2, 128, 12, 17, 64, 3, pad=1, nonline=1, scales=sc), {"int_range": 127})]
     if stage == "dw":
         out = []
         for kind in ("bf16", "f16", "f32", "qs8"):
