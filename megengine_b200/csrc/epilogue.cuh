@@ -145,9 +145,17 @@ __device__ __forceinline__ f32x2_t f2_add_rm(f32x2_t a, f32x2_t b) {
 }
 // loop-invariant operands of the packed requantize
 struct RequantPacked {
-    f32x2_t s_bias, inv, neg_s, half, magic;
+    f32x2_t s_bias, inv, neg_s, half, magic, neg_i2f;
     float s_bias1, s_z1;
 };
+// int32 -> float without the conversion pipe (I2F issues 16 lanes / clk / SM and was the busiest pipe of the
+// int8 epilogue): for v in [-2^22, 2^22) the integer add 0x4B400000 + v yields the bits of the float
+// 2^23 + 2^22 + v, and one exact FADD of -(2^23 + 2^22) leaves float(v).  The callers fold the constant into
+// the bias they add anyway (`MAGIC` forms below) after proving the range: |acc| <= K * 2^14 from the
+// descriptor, |bias| from the data (igemm: per bias slice; depthwise: per thread).
+constexpr uint32_t I2F_MAGIC_BITS = 0x4B400000u;
+constexpr float I2F_MAGIC = 12582912.f;
+constexpr uint32_t I2F_RANGE = 1u << 22;
 // A product that feeds an add must stay a separately rounded product -- and ptxas (12.9) contracts
 // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2 although the explicit .rn forbids that for the scalar
 // forms; --fmad=false does not stop it, and fma(a, b, -0.0) is simplified back and fused as well
@@ -163,22 +171,31 @@ __device__ __forceinline__ RequantPacked make_requant_packed(const RequantParams
     r.neg_s = f2_pack(-q.s_dst, -q.s_dst);
     r.half = f2_pack(0.5f, 0.5f);
     r.magic = f2_pack(8388608.f, 8388608.f);
+    r.neg_i2f = f2_pack(-I2F_MAGIC, -I2F_MAGIC);
     return r;
 }
 // two RELU outputs at once: (acc + bias) pairs -> the two result bytes in the low bytes of lo / hi.
 // Same operation sequence as dequant + fmaxf + div_by_scale_noguard + round_sat_s8_nonneg.
-template <bool HAS_Z>
+// MAGIC: sfb0 / sfb1 already carry I2F_MAGIC_BITS (acc + bias + magic, range proven by the caller)
+template <bool HAS_Z, bool MAGIC = false>
 __device__ __forceinline__ void requant_pair_nonneg(
         int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
         uint32_t& hi) {
     f32x2_t x;
+    f32x2_t a;
+    if constexpr (MAGIC)
+        a = f2_add(f2_pack(__int_as_float(sfb0), __int_as_float(sfb1)), k.neg_i2f);   // exact
+    else
+        a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
     if constexpr (HAS_Z) {
+        float a0, a1;
+        f2_unpack(a, a0, a1);
         const float z0 = __fadd_rn(__uint_as_float(zbits0), -8388736.f);
         const float z1 = __fadd_rn(__uint_as_float(zbits1), -8388736.f);
-        x = f2_pack(__fadd_rn(__fmul_rn(__int2float_rn(sfb0), k.s_bias1), __fmul_rn(z0, k.s_z1)),
-                    __fadd_rn(__fmul_rn(__int2float_rn(sfb1), k.s_bias1), __fmul_rn(z1, k.s_z1)));
+        x = f2_pack(__fadd_rn(__fmul_rn(a0, k.s_bias1), __fmul_rn(z0, k.s_z1)),
+                    __fadd_rn(__fmul_rn(a1, k.s_bias1), __fmul_rn(z1, k.s_z1)));
     } else {
-        x = f2_mul(f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1)), k.s_bias);
+        x = f2_mul(a, k.s_bias);
     }
     float x0, x1;
     f2_unpack(x, x0, x1);
@@ -196,18 +213,25 @@ __device__ __forceinline__ void requant_pair_nonneg(
 }
 
 // the IDENTITY (any sign) form of the same: clamp to [-128, 127], round the magnitude, negate the byte
-template <bool HAS_Z>
+template <bool HAS_Z, bool MAGIC = false>
 __device__ __forceinline__ void requant_pair_signed(
         int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
         uint32_t& hi) {
     f32x2_t x;
+    f32x2_t a;
+    if constexpr (MAGIC)
+        a = f2_add(f2_pack(__int_as_float(sfb0), __int_as_float(sfb1)), k.neg_i2f);   // exact
+    else
+        a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
     if constexpr (HAS_Z) {
+        float a0, a1;
+        f2_unpack(a, a0, a1);
         const float z0 = __fadd_rn(__uint_as_float(zbits0), -8388736.f);
         const float z1 = __fadd_rn(__uint_as_float(zbits1), -8388736.f);
-        x = f2_pack(__fadd_rn(__fmul_rn(__int2float_rn(sfb0), k.s_bias1), __fmul_rn(z0, k.s_z1)),
-                    __fadd_rn(__fmul_rn(__int2float_rn(sfb1), k.s_bias1), __fmul_rn(z1, k.s_z1)));
+        x = f2_pack(__fadd_rn(__fmul_rn(a0, k.s_bias1), __fmul_rn(z0, k.s_z1)),
+                    __fadd_rn(__fmul_rn(a1, k.s_bias1), __fmul_rn(z1, k.s_z1)));
     } else {
-        x = f2_mul(f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1)), k.s_bias);
+        x = f2_mul(a, k.s_bias);
     }
     const f32x2_t q0 = f2_mul(x, k.inv);
     const f32x2_t e = f2_fma(q0, k.neg_s, x);

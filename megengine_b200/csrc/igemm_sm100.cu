@@ -88,6 +88,7 @@ struct IgemmParams {
     // (QuantizedS8 inputs) or the fp32 accumulator (bf16 inputs) + fp32 bias [+ fp32 z], activation
     uint32_t out_f32;
     float acc_scale;
+    uint32_t acc_bound;  // QuantizedS8: K * 2^14 >= |accumulator| (saturated), for the conversion-free int -> float path
     const void* z;
     RequantParams rq;
     long long* dbg;   // -DB200CB_DEBUG_TIMING builds only: 148 x 3 roles x 17 counters
@@ -197,7 +198,9 @@ __host__ __device__ constexpr uint32_t off_sd(uint32_t /*groups*/, uint32_t /*bn
 // QuantizedS8 fast epilogue for one thread's 32 accumulator columns (IDENTITY / RELU, fast_div == 2):
 // bias add, dequantize, optional z, activation, correctly rounded division, round-half-away, clamp,
 // pack -- all on the FMA / ALU pipes (see epilogue.cuh), written as two swizzled 16-byte pieces.
-template <bool HAS_Z, bool NONNEG>
+// MAGIC: the bias slice in shared memory carries I2F_MAGIC_BITS and |acc + bias| < 2^22 was proven for the
+// chunk (epilogue.cuh): no conversion-pipe instruction is left in the sequence.
+template <bool HAS_Z, bool NONNEG, bool MAGIC>
 __device__ __forceinline__ void requant_row32(
         const uint32_t (&r)[32], const uint32_t* bcol, const uint8_t* zrow, uint8_t* drow, uint32_t h,
         uint32_t lane, const RequantParams& rq) {
@@ -224,7 +227,7 @@ __device__ __forceinline__ void requant_row32(
                 for (uint32_t b = 0; b < 4; b += 2) {
                     const int32_t s0 = static_cast<int32_t>(r[j * 16 + w * 4 + b] + bb[b]);
                     const int32_t s1 = static_cast<int32_t>(r[j * 16 + w * 4 + b + 1] + bb[b + 1]);
-                    requant_pair_nonneg<HAS_Z>(
+                    requant_pair_nonneg<HAS_Z, MAGIC>(
                             s0, s1, __byte_perm(zx[w], 0x4B000000u, 0x7540u | b),
                             __byte_perm(zx[w], 0x4B000000u, 0x7540u | (b + 1)), kp, ub[b], ub[b + 1]);
                 }
@@ -233,7 +236,7 @@ __device__ __forceinline__ void requant_row32(
                 for (uint32_t b = 0; b < 4; b += 2) {
                     const int32_t s0 = static_cast<int32_t>(r[j * 16 + w * 4 + b] + bb[b]);
                     const int32_t s1 = static_cast<int32_t>(r[j * 16 + w * 4 + b + 1] + bb[b + 1]);
-                    requant_pair_signed<HAS_Z>(
+                    requant_pair_signed<HAS_Z, MAGIC>(
                             s0, s1, __byte_perm(zx[w], 0x4B000000u, 0x7540u | b),
                             __byte_perm(zx[w], 0x4B000000u, 0x7540u | (b + 1)), kp, ub[b], ub[b + 1]);
                 }
@@ -979,6 +982,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         const bool generic_act = p.nonline == B200CB_NL_H_SWISH || p.nonline == B200CB_NL_SIGMOID;
         const bool fast8 = KIND == KIND_S8 && !generic_act && p.rq.fast_div == 2;
         uint32_t acc = 0, acc_phase = 0, db = 0, cur_key = 0xffffffffu;
+        bool magic = false;  // (int8) the current bias slice carries I2F_MAGIC_BITS
         // this group's z sub-ring (see the z prefetch warp): position and phase advance once per chunk the
         // group consumes
         const uint32_t ZD = nz / T::GROUPS;
@@ -1034,6 +1038,22 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             const uint32_t key = T::GROUPS > 1 ? n_blk * NUM_CHUNKS + c_own : n_blk;
             if (key != cur_key) {
                 const uint32_t b0 = n0 + (T::GROUPS > 1 ? c_own * T::EPI_N : 0u);
+                if constexpr (KIND == KIND_S8 && !OUT32) {
+                    // conversion-free int -> float (epilogue.cuh): legal for this chunk when K * 2^14 + max |bias|
+                    // of its 64 columns stays below 2^22; every warp of the group derives the same flag
+                    uint32_t mx = 0;
+                    if (p.has_bias) {
+                        const int32_t* bp = reinterpret_cast<const int32_t*>(p.bias);
+                        for (uint32_t i = lane; i < BIAS_COLS; i += 32)
+                            if (b0 + i < p.OC) {
+                                const int32_t v = bp[b0 + i];
+                                const uint32_t a = v < 0 ? 0u - static_cast<uint32_t>(v) : static_cast<uint32_t>(v);
+                                mx = a > mx ? a : mx;
+                            }
+                    }
+                    mx = __reduce_max_sync(0xffffffffu, mx);
+                    magic = fast8 && !p.nchw4 && static_cast<uint64_t>(p.acc_bound) + mx < I2F_RANGE;
+                }
                 named_bar_sync(1 + group, 128);
                 for (uint32_t i = quad * 32 + lane; i < BIAS_COLS; i += 128) {
                     uint32_t v = 0;
@@ -1051,7 +1071,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                     __half2float(reinterpret_cast<const __half*>(p.bias)[b0 + i]));
                         }
                     }
-                    sbias[i] = v;
+                    sbias[i] = v + (magic ? I2F_MAGIC_BITS : 0u);
                 }
                 named_bar_sync(1 + group, 128);
                 cur_key = key;
@@ -1205,17 +1225,25 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         }
 #undef B200CB_NCHW4_CASE
                       } else if (fast8) {
+#define B200CB_RQ_CASE(Z_, R_)                                                      \
+    do {                                                                            \
+        if (magic)                                                                  \
+            requant_row32<Z_, R_, true>(r, bcol, zrow, drow, h, lane, p.rq);        \
+        else                                                                        \
+            requant_row32<Z_, R_, false>(r, bcol, zrow, drow, h, lane, p.rq);       \
+    } while (0)
                         if (p.has_z) {
                             if (p.nonline == B200CB_NL_RELU)
-                                requant_row32<true, true>(r, bcol, zrow, drow, h, lane, p.rq);
+                                B200CB_RQ_CASE(true, true);
                             else
-                                requant_row32<true, false>(r, bcol, zrow, drow, h, lane, p.rq);
+                                B200CB_RQ_CASE(true, false);
                         } else {
                             if (p.nonline == B200CB_NL_RELU)
-                                requant_row32<false, true>(r, bcol, zrow, drow, h, lane, p.rq);
+                                B200CB_RQ_CASE(false, true);
                             else
-                                requant_row32<false, false>(r, bcol, zrow, drow, h, lane, p.rq);
+                                B200CB_RQ_CASE(false, false);
                         }
+#undef B200CB_RQ_CASE
                       } else {
                         float x[32];
 #pragma unroll
@@ -2503,6 +2531,10 @@ int launch_dense(
     p.direct_store = ((plan.reserved[2] >> 1) & 1) && ld_dst == d.oc;  // (the st.global path assumes a dense dst)
     p.out_f32 = out_f32 ? 1 : 0;
     p.acc_scale = d.src_scale * d.filter_scale;
+    {
+        const uint64_t kb = (uint64_t)d.fh * d.fw * d.ic * 16384ull;  // |int8 * int8| <= 2^14 per tap and channel
+        p.acc_bound = kb > 0xffffffffull ? 0xffffffffu : (uint32_t)kb;
+    }
     p.z = z;
     p.nz = (plan.reserved[5] >> 16) ? (plan.reserved[5] >> 16) : NZ_MIN;
     p.nonline = d.nonline_mode;

@@ -199,7 +199,9 @@ def test_int8_epilogue_sass_has_no_contracted_packed_ops():
     """Bit-exactness guard.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (see
     megengine_b200/csrc/epilogue.cuh), so the packed requantize keeps no product that feeds an add.  In
     every QuantizedS8 igemm kernel the machine code must then hold exactly the explicit FMAs of the
-    division (2 FFMA2 per FADD2.RM pair rounding) and no round-to-nearest FADD2 at all."""
+    division (2 FFMA2 per FADD2.RM pair rounding); the only round-to-nearest FADD2s are the exact magic-number
+    subtractions of the conversion-free int -> float variants (a third of the igemm rounding sites, none in the
+    generic depthwise kernel) -- an add never follows a product."""
     import re
     import shutil
     import subprocess
@@ -219,6 +221,6 @@ def test_int8_epilogue_sass_has_no_contracted_packed_ops():
         plain = len(re.findall(r"FADD2 ", f))
         assert rm > 0 and rm == rz, (name, rm, rz)
         assert ffma2 == 2 * rm, (name, ffma2, rm)
-        assert plain == 0, (name, plain)
+        assert plain == (rm // 3 if is_igemm8 else 0), (name, plain, rm)
         checked += 1
     assert checked >= 11, checked
