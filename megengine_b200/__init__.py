@@ -10,7 +10,14 @@ from .conv_bias import (  # noqa: F401
     empty_like_dtype, make_tensor, mul_scale,
 )
 
+from .nn_ops import (  # noqa: F401  (the operators either side of ConvBias)
+    BatchConvBiasForward, ConvolutionBackwardData, ConvolutionForward, ElemwiseForward, ElemwiseMultiType,
+    PoolingForward, PoolingParam, TypeCvt,
+)
+
 __all__ = [
+    "BatchConvBiasForward", "ConvolutionBackwardData", "ConvolutionForward", "ElemwiseForward", "ElemwiseMultiType",
+    "PoolingForward", "PoolingParam", "TypeCvt",
     "ConvBiasForward", "DType", "EMPTY", "Handle", "MegDNNError", "Param", "TensorLayout", "TensorND",
     "dtype", "empty_like_dtype", "make_tensor", "mul_scale",
 ]

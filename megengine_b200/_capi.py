@@ -88,6 +88,34 @@ SYMBOLS = [
     ("b200cb_last_error_detail", ctypes.c_char_p, []),
 ]
 
+
+
+class PoolDesc(ctypes.Structure):
+    """b200cb_pool_desc (include/b200cb_nn.h)"""
+    _fields_ = [(n, ctypes.c_uint32) for n in (
+        "format", "mode", "dtype", "n", "c", "ih", "iw", "oh", "ow", "window_h", "window_w", "stride_h", "stride_w",
+        "pad_h", "pad_w")]
+
+
+POOL_MAX, POOL_AVERAGE, POOL_AVERAGE_COUNT_EXCLUDE_PADDING = 0, 1, 2
+ELEM_RELU, ELEM_ADD, ELEM_MAX, ELEM_MUL, ELEM_FUSE_ADD_RELU, ELEM_H_SWISH = 0, 16, 18, 21, 37, 49
+
+# every symbol include/b200cb_nn.h declares
+_U32, _U64, _F = ctypes.c_uint32, ctypes.c_uint64, ctypes.c_float
+NN_SYMBOLS = [
+    ("b200cb_pooling", ctypes.c_int, [ctypes.POINTER(PoolDesc), _P, _P, _P]),
+    ("b200cb_elemwise", ctypes.c_int, [_U32, _U32, _U64, _P, _P, _P, _P]),
+    ("b200cb_elemwise_q", ctypes.c_int, [_U32, _U64, _P, _F, _P, _F, _P, _F, _P]),
+    ("b200cb_typecvt", ctypes.c_int, [_U32, _F, _U32, _F, _U64, _P, _P, _P]),
+    ("b200cb_convolution_query", ctypes.c_int, [ctypes.POINTER(Desc), ctypes.POINTER(Plan)]),
+    ("b200cb_convolution_launch", ctypes.c_int, [ctypes.POINTER(Plan), _P, _P, _P, _P, ctypes.c_size_t, _P]),
+    ("b200cb_deconv_query", ctypes.c_int, [ctypes.POINTER(Desc), ctypes.POINTER(Plan)]),
+    ("b200cb_deconv_launch", ctypes.c_int, [ctypes.POINTER(Plan), _P, _P, _P, _P, ctypes.c_size_t, _P]),
+    ("b200cb_batch_convbias_query", ctypes.c_int, [ctypes.POINTER(Desc), ctypes.POINTER(Plan)]),
+    ("b200cb_batch_convbias_launch", ctypes.c_int,
+     [ctypes.POINTER(Plan), _P, _P, _P, _P, _P, _P, ctypes.c_size_t, _P]),
+]
+
 _lib = None
 
 
@@ -101,7 +129,7 @@ def load():
             "libb200cb.so not built (%s). Run `python -c 'import __graft_entry__ as g; g.build()'` "
             "-- megengine_b200 has no CPU/PyTorch fallback path." % LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
-    for name, res, args in SYMBOLS:
+    for name, res, args in SYMBOLS + NN_SYMBOLS:
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -1,0 +1,702 @@
+// Operators either side of ConvBiasForward (include/b200cb_nn.h): pooling,
+// elementwise (plain and quantized), TypeCvt -- pure HBM-bound kernels, 16-byte vectors, grids sized in
+// multiples of the SM count -- and the convolution front-ends (ConvolutionForward, ConvolutionBackwardData,
+// BatchConvBiasForward) that run on the ConvBias kernels.
+//
+// Arithmetic restates the reference's naive operators element for element:
+//   pooling      dnn/src/naive/pooling/opr_impl.cpp:17-330 (MaxPooler, MeanInclude / MeanExclude poolers: half
+//                types accumulate IN the half type, QuantizedS8 averages round half away from zero)
+//   elemwise     dnn/src/common/elemwise/kern_defs.cuh:169-270 (ctype arithmetic: half types round every op)
+//   quantized    dnn/src/naive/elemwise_multi_type/opr_impl.h:45-120 (quantize(op(dequantize(a), dequantize(b))))
+//   TypeCvt      dnn/src/naive/type_cvt/opr_impl.cpp:24-57, dnn/include/megdnn/dtype.h:845-897
+//   deconv       dnn/src/naive/convolution/opr_impl.cpp:92-167 (fp32 / int32 accumulation, one final TypeCvt)
+#include <cuda_bf16.h>
+#include <cuda_fp16.h>
+#include <float.h>
+#include <math.h>
+#include <string.h>
+#include "b200cb_nn.h"
+#include "common.h"
+#include "epilogue.cuh"
+
+namespace b200cb {
+namespace {
+
+// ---------------------------------------------------------------- element helpers
+template <int DT>
+struct Elem;
+template <>
+struct Elem<B200CB_DT_F32> {
+    using T = float;
+    static __device__ __forceinline__ float ld(T v) { return v; }
+    static __device__ __forceinline__ T st(float v) { return v; }
+};
+// float -> fp16 the way the reference's half type rounds (third_party half.hpp built with HALF_ROUND_STYLE 1,
+// HALF_ROUND_TIES_TO_EVEN 0): to nearest, TIES AWAY FROM ZERO.  Sums of two fp16 values tie all the time, so the
+// pooling / elementwise results are bit-exact only with this rounding (cvt.rn.f16.f32 breaks ties to even).
+__device__ __forceinline__ __half f2h_ties_away(float v) {
+    const uint32_t bits = __float_as_uint(v);
+    const uint32_t sign = (bits >> 16) & 0x8000u, e = (bits >> 23) & 0xffu, m = bits & 0x7fffffu;
+    uint32_t h;
+    if (e == 255)
+        h = 0x7c00u + (m >> 13);             // inf / nan
+    else if (e > 142)
+        h = 0x7c00u;                          // overflow
+    else if (e >= 113)
+        h = ((e - 112) << 10) + (m >> 13) + ((m >> 12) & 1u);   // normal: add the first dropped bit
+    else if (e >= 103) {
+        const uint32_t shift = 126 - e;       // subnormal result
+        h = (0x0400u >> (113 - e)) + (m >> shift) + ((m >> (shift - 1)) & 1u);
+    } else
+        h = e == 102 ? 1u : 0u;
+    return __ushort_as_half(static_cast<unsigned short>(sign | h));
+}
+template <>
+struct Elem<B200CB_DT_F16> {
+    using T = __half;
+    static __device__ __forceinline__ float ld(T v) { return __half2float(v); }
+    static __device__ __forceinline__ T st(float v) { return f2h_ties_away(v); }
+};
+template <>
+struct Elem<B200CB_DT_BF16> {
+    using T = __nv_bfloat16;
+    static __device__ __forceinline__ float ld(T v) { return __bfloat162float(v); }
+    static __device__ __forceinline__ T st(float v) { return __float2bfloat16_rn(v); }
+};
+template <>
+struct Elem<B200CB_DT_QS8> {
+    using T = int8_t;
+    static __device__ __forceinline__ float ld(T v) { return static_cast<float>(v); }
+    static __device__ __forceinline__ T st(float v) { return static_cast<int8_t>(v); }
+};
+// a value rounded to the element type and widened again (every ctype operation of the reference rounds)
+template <int DT>
+__device__ __forceinline__ float rnd(float v) {
+    return Elem<DT>::ld(Elem<DT>::st(v));
+}
+
+template <typename T, int V>
+struct alignas(sizeof(T) * V) Vec {
+    T v[V];
+};
+
+inline uint32_t grid_for(uint64_t items, uint32_t threads) {
+    const uint64_t blocks = (items + threads - 1) / threads;
+    const uint64_t cap = (uint64_t)device_sm_count() * 16;   // persistent-ish: grid-stride beyond 16 CTAs / SM
+    return (uint32_t)(blocks < cap ? (blocks ? blocks : 1) : cap);
+}
+
+// ---------------------------------------------------------------- pooling
+struct PoolParams {
+    uint32_t n, c, ih, iw, oh, ow, wh, ww, sh, sw, ph, pw;
+    uint32_t cg;          // channel groups of V elements a thread handles (NHWC: c / V, NCHW4: c / 4, NCHW: c)
+    uint32_t layout;      // 0 NHWC (pixel pitch c), 1 NCHW (planes), 2 NCHW4 (planes of 4-channel pixels)
+    float count_all;      // window_h * window_w rounded to the element type (MeanIncludePooler::count)
+};
+
+// one thread = one output pixel x V consecutive channels
+template <int DT, int MODE, int V>
+__global__ void __launch_bounds__(256) pool_kernel(
+        const typename Elem<DT>::T* __restrict__ src, typename Elem<DT>::T* __restrict__ dst, PoolParams p) {
+    using T = typename Elem<DT>::T;
+    const uint64_t total = (uint64_t)p.n * p.oh * p.ow * p.cg;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint32_t g, ow, oh, n;
+        if (p.layout == 0) {   // NHWC: channel groups fastest
+            g = i % p.cg;
+            ow = (i / p.cg) % p.ow;
+            oh = (i / ((uint64_t)p.cg * p.ow)) % p.oh;
+            n = i / ((uint64_t)p.cg * p.ow * p.oh);
+        } else {               // planes: pixels fastest
+            ow = i % p.ow;
+            oh = (i / p.ow) % p.oh;
+            g = (i / ((uint64_t)p.ow * p.oh)) % p.cg;
+            n = i / ((uint64_t)p.ow * p.oh * p.cg);
+        }
+        const T* sb;
+        T* db;
+        uint64_t pitch;   // elements between horizontally adjacent pixels
+        if (p.layout == 0) {
+            sb = src + (uint64_t)n * p.ih * p.iw * p.c + (uint64_t)g * V;
+            db = dst + (((uint64_t)n * p.oh + oh) * p.ow + ow) * p.c + (uint64_t)g * V;
+            pitch = p.c;
+        } else {
+            sb = src + ((uint64_t)n * p.cg + g) * p.ih * p.iw * V;
+            db = dst + (((uint64_t)n * p.cg + g) * p.oh * p.ow + (uint64_t)oh * p.ow + ow) * V;
+            pitch = V;
+        }
+        float acc[V];
+        int32_t iacc[V];
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            acc[k] = MODE == B200CB_POOL_MAX ? (DT == B200CB_DT_QS8 ? -128.f : (DT == B200CB_DT_F16 ? -65504.f : -FLT_MAX)) : 0.f;
+            iacc[k] = 0;
+        }
+        if (DT == B200CB_DT_BF16 && MODE == B200CB_POOL_MAX) {
+#pragma unroll
+            for (int k = 0; k < V; ++k)
+                acc[k] = __uint_as_float(0xff7f0000u);   // bfloat16 lowest
+        }
+        uint32_t cnt = 0;
+        for (uint32_t fh = 0; fh < p.wh; ++fh) {
+            const uint32_t ih = oh * p.sh + fh - p.ph;   // unsigned wrap == the reference's size_t arithmetic
+            if (ih >= p.ih)
+                continue;
+            for (uint32_t fw = 0; fw < p.ww; ++fw) {
+                const uint32_t iw = ow * p.sw + fw - p.pw;
+                if (iw >= p.iw)
+                    continue;
+                const Vec<T, V> x = *reinterpret_cast<const Vec<T, V>*>(sb + ((uint64_t)ih * p.iw + iw) * pitch);
+                ++cnt;
+#pragma unroll
+                for (int k = 0; k < V; ++k) {
+                    if constexpr (MODE == B200CB_POOL_MAX) {
+                        const float xv = Elem<DT>::ld(x.v[k]);
+                        acc[k] = acc[k] > xv ? acc[k] : xv;
+                    } else if constexpr (DT == B200CB_DT_QS8) {
+                        iacc[k] += x.v[k];
+                    } else {
+                        acc[k] = rnd<DT>(__fadd_rn(acc[k], Elem<DT>::ld(x.v[k])));   // sum lives in the element type
+                    }
+                }
+            }
+        }
+        Vec<T, V> o;
+#pragma unroll
+        for (int k = 0; k < V; ++k) {
+            float r;
+            if constexpr (MODE == B200CB_POOL_MAX) {
+                r = acc[k];
+            } else if constexpr (DT == B200CB_DT_QS8) {
+                // T(std::round(float(sum) / count)): count is the window size (include) or the fed count
+                const float c = MODE == B200CB_POOL_AVERAGE ? static_cast<float>(p.wh * p.ww) : static_cast<float>(cnt);
+                r = roundf(__fdiv_rn(static_cast<float>(iacc[k]), c));
+            } else {
+                const float c = MODE == B200CB_POOL_AVERAGE ? p.count_all : rnd<DT>(static_cast<float>(cnt));
+                r = __fdiv_rn(acc[k], c);
+            }
+            o.v[k] = Elem<DT>::st(r);
+        }
+        *reinterpret_cast<Vec<T, V>*>(db) = o;
+    }
+}
+
+template <int DT, int MODE>
+int pool_launch_v(const b200cb_pool_desc& d, const void* src, void* dst, cudaStream_t stream) {
+    using T = typename Elem<DT>::T;
+    PoolParams p;
+    p.n = d.n, p.c = d.c, p.ih = d.ih, p.iw = d.iw, p.oh = d.oh, p.ow = d.ow;
+    p.wh = d.window_h, p.ww = d.window_w, p.sh = d.stride_h, p.sw = d.stride_w, p.ph = d.pad_h, p.pw = d.pad_w;
+    const float cnt = (float)(d.window_h * d.window_w);
+    p.count_all = DT == B200CB_DT_F16   ? __half2float(__float2half_rn(cnt))   /* window sizes < 2048 are exact */
+                  : DT == B200CB_DT_BF16 ? __bfloat162float(__float2bfloat16_rn(cnt))
+                                         : cnt;
+    constexpr int VMAX = 16 / (int)sizeof(T);
+    int v = 1;
+    if (d.format == B200CB_FORMAT_NHWC) {
+        p.layout = 0;
+        for (v = VMAX; v > 1 && d.c % v != 0; v /= 2) {
+        }
+    } else if (d.format == B200CB_FORMAT_NCHW) {
+        p.layout = 1;
+    } else {
+        p.layout = 2;
+        v = 4;
+    }
+    p.cg = d.c / v;
+    const uint64_t items = (uint64_t)d.n * d.oh * d.ow * p.cg;
+    const uint32_t grid = grid_for(items, 256);
+    const T* s = static_cast<const T*>(src);
+    T* o = static_cast<T*>(dst);
+    switch (v) {
+        case 1: pool_kernel<DT, MODE, 1><<<grid, 256, 0, stream>>>(s, o, p); break;
+        case 2: pool_kernel<DT, MODE, 2><<<grid, 256, 0, stream>>>(s, o, p); break;
+        case 4: pool_kernel<DT, MODE, 4><<<grid, 256, 0, stream>>>(s, o, p); break;
+        case 8:
+            if constexpr (VMAX >= 8) {
+                pool_kernel<DT, MODE, 8><<<grid, 256, 0, stream>>>(s, o, p);
+                break;
+            }
+        case 16:
+            if constexpr (VMAX >= 16) {
+                pool_kernel<DT, MODE, 16><<<grid, 256, 0, stream>>>(s, o, p);
+                break;
+            }
+        default: return B200CB_UNSUPPORTED_ALIGNMENT;
+    }
+    return B200CB_OK;
+}
+
+template <int DT>
+int pool_launch(const b200cb_pool_desc& d, const void* src, void* dst, cudaStream_t stream) {
+    switch (d.mode) {
+        case B200CB_POOL_MAX: return pool_launch_v<DT, B200CB_POOL_MAX>(d, src, dst, stream);
+        case B200CB_POOL_AVERAGE: return pool_launch_v<DT, B200CB_POOL_AVERAGE>(d, src, dst, stream);
+        case B200CB_POOL_AVERAGE_COUNT_EXCLUDE_PADDING:
+            return pool_launch_v<DT, B200CB_POOL_AVERAGE_COUNT_EXCLUDE_PADDING>(d, src, dst, stream);
+        default: return B200CB_UNSUPPORTED_PARAM;
+    }
+}
+
+// ---------------------------------------------------------------- elementwise
+template <int DT>
+__device__ __forceinline__ float elem_apply(uint32_t mode, float x, float y) {
+    switch (mode) {
+        case B200CB_ELEM_RELU: return x <= 0.f ? 0.f : x;
+        case B200CB_ELEM_ADD: return rnd<DT>(__fadd_rn(x, y));
+        case B200CB_ELEM_MAX: return x > y ? x : y;
+        case B200CB_ELEM_MUL: return rnd<DT>(__fmul_rn(x, y));
+        case B200CB_ELEM_FUSE_ADD_RELU: {
+            const float s = rnd<DT>(__fadd_rn(x, y));
+            return s <= 0.f ? 0.f : s;
+        }
+        default:   // H_SWISH: x * min(max(x + 3, 0.f), 6.f) * (1.f / 6.f) -- the float literals promote the whole
+                   // expression to fp32 for the half types too: one rounding at the end (kern_defs.cuh:203)
+            return rnd<DT>(act_generic(x, B200CB_NL_H_SWISH));
+    }
+}
+
+template <int DT>
+__global__ void __launch_bounds__(256) elemwise_kernel(
+        uint32_t mode, bool binary, uint64_t nvec, uint64_t n, const typename Elem<DT>::T* __restrict__ a,
+        const typename Elem<DT>::T* __restrict__ b, typename Elem<DT>::T* __restrict__ dst) {
+    using T = typename Elem<DT>::T;
+    constexpr int V = 16 / (int)sizeof(T);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+        const Vec<T, V> x = reinterpret_cast<const Vec<T, V>*>(a)[i];
+        Vec<T, V> y = x, o;
+        if (binary)
+            y = reinterpret_cast<const Vec<T, V>*>(b)[i];
+#pragma unroll
+        for (int k = 0; k < V; ++k)
+            o.v[k] = Elem<DT>::st(elem_apply<DT>(mode, Elem<DT>::ld(x.v[k]), Elem<DT>::ld(y.v[k])));
+        reinterpret_cast<Vec<T, V>*>(dst)[i] = o;
+    }
+    // tail (< one vector)
+    if (blockIdx.x == 0 && threadIdx.x < n - nvec * V) {
+        const uint64_t i = nvec * V + threadIdx.x;
+        dst[i] = Elem<DT>::st(elem_apply<DT>(mode, Elem<DT>::ld(a[i]), Elem<DT>::ld(binary ? b[i] : a[i])));
+    }
+}
+
+__device__ __forceinline__ float q_apply(uint32_t mode, float x, float y) {
+    switch (mode) {
+        case B200CB_ELEM_RELU: return x <= 0.f ? 0.f : x;
+        case B200CB_ELEM_ADD: return __fadd_rn(x, y);
+        case B200CB_ELEM_FUSE_ADD_RELU: {
+            const float s = __fadd_rn(x, y);
+            return s <= 0.f ? 0.f : s;
+        }
+        default: return act_generic(x, B200CB_NL_H_SWISH);
+    }
+}
+
+__global__ void __launch_bounds__(256) elemwise_q_kernel(
+        uint32_t mode, bool binary, uint64_t nvec, uint64_t n, const int8_t* __restrict__ a, float sa,
+        const int8_t* __restrict__ b, float sb, int8_t* __restrict__ dst, RequantParams rq) {
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+        const Vec<int8_t, 16> x = reinterpret_cast<const Vec<int8_t, 16>*>(a)[i];
+        Vec<int8_t, 16> y = x, o;
+        if (binary)
+            y = reinterpret_cast<const Vec<int8_t, 16>*>(b)[i];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+            const float r = q_apply(mode, __fmul_rn((float)x.v[k], sa), __fmul_rn((float)y.v[k], sb));
+            o.v[k] = (int8_t)quant_s8(r, rq);
+        }
+        reinterpret_cast<Vec<int8_t, 16>*>(dst)[i] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n - nvec * 16) {
+        const uint64_t i = nvec * 16 + threadIdx.x;
+        const float r = q_apply(mode, __fmul_rn((float)a[i], sa), __fmul_rn((float)(binary ? b[i] : a[i]), sb));
+        dst[i] = (int8_t)quant_s8(r, rq);
+    }
+}
+
+// ---------------------------------------------------------------- TypeCvt
+// from<T>: quantized -> dequantize (int * scale), normal -> the value; to<T>: quantized -> quantize(float(in)),
+// normal -> static_cast (float -> half types round to nearest even)
+template <int DT>
+struct Raw {
+    using T = typename Elem<DT>::T;
+};
+template <>
+struct Raw<B200CB_DT_QS32> {
+    using T = int32_t;
+};
+template <int SDT, int DDT>
+__global__ void __launch_bounds__(256) typecvt_kernel(
+        uint64_t n, const void* __restrict__ src_, void* __restrict__ dst_, float s_src, RequantParams rq) {
+    using ST = typename Raw<SDT>::T;
+    using DT_ = typename Raw<DDT>::T;
+    const ST* src = static_cast<const ST*>(src_);
+    DT_* dst = static_cast<DT_*>(dst_);
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
+        float v;
+        if constexpr (SDT == B200CB_DT_QS8 || SDT == B200CB_DT_QS32)
+            v = __fmul_rn(static_cast<float>(src[i]), s_src);
+        else
+            v = Elem<SDT>::ld(src[i]);
+        if constexpr (DDT == B200CB_DT_QS8) {
+            dst[i] = (int8_t)quant_s8(v, rq);
+        } else if constexpr (DDT == B200CB_DT_QS32) {
+            float q = roundf(__fdiv_rn(v, rq.s_dst));
+            q = fminf(fmaxf(-2147483648.f, q), 2147483520.f);
+            dst[i] = static_cast<int32_t>(q);
+        } else {
+            dst[i] = Elem<DDT>::st(v);
+        }
+    }
+}
+
+// ---------------------------------------------------------------- deconvolution helpers
+// KRSC filter (OC, FH, FW, IC) -> (IC, FH, FW, OC), spatially flipped: the filter of the stride-1 convolution
+// over diff that equals the data gradient
+template <typename T>
+__global__ void deconv_filter_kernel(const T* __restrict__ w, T* __restrict__ o, uint32_t OC, uint32_t FH, uint32_t FW, uint32_t IC) {
+    const uint64_t total = (uint64_t)OC * FH * FW * IC;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t oc = i % OC;
+        const uint32_t fw = (i / OC) % FW;
+        const uint32_t fh = (i / ((uint64_t)OC * FW)) % FH;
+        const uint32_t ic = i / ((uint64_t)OC * FW * FH);
+        o[i] = w[(((uint64_t)oc * FH + (FH - 1 - fh)) * FW + (FW - 1 - fw)) * IC + ic];
+    }
+}
+// diff (N, OH, OW, C) -> zero-upsampled (N, UH, UW, C): up[n, oh * sh, ow * sw, :] = diff[n, oh, ow, :], 16-byte vectors
+__global__ void deconv_upsample_kernel(
+        const uint4* __restrict__ in, uint4* __restrict__ out, uint32_t N, uint32_t OH, uint32_t OW, uint32_t UH,
+        uint32_t UW, uint32_t cv, uint32_t sh, uint32_t sw) {
+    const uint64_t total = (uint64_t)N * UH * UW * cv;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = i % cv;
+        const uint32_t uw = (i / cv) % UW;
+        const uint32_t uh = (i / ((uint64_t)cv * UW)) % UH;
+        const uint32_t n = i / ((uint64_t)cv * UW * UH);
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (uh % sh == 0 && uw % sw == 0 && uh / sh < OH && uw / sw < OW)
+            v = in[(((uint64_t)n * OH + uh / sh) * OW + uw / sw) * cv + c];
+        out[i] = v;
+    }
+}
+
+constexpr uint32_t KERNEL_DECONV = 16, KERNEL_BATCH_CONVBIAS = 17;
+inline size_t al256(size_t v) {
+    return (v + 255) & ~size_t(255);
+}
+
+struct DeconvGeom {
+    b200cb_desc inner;       // the stride-1 forward convolution over (upsampled) diff
+    uint32_t uh, uw;         // upsampled diff extent (== oh, ow for stride 1)
+    bool upsample;
+    size_t flt_bytes, up_bytes;
+};
+int deconv_geometry(const b200cb_desc& f, DeconvGeom* g) {
+    if (f.format != B200CB_FORMAT_NHWC || f.sparse != B200CB_SPARSE_DENSE || f.group != 1)
+        return B200CB_UNSUPPORTED_FORMAT;
+    const uint32_t eh = (f.fh - 1) * f.dilate_h, ew = (f.fw - 1) * f.dilate_w;
+    if (f.pad_h > eh || f.pad_w > ew)
+        return B200CB_UNSUPPORTED_PARAM;   // (negative padding of the equivalent convolution: cropping, not implemented)
+    if (f.stride_h == 0 || f.stride_w == 0)
+        return B200CB_UNSUPPORTED_PARAM;
+    // diff extent must be what the forward convolution produces from grad's extent
+    if ((f.ih + 2 * f.pad_h < eh + 1) || (f.iw + 2 * f.pad_w < ew + 1) ||
+        (f.ih + 2 * f.pad_h - eh - 1) / f.stride_h + 1 != f.oh || (f.iw + 2 * f.pad_w - ew - 1) / f.stride_w + 1 != f.ow)
+        return B200CB_UNSUPPORTED_SHAPE;
+    g->upsample = f.stride_h > 1 || f.stride_w > 1;
+    g->uh = f.ih + 2 * f.pad_h - eh;   // == (oh - 1) * stride + 1 + the rows the forward stride skipped
+    g->uw = f.iw + 2 * f.pad_w - ew;
+    b200cb_desc e;
+    memset(&e, 0, sizeof(e));
+    e.format = B200CB_FORMAT_NHWC, e.sparse = B200CB_SPARSE_DENSE, e.mode = f.mode;
+    e.nonline_mode = B200CB_NL_IDENTITY, e.compute_mode = f.compute_mode;
+    e.bias_mode = B200CB_BIAS_NONE, e.has_z = 0;
+    e.src_dtype = f.dst_dtype, e.filter_dtype = f.filter_dtype, e.dst_dtype = f.src_dtype;   // diff -> grad
+    e.bias_dtype = e.z_dtype = B200CB_DT_NONE;
+    e.src_scale = f.dst_scale, e.filter_scale = f.filter_scale, e.dst_scale = f.src_scale;
+    e.n = f.n, e.ic = f.oc, e.ih = g->uh, e.iw = g->uw;
+    e.oc = f.ic, e.oh = f.ih, e.ow = f.iw;
+    e.fh = f.fh, e.fw = f.fw, e.group = 1;
+    e.pad_h = eh - f.pad_h, e.pad_w = ew - f.pad_w;
+    e.stride_h = e.stride_w = 1;
+    e.dilate_h = f.dilate_h, e.dilate_w = f.dilate_w;
+    g->inner = e;
+    const size_t es = dtype_size(f.filter_dtype);
+    g->flt_bytes = al256((size_t)f.oc * f.fh * f.fw * f.ic * es);
+    g->up_bytes = g->upsample ? al256((size_t)f.n * g->uh * g->uw * f.oc * dtype_size(f.dst_dtype)) : 0;
+    return B200CB_OK;
+}
+
+int cuda_rc(const char* what) {
+    const cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) {
+        set_last_error(what, cudaGetErrorString(e));
+        return B200CB_ERR_CUDA;
+    }
+    return B200CB_OK;
+}
+
+}  // namespace
+}  // namespace b200cb
+
+using namespace b200cb;
+
+extern "C" {
+
+int b200cb_pooling(const b200cb_pool_desc* d, const void* src, void* dst, void* stream) {
+    if (!d || !src || !dst)
+        return B200CB_ERR_NULL;
+    if (d->window_h == 0 || d->window_w == 0 || d->stride_h == 0 || d->stride_w == 0 || d->n == 0 || d->c == 0)
+        return B200CB_UNSUPPORTED_PARAM;
+    if (d->ih + 2 * d->pad_h < d->window_h || d->iw + 2 * d->pad_w < d->window_w ||
+        (d->ih + 2 * d->pad_h - d->window_h) / d->stride_h + 1 != d->oh ||
+        (d->iw + 2 * d->pad_w - d->window_w) / d->stride_w + 1 != d->ow)
+        return B200CB_UNSUPPORTED_SHAPE;
+    // every window must see at least one pixel (the reference throws "The pooling window lies outside completely")
+    if (d->pad_h >= d->window_h || d->pad_w >= d->window_w ||
+        (d->oh - 1) * d->stride_h >= d->ih + d->pad_h || (d->ow - 1) * d->stride_w >= d->iw + d->pad_w)
+        return B200CB_UNSUPPORTED_PARAM;
+    if (d->format == B200CB_FORMAT_NCHW4 && (d->dtype != B200CB_DT_QS8 || d->c % 4 != 0))
+        return B200CB_UNSUPPORTED_FORMAT;
+    if (d->format != B200CB_FORMAT_NHWC && d->format != B200CB_FORMAT_NCHW && d->format != B200CB_FORMAT_NCHW4)
+        return B200CB_UNSUPPORTED_FORMAT;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc;
+    switch (d->dtype) {
+        case B200CB_DT_F32: rc = pool_launch<B200CB_DT_F32>(*d, src, dst, s); break;
+        case B200CB_DT_F16: rc = pool_launch<B200CB_DT_F16>(*d, src, dst, s); break;
+        case B200CB_DT_BF16: rc = pool_launch<B200CB_DT_BF16>(*d, src, dst, s); break;
+        case B200CB_DT_QS8: rc = pool_launch<B200CB_DT_QS8>(*d, src, dst, s); break;
+        default: return B200CB_UNSUPPORTED_DTYPE;
+    }
+    return rc != B200CB_OK ? rc : cuda_rc("pooling launch");
+}
+
+int b200cb_elemwise(uint32_t mode, uint32_t dtype, uint64_t n, const void* a, const void* b, void* dst, void* stream) {
+    const bool binary = mode == B200CB_ELEM_ADD || mode == B200CB_ELEM_MAX || mode == B200CB_ELEM_MUL ||
+                        mode == B200CB_ELEM_FUSE_ADD_RELU;
+    if (!binary && mode != B200CB_ELEM_RELU && mode != B200CB_ELEM_H_SWISH)
+        return B200CB_UNSUPPORTED_PARAM;
+    if (!a || !dst || (binary && !b))
+        return B200CB_ERR_NULL;
+    if (n == 0)
+        return B200CB_OK;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t es = dtype_size(dtype);
+    if (es != 2 && es != 4)
+        return B200CB_UNSUPPORTED_DTYPE;
+    const uint64_t nvec = n / (16 / es);
+    const uint32_t grid = grid_for(nvec ? nvec : 1, 256);
+    switch (dtype) {
+        case B200CB_DT_F32:
+            elemwise_kernel<B200CB_DT_F32><<<grid, 256, 0, s>>>(
+                    mode, binary, nvec, n, static_cast<const float*>(a), static_cast<const float*>(b), static_cast<float*>(dst));
+            break;
+        case B200CB_DT_F16:
+            elemwise_kernel<B200CB_DT_F16><<<grid, 256, 0, s>>>(
+                    mode, binary, nvec, n, static_cast<const __half*>(a), static_cast<const __half*>(b), static_cast<__half*>(dst));
+            break;
+        case B200CB_DT_BF16:
+            elemwise_kernel<B200CB_DT_BF16><<<grid, 256, 0, s>>>(
+                    mode, binary, nvec, n, static_cast<const __nv_bfloat16*>(a), static_cast<const __nv_bfloat16*>(b),
+                    static_cast<__nv_bfloat16*>(dst));
+            break;
+        default: return B200CB_UNSUPPORTED_DTYPE;
+    }
+    return cuda_rc("elemwise launch");
+}
+
+int b200cb_elemwise_q(
+        uint32_t mode, uint64_t n, const void* a, float sa, const void* b, float sb, void* dst, float sd, void* stream) {
+    const bool binary = mode == B200CB_ELEM_ADD || mode == B200CB_ELEM_FUSE_ADD_RELU;
+    if (!binary && mode != B200CB_ELEM_RELU && mode != B200CB_ELEM_H_SWISH)
+        return B200CB_UNSUPPORTED_PARAM;
+    if (!a || !dst || (binary && !b))
+        return B200CB_ERR_NULL;
+    if (n == 0)
+        return B200CB_OK;
+    b200cb_desc t;
+    memset(&t, 0, sizeof(t));
+    t.dst_scale = sd, t.src_scale = t.filter_scale = 1.f, t.bias_dtype = B200CB_DT_NONE;
+    RequantParams rq = make_requant(t);
+    if (rq.fast_div == 2)
+        rq.fast_div = 1;   // the guarded division: dividends here are not bounded by an accumulator range
+    const uint64_t nvec = n / 16;
+    elemwise_q_kernel<<<grid_for(nvec ? nvec : 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+            mode, binary, nvec, n, static_cast<const int8_t*>(a), sa, static_cast<const int8_t*>(b), sb,
+            static_cast<int8_t*>(dst), rq);
+    return cuda_rc("elemwise_q launch");
+}
+
+int b200cb_typecvt(
+        uint32_t sdt, float s_src, uint32_t ddt, float s_dst, uint64_t n, const void* src, void* dst, void* stream) {
+    if (!src || !dst)
+        return B200CB_ERR_NULL;
+    if (n == 0)
+        return B200CB_OK;
+    b200cb_desc t;
+    memset(&t, 0, sizeof(t));
+    t.dst_scale = s_dst, t.src_scale = t.filter_scale = 1.f, t.bias_dtype = B200CB_DT_NONE;
+    RequantParams rq = make_requant(t);
+    if (rq.fast_div == 2)
+        rq.fast_div = 1;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const uint32_t grid = grid_for(n, 256);
+#define CVT(S_, D_)                                                                      \
+    if (sdt == S_ && ddt == D_) {                                                        \
+        typecvt_kernel<S_, D_><<<grid, 256, 0, s>>>(n, src, dst, s_src, rq);             \
+        return cuda_rc("typecvt launch");                                                \
+    }
+    CVT(B200CB_DT_F32, B200CB_DT_F16) CVT(B200CB_DT_F32, B200CB_DT_BF16) CVT(B200CB_DT_F32, B200CB_DT_QS8)
+    CVT(B200CB_DT_F32, B200CB_DT_QS32) CVT(B200CB_DT_F32, B200CB_DT_F32)
+    CVT(B200CB_DT_F16, B200CB_DT_F32) CVT(B200CB_DT_BF16, B200CB_DT_F32) CVT(B200CB_DT_F16, B200CB_DT_QS8)
+    CVT(B200CB_DT_BF16, B200CB_DT_QS8)
+    CVT(B200CB_DT_QS8, B200CB_DT_F32) CVT(B200CB_DT_QS8, B200CB_DT_F16) CVT(B200CB_DT_QS8, B200CB_DT_BF16)
+    CVT(B200CB_DT_QS8, B200CB_DT_QS8) CVT(B200CB_DT_QS8, B200CB_DT_QS32)
+    CVT(B200CB_DT_QS32, B200CB_DT_QS8) CVT(B200CB_DT_QS32, B200CB_DT_F32) CVT(B200CB_DT_QS32, B200CB_DT_QS32)
+#undef CVT
+    return B200CB_UNSUPPORTED_DTYPE;
+}
+
+// ---- ConvolutionForward: ConvBias without bias / z / activation (the reference's CUDA ConvolutionForwardImpl
+// builds the same ConvBias operator internally)
+int b200cb_convolution_query(const b200cb_desc* desc, b200cb_plan* plan) {
+    if (!desc || !plan)
+        return B200CB_ERR_NULL;
+    b200cb_desc d = *desc;
+    d.bias_mode = B200CB_BIAS_NONE, d.bias_dtype = B200CB_DT_NONE;
+    d.has_z = 0, d.z_dtype = B200CB_DT_NONE;
+    d.nonline_mode = B200CB_NL_IDENTITY;
+    return b200cb_query(&d, plan);
+}
+int b200cb_convolution_launch(
+        const b200cb_plan* plan, const void* src, const void* filter, void* dst, void* workspace, size_t ws_bytes,
+        void* stream) {
+    if (!plan)
+        return B200CB_ERR_NULL;
+    if (plan->desc.bias_mode != B200CB_BIAS_NONE || plan->desc.has_z)
+        return B200CB_ERR_BAD_PLAN;
+    return b200cb_launch(plan, src, filter, nullptr, nullptr, dst, workspace, ws_bytes, stream);
+}
+
+// ---- ConvolutionBackwardData
+int b200cb_deconv_query(const b200cb_desc* fwd, b200cb_plan* plan) {
+    if (!fwd || !plan)
+        return B200CB_ERR_NULL;
+    DeconvGeom g;
+    int rc = deconv_geometry(*fwd, &g);
+    if (rc != B200CB_OK)
+        return rc;
+    b200cb_plan inner;
+    rc = b200cb_query(&g.inner, &inner);
+    if (rc != B200CB_OK)
+        return rc;
+    *plan = inner;
+    plan->kernel = KERNEL_DECONV;
+    plan->desc = *fwd;
+    plan->workspace_bytes = g.flt_bytes + g.up_bytes + inner.workspace_bytes;
+    // accounting of the gradient itself: the zero taps of the upsampled convolution are not useful work
+    plan->flops = 2ull * fwd->n * fwd->oc * fwd->oh * fwd->ow * fwd->ic * fwd->fh * fwd->fw;
+    plan->bytes = (uint64_t)fwd->n * fwd->oh * fwd->ow * fwd->oc * dtype_size(fwd->dst_dtype) +
+                  (uint64_t)fwd->oc * fwd->fh * fwd->fw * fwd->ic * dtype_size(fwd->filter_dtype) +
+                  (uint64_t)fwd->n * fwd->ih * fwd->iw * fwd->ic * dtype_size(fwd->src_dtype);
+    return B200CB_OK;
+}
+int b200cb_deconv_launch(
+        const b200cb_plan* plan, const void* filter, const void* diff, void* grad, void* workspace, size_t ws_bytes,
+        void* stream) {
+    if (!plan || !filter || !diff || !grad)
+        return B200CB_ERR_NULL;
+    if (plan->magic != PLAN_MAGIC || plan->kernel != KERNEL_DECONV)
+        return B200CB_ERR_BAD_PLAN;
+    const b200cb_desc& f = plan->desc;
+    DeconvGeom g;
+    if (deconv_geometry(f, &g) != B200CB_OK)
+        return B200CB_ERR_BAD_PLAN;
+    b200cb_plan inner;
+    if (b200cb_query_algo(&g.inner, plan->algo, &inner) != B200CB_OK)
+        return B200CB_ERR_BAD_PLAN;
+    if (!workspace || ws_bytes < g.flt_bytes + g.up_bytes + inner.workspace_bytes)
+        return B200CB_ERR_WORKSPACE;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    uint8_t* ws = static_cast<uint8_t*>(workspace);
+    void* wt = ws;
+    void* up = ws + g.flt_bytes;
+    void* inner_ws = ws + g.flt_bytes + g.up_bytes;
+    const uint64_t fl = (uint64_t)f.oc * f.fh * f.fw * f.ic;
+    const uint32_t es = dtype_size(f.filter_dtype);
+    if (es == 1)
+        deconv_filter_kernel<uint8_t><<<grid_for(fl, 256), 256, 0, s>>>(
+                static_cast<const uint8_t*>(filter), static_cast<uint8_t*>(wt), f.oc, f.fh, f.fw, f.ic);
+    else if (es == 2)
+        deconv_filter_kernel<uint16_t><<<grid_for(fl, 256), 256, 0, s>>>(
+                static_cast<const uint16_t*>(filter), static_cast<uint16_t*>(wt), f.oc, f.fh, f.fw, f.ic);
+    else
+        deconv_filter_kernel<uint32_t><<<grid_for(fl, 256), 256, 0, s>>>(
+                static_cast<const uint32_t*>(filter), static_cast<uint32_t*>(wt), f.oc, f.fh, f.fw, f.ic);
+    int rc = cuda_rc("deconv filter transform");
+    if (rc != B200CB_OK)
+        return rc;
+    const void* a = diff;
+    if (g.upsample) {
+        const uint32_t row = f.oc * dtype_size(f.dst_dtype);
+        if (row % 16 != 0)
+            return B200CB_ERR_BAD_PLAN;   // (the inner query already demands 16-byte pixels)
+        const uint64_t items = (uint64_t)f.n * g.uh * g.uw * (row / 16);
+        deconv_upsample_kernel<<<grid_for(items, 256), 256, 0, s>>>(
+                static_cast<const uint4*>(diff), static_cast<uint4*>(up), f.n, f.oh, f.ow, g.uh, g.uw, row / 16,
+                f.stride_h, f.stride_w);
+        rc = cuda_rc("deconv upsample");
+        if (rc != B200CB_OK)
+            return rc;
+        a = up;
+    }
+    return b200cb_launch(&inner, a, wt, nullptr, nullptr, grad, inner_ws, inner.workspace_bytes, stream);
+}
+
+// ---- BatchConvBiasForward: per-image filters, one ConvBias launch per image
+int b200cb_batch_convbias_query(const b200cb_desc* desc, b200cb_plan* plan) {
+    if (!desc || !plan)
+        return B200CB_ERR_NULL;
+    b200cb_desc one = *desc;
+    one.n = 1;
+    one.src_batch_stride = one.z_batch_stride = one.dst_batch_stride = 0;
+    const int rc = b200cb_query(&one, plan);
+    if (rc != B200CB_OK)
+        return rc;
+    plan->kernel = KERNEL_BATCH_CONVBIAS;
+    plan->desc = *desc;
+    plan->flops *= desc->n;
+    plan->bytes = plan->bytes * desc->n;
+    return B200CB_OK;
+}
+int b200cb_batch_convbias_launch(
+        const b200cb_plan* plan, const void* src, const void* filter, const void* bias, const void* z, void* dst,
+        void* workspace, size_t ws_bytes, void* stream) {
+    if (!plan || !src || !filter || !dst)
+        return B200CB_ERR_NULL;
+    if (plan->magic != PLAN_MAGIC || plan->kernel != KERNEL_BATCH_CONVBIAS)
+        return B200CB_ERR_BAD_PLAN;
+    const b200cb_desc& d = plan->desc;
+    b200cb_desc one = d;
+    one.n = 1;
+    one.src_batch_stride = one.z_batch_stride = one.dst_batch_stride = 0;
+    b200cb_plan inner;
+    if (b200cb_query_algo(&one, plan->algo, &inner) != B200CB_OK)
+        return B200CB_ERR_BAD_PLAN;
+    const size_t src_img = (d.src_batch_stride ? d.src_batch_stride : (size_t)d.ih * d.iw * d.ic) * dtype_size(d.src_dtype);
+    const size_t dst_img = (d.dst_batch_stride ? d.dst_batch_stride : (size_t)d.oh * d.ow * d.oc) * dtype_size(d.dst_dtype);
+    const size_t z_img = (d.z_batch_stride ? d.z_batch_stride : (size_t)d.oh * d.ow * d.oc) * dtype_size(d.z_dtype);
+    const size_t flt_img = (size_t)d.oc * (d.ic / d.group) * d.fh * d.fw * dtype_size(d.filter_dtype);
+    for (uint32_t i = 0; i < d.n; ++i) {
+        const int rc = b200cb_launch(
+                &inner, static_cast<const uint8_t*>(src) + i * src_img, static_cast<const uint8_t*>(filter) + i * flt_img,
+                bias, z ? static_cast<const uint8_t*>(z) + i * z_img : nullptr, static_cast<uint8_t*>(dst) + i * dst_img,
+                workspace, ws_bytes, stream);
+        if (rc != B200CB_OK)
+            return rc;
+    }
+    return B200CB_OK;
+}
+
+}  // extern "C"

@@ -20,6 +20,7 @@
 #include <vector>
 
 #include "b200cb.h"
+#include "b200cb_nn.h"
 #include "megcore.h"
 #include "megdnn/basic_types.h"
 #include "megdnn/dtype.h"
@@ -262,6 +263,186 @@ int ref_convbias(
         g_err = "unknown exception";
         return 2;
     }
+}
+
+// ---- operators either side of ConvBias (include/b200cb_nn.h), reference's naive implementations
+#define REF_TRY try {
+#define REF_CATCH                          \
+    return 0;                              \
+    }                                      \
+    catch (const std::exception& e) {      \
+        g_err = e.what();                  \
+        return 1;                          \
+    }                                      \
+    catch (...) {                          \
+        g_err = "unknown exception";       \
+        return 2;                          \
+    }
+
+int ref_pooling(const b200cb_pool_desc* d, const void* src, void* dst) {
+    REF_TRY
+    HandleBox* hb = get_handle(2, 1);
+    auto opr = hb->handle->create_operator<PoolingForward>();
+    auto& p = opr->param();
+    p.mode = static_cast<param::Pooling::Mode>(d->mode);
+    p.format = static_cast<param::Pooling::Format>(d->format);
+    p.pad_h = d->pad_h, p.pad_w = d->pad_w, p.stride_h = d->stride_h, p.stride_w = d->stride_w;
+    p.window_h = d->window_h, p.window_w = d->window_w;
+    DType dt = make_dtype(d->dtype, 0.5f);
+    TensorLayout ls, ld;
+    if (d->format == B200CB_FORMAT_NHWC)
+        ls = TensorLayout({d->n, d->ih, d->iw, d->c}, dt);
+    else if (d->format == B200CB_FORMAT_NCHW)
+        ls = TensorLayout({d->n, d->c, d->ih, d->iw}, dt);
+    else
+        ls = TensorLayout({d->n, d->c / 4, d->ih, d->iw, 4}, dt);
+    ld.dtype = dt;
+    opr->deduce_layout(ls, ld);
+    const size_t oh = d->format == B200CB_FORMAT_NHWC ? ld[1] : ld[2], ow = d->format == B200CB_FORMAT_NHWC ? ld[2] : ld[3];
+    if (oh != d->oh || ow != d->ow)
+        throw std::runtime_error("ref_driver: pooling dst shape mismatch, reference deduces " + ld.to_string());
+    size_t ws_size = opr->get_workspace_in_bytes(ls, ld);
+    std::vector<dt_byte> ws(ws_size + 64);
+    opr->exec(TensorND(const_cast<void*>(src), ls), TensorND(dst, ld), Workspace(ws.data(), ws_size));
+    megcoreSynchronize(hb->comp);
+    REF_CATCH
+}
+
+int ref_elemwise(uint32_t mode, uint32_t dtype, uint64_t n, const void* a, const void* b, void* dst) {
+    REF_TRY
+    HandleBox* hb = get_handle(2, 1);
+    auto opr = hb->handle->create_operator<ElemwiseForward>();
+    opr->param().mode = static_cast<param::Elemwise::Mode>(mode);
+    TensorLayout l({(size_t)n}, make_dtype(dtype, 1.f));
+    TensorNDArray in;
+    in.emplace_back(const_cast<void*>(a), l);
+    if (b)
+        in.emplace_back(const_cast<void*>(b), l);
+    opr->exec(in, TensorND(dst, l));
+    megcoreSynchronize(hb->comp);
+    REF_CATCH
+}
+
+int ref_elemwise_q(
+        uint32_t mode, uint64_t n, const void* a, float sa, const void* b, float sb, void* dst, float sd) {
+    REF_TRY
+    HandleBox* hb = get_handle(2, 1);
+    auto opr = hb->handle->create_operator<ElemwiseMultiType>();
+    using M = param::ElemwiseMultiType::Mode;
+    M m;
+    switch (mode) {
+        case B200CB_ELEM_RELU: m = M::QRELU; break;
+        case B200CB_ELEM_ADD: m = M::QADD; break;
+        case B200CB_ELEM_FUSE_ADD_RELU: m = M::QFUSE_ADD_RELU; break;
+        case B200CB_ELEM_H_SWISH: m = M::QH_SWISH; break;
+        default: throw std::runtime_error("ref_driver: bad quantized elemwise mode");
+    }
+    opr->param().mode = m;
+    TensorNDArray in;
+    in.emplace_back(const_cast<void*>(a), TensorLayout({(size_t)n}, dtype::QuantizedS8(sa)));
+    if (b)
+        in.emplace_back(const_cast<void*>(b), TensorLayout({(size_t)n}, dtype::QuantizedS8(sb)));
+    opr->exec(in, TensorND(dst, TensorLayout({(size_t)n}, dtype::QuantizedS8(sd))));
+    megcoreSynchronize(hb->comp);
+    REF_CATCH
+}
+
+int ref_typecvt(uint32_t sdt, float ss, uint32_t ddt, float sd, uint64_t n, const void* src, void* dst) {
+    REF_TRY
+    HandleBox* hb = get_handle(2, 1);
+    auto opr = hb->handle->create_operator<TypeCvt>();
+    opr->exec(
+            TensorND(const_cast<void*>(src), TensorLayout({(size_t)n}, make_dtype(sdt, ss))),
+            TensorND(dst, TensorLayout({(size_t)n}, make_dtype(ddt, sd))));
+    megcoreSynchronize(hb->comp);
+    REF_CATCH
+}
+
+static void fill_conv_param(param::Convolution& p, const b200cb_desc* d) {
+    p.mode = static_cast<param::Convolution::Mode>(d->mode);
+    p.sparse = static_cast<param::Convolution::Sparse>(d->sparse);
+    p.format = static_cast<param::Convolution::Format>(d->format);
+    p.pad_h = d->pad_h, p.pad_w = d->pad_w;
+    p.stride_h = d->stride_h, p.stride_w = d->stride_w;
+    p.dilate_h = d->dilate_h, p.dilate_w = d->dilate_w;
+    p.compute_mode = static_cast<param::Convolution::ComputeMode>(d->compute_mode);
+}
+
+// ConvolutionForward (bias / z / activation fields of the descriptor are ignored)
+int ref_convolution(const b200cb_desc* d, const void* src, const void* filter, void* dst) {
+    REF_TRY
+    HandleBox* hb = get_handle(2, 1);
+    auto opr = hb->handle->create_operator<ConvolutionForward>();
+    fill_conv_param(opr->param(), d);
+    b200cb_desc dd = *d;
+    dd.bias_mode = B200CB_BIAS_NONE, dd.has_z = 0;
+    Layouts l = make_layouts(dd);
+    TensorLayout deduced;
+    deduced.dtype = l.dst.dtype;
+    opr->deduce_layout(l.src, l.flt, deduced);
+    if (!deduced.eq_shape(l.dst))
+        throw std::runtime_error("ref_driver: conv dst shape mismatch, reference deduces " + deduced.to_string());
+    size_t ws_size = opr->get_workspace_in_bytes(l.src, l.flt, l.dst, nullptr);
+    std::vector<dt_byte> ws(ws_size + 64);
+    opr->exec(
+            TensorND(const_cast<void*>(src), l.src), TensorND(const_cast<void*>(filter), l.flt), TensorND(dst, l.dst),
+            nullptr, Workspace(ws.data(), ws_size));
+    megcoreSynchronize(hb->comp);
+    REF_CATCH
+}
+
+// ConvolutionBackwardData: `d` describes the forward convolution (src = grad, dst = diff)
+int ref_deconv(const b200cb_desc* d, const void* filter, const void* diff, void* grad) {
+    REF_TRY
+    HandleBox* hb = get_handle(2, 1);
+    auto opr = hb->handle->create_operator<ConvolutionBackwardData>();
+    fill_conv_param(opr->param(), d);
+    b200cb_desc dd = *d;
+    dd.bias_mode = B200CB_BIAS_NONE, dd.has_z = 0;
+    Layouts l = make_layouts(dd);
+    TensorLayout deduced;
+    deduced.dtype = l.src.dtype;
+    opr->deduce_layout(l.flt, l.dst, deduced);
+    // (deduce_layout gives the smallest grad extent; the forward descriptor may name a larger one)
+    size_t ws_size = opr->get_workspace_in_bytes(l.flt, l.dst, l.src);
+    std::vector<dt_byte> ws(ws_size + 64);
+    opr->exec(
+            TensorND(const_cast<void*>(filter), l.flt), TensorND(const_cast<void*>(diff), l.dst), TensorND(grad, l.src),
+            Workspace(ws.data(), ws_size));
+    megcoreSynchronize(hb->comp);
+    REF_CATCH
+}
+
+// BatchConvBiasForward: filter carries a leading batch dimension
+int ref_batch_convbias(
+        const b200cb_desc* d, const void* src, const void* filter, const void* bias, const void* z, void* dst) {
+    REF_TRY
+    HandleBox* hb = get_handle(2, 1);
+    auto opr = hb->handle->create_operator<BatchConvBiasForward>();
+    auto& p = opr->param();
+    p.nonlineMode = static_cast<param::BatchConvBias::NonlineMode>(d->nonline_mode);
+    p.mode = static_cast<param::BatchConvBias::Mode>(d->mode);
+    p.sparse = static_cast<param::BatchConvBias::Sparse>(d->sparse);
+    p.format = static_cast<param::BatchConvBias::Format>(d->format);
+    p.pad_h = d->pad_h, p.pad_w = d->pad_w, p.stride_h = d->stride_h, p.stride_w = d->stride_w;
+    p.dilate_h = d->dilate_h, p.dilate_w = d->dilate_w;
+    p.compute_mode = static_cast<param::BatchConvBias::ComputeMode>(d->compute_mode);
+    Layouts l = make_layouts(*d);
+    TensorShape fs;
+    fs.ndim = l.flt.ndim + 1;
+    fs[0] = d->n;
+    for (size_t i = 0; i < l.flt.ndim; ++i)
+        fs[i + 1] = l.flt[i];
+    TensorLayout lf(fs, l.flt.dtype);
+    size_t ws_size = opr->get_workspace_in_bytes(l.src, lf, l.bias, l.z, l.dst);
+    std::vector<dt_byte> ws(ws_size + 64);
+    static char dummy[64];
+    opr->exec(
+            TensorND(const_cast<void*>(src), l.src), TensorND(const_cast<void*>(filter), lf),
+            TensorND(bias ? const_cast<void*>(bias) : dummy, l.bias), TensorND(z ? const_cast<void*>(z) : dummy, l.z),
+            TensorND(dst, l.dst), Workspace(ws.data(), ws_size));
+    megcoreSynchronize(hb->comp);
+    REF_CATCH
 }
 
 int ref_hardware_threads(void) {

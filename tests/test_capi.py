@@ -14,8 +14,8 @@ from . import _cases as K
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def declared_symbols():
-    text = open(os.path.join(ROOT, "include", "b200cb.h")).read()
+def declared_symbols(header="b200cb.h"):
+    text = open(os.path.join(ROOT, "include", header)).read()
     text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
     return sorted(set(re.findall(r"\b(b200cb_[a-z_0-9]+)\s*\(", text)))
 
@@ -26,6 +26,11 @@ def test_library_exports_every_declared_symbol(lib):
     for s in syms:
         assert hasattr(lib, s), "libb200cb.so does not export " + s
     assert sorted(n for n, _r, _a in C.SYMBOLS) == syms, "ctypes binding and header disagree"
+    nn = declared_symbols("b200cb_nn.h")
+    assert len(nn) >= 10
+    for s in nn:
+        assert hasattr(lib, s), "libb200cb.so does not export " + s
+    assert sorted(n for n, _r, _a in C.NN_SYMBOLS) == nn, "ctypes binding and b200cb_nn.h disagree"
 
 
 def test_struct_sizes_match_header(lib):
