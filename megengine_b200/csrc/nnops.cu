@@ -35,21 +35,12 @@ struct Elem<B200CB_DT_F32> {
 // HALF_ROUND_TIES_TO_EVEN 0): to nearest, TIES AWAY FROM ZERO.  Sums of two fp16 values tie all the time, so the
 // pooling / elementwise results are bit-exact only with this rounding (cvt.rn.f16.f32 breaks ties to even).
 __device__ __forceinline__ __half f2h_ties_away(float v) {
+    // cvt.rn breaks ties to even; setting the lowest fp32 mantissa bit moves an exact tie (dropped bits 100..0)
+    // just past the midpoint -- away from zero -- and cannot move any other value across a rounding boundary
+    // (dropped bits d != tie: d | 1 stays on d's side of the tie).  Infinities keep their bits.
     const uint32_t bits = __float_as_uint(v);
-    const uint32_t sign = (bits >> 16) & 0x8000u, e = (bits >> 23) & 0xffu, m = bits & 0x7fffffu;
-    uint32_t h;
-    if (e == 255)
-        h = 0x7c00u + (m >> 13);             // inf / nan
-    else if (e > 142)
-        h = 0x7c00u;                          // overflow
-    else if (e >= 113)
-        h = ((e - 112) << 10) + (m >> 13) + ((m >> 12) & 1u);   // normal: add the first dropped bit
-    else if (e >= 103) {
-        const uint32_t shift = 126 - e;       // subnormal result
-        h = (0x0400u >> (113 - e)) + (m >> shift) + ((m >> (shift - 1)) & 1u);
-    } else
-        h = e == 102 ? 1u : 0u;
-    return __ushort_as_half(static_cast<unsigned short>(sign | h));
+    const uint32_t finite = (bits & 0x7f800000u) != 0x7f800000u;
+    return __float2half_rn(__uint_as_float(bits | finite));
 }
 template <>
 struct Elem<B200CB_DT_F16> {
@@ -76,7 +67,7 @@ __device__ __forceinline__ float rnd(float v) {
 }
 
 template <typename T, int V>
-struct alignas(sizeof(T) * V) Vec {
+struct alignas(sizeof(T) * V > 16 ? 16 : sizeof(T) * V) Vec {
     T v[V];
 };
 
@@ -92,92 +83,144 @@ struct PoolParams {
     uint32_t cg;          // channel groups of V elements a thread handles (NHWC: c / V, NCHW4: c / 4, NCHW: c)
     uint32_t layout;      // 0 NHWC (pixel pitch c), 1 NCHW (planes), 2 NCHW4 (planes of 4-channel pixels)
     float count_all;      // window_h * window_w rounded to the element type (MeanIncludePooler::count)
+    uint32_t tpr;         // threads per output row (power of two <= 256)
 };
 
-// one thread = one output pixel x V consecutive channels
+// lane-wise maximum of two packed words of the element type (MaxPooler: answer > x ? answer : x; NaN inputs aside)
+template <int DT>
+__device__ __forceinline__ uint32_t packed_max(uint32_t a, uint32_t b) {
+    if constexpr (DT == B200CB_DT_QS8) {
+        return __vmaxs4(a, b);
+    } else if constexpr (DT == B200CB_DT_F16) {
+        uint32_t r;
+        asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+        return r;
+    } else if constexpr (DT == B200CB_DT_BF16) {
+        uint32_t r;
+        asm("max.bf16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+        return r;
+    } else {
+        return __float_as_uint(fmaxf(__uint_as_float(a), __uint_as_float(b)));
+    }
+}
+
+// one thread = one output pixel x V consecutive channels.  Work item = (output row, position in the row): 32-bit
+// index arithmetic, the valid part of the window computed once (no bounds test per tap), loads of a window row
+// issued together.
 template <int DT, int MODE, int V>
 __global__ void __launch_bounds__(256) pool_kernel(
         const typename Elem<DT>::T* __restrict__ src, typename Elem<DT>::T* __restrict__ dst, PoolParams p) {
     using T = typename Elem<DT>::T;
-    const uint64_t total = (uint64_t)p.n * p.oh * p.ow * p.cg;
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
-        uint32_t g, ow, oh, n;
-        if (p.layout == 0) {   // NHWC: channel groups fastest
-            g = i % p.cg;
-            ow = (i / p.cg) % p.ow;
-            oh = (i / ((uint64_t)p.cg * p.ow)) % p.oh;
-            n = i / ((uint64_t)p.cg * p.ow * p.oh);
-        } else {               // planes: pixels fastest
-            ow = i % p.ow;
-            oh = (i / p.ow) % p.oh;
-            g = (i / ((uint64_t)p.ow * p.oh)) % p.cg;
-            n = i / ((uint64_t)p.ow * p.oh * p.cg);
-        }
-        const T* sb;
-        T* db;
-        uint64_t pitch;   // elements between horizontally adjacent pixels
-        if (p.layout == 0) {
-            sb = src + (uint64_t)n * p.ih * p.iw * p.c + (uint64_t)g * V;
-            db = dst + (((uint64_t)n * p.oh + oh) * p.ow + ow) * p.c + (uint64_t)g * V;
-            pitch = p.c;
-        } else {
-            sb = src + ((uint64_t)n * p.cg + g) * p.ih * p.iw * V;
-            db = dst + (((uint64_t)n * p.cg + g) * p.oh * p.ow + (uint64_t)oh * p.ow + ow) * V;
-            pitch = V;
-        }
-        float acc[V];
-        int32_t iacc[V];
+    const uint32_t row_items = p.layout == 0 ? p.ow * p.cg : p.ow;   // items of one output row (NHWC) / one plane row
+    const uint32_t rows = p.layout == 0 ? p.n * p.oh : p.n * p.cg * p.oh;
+    const uint32_t per_block = blockDim.x / p.tpr * 1u;           // rows a block handles at once (tpr threads per row)
+    for (uint32_t r0 = blockIdx.x * per_block; r0 < rows; r0 += gridDim.x * per_block) {
+        const uint32_t r = r0 + threadIdx.x / p.tpr;
+        if (r >= rows)
+            continue;
+        for (uint32_t it = threadIdx.x % p.tpr; it < row_items; it += p.tpr) {
+            uint32_t g, ow, oh, n;
+            const T* sb;
+            T* db;
+            uint32_t pitch;   // elements between horizontally adjacent pixels
+            if (p.layout == 0) {   // NHWC: channel groups fastest
+                g = it % p.cg, ow = it / p.cg;
+                oh = r % p.oh, n = r / p.oh;
+                sb = src + (size_t)n * p.ih * p.iw * p.c + (size_t)g * V;
+                db = dst + ((size_t)r * p.ow + ow) * p.c + (size_t)g * V;
+                pitch = p.c;
+            } else {               // planes: pixels fastest
+                ow = it, oh = r % p.oh;
+                const uint32_t plane = r / p.oh;   // n * cg + g
+                sb = src + (size_t)plane * p.ih * p.iw * V;
+                db = dst + ((size_t)r * p.ow + ow) * V;
+                pitch = V;
+            }
+            // valid taps: ih = oh * sh - ph + fh in [0, ih)
+            const int32_t h0 = (int32_t)(oh * p.sh) - (int32_t)p.ph, w0 = (int32_t)(ow * p.sw) - (int32_t)p.pw;
+            const uint32_t fh_lo = h0 < 0 ? (uint32_t)-h0 : 0u, fw_lo = w0 < 0 ? (uint32_t)-w0 : 0u;
+            const uint32_t fh_hi = min(p.wh, p.ih - (uint32_t)min(h0, (int32_t)p.ih)), fw_hi = min(p.ww, p.iw - (uint32_t)min(w0, (int32_t)p.iw));
+            constexpr bool WORDS = MODE == B200CB_POOL_MAX && sizeof(T) * V >= 4;   // packed maxima on 32-bit words
+            constexpr int NW = WORDS ? (int)(sizeof(T) * V / 4) : 1;
+            uint32_t wacc[NW];
+            float acc[V];
+            int32_t iacc[V];
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-            acc[k] = MODE == B200CB_POOL_MAX ? (DT == B200CB_DT_QS8 ? -128.f : (DT == B200CB_DT_F16 ? -65504.f : -FLT_MAX)) : 0.f;
-            iacc[k] = 0;
-        }
-        if (DT == B200CB_DT_BF16 && MODE == B200CB_POOL_MAX) {
+            for (int k = 0; k < V; ++k) {
+                acc[k] = MODE == B200CB_POOL_MAX ? (DT == B200CB_DT_QS8 ? -128.f : (DT == B200CB_DT_F16 ? -65504.f : -FLT_MAX)) : 0.f;
+                iacc[k] = 0;
+            }
+            if (DT == B200CB_DT_BF16 && MODE == B200CB_POOL_MAX) {
 #pragma unroll
-            for (int k = 0; k < V; ++k)
-                acc[k] = __uint_as_float(0xff7f0000u);   // bfloat16 lowest
-        }
-        uint32_t cnt = 0;
-        for (uint32_t fh = 0; fh < p.wh; ++fh) {
-            const uint32_t ih = oh * p.sh + fh - p.ph;   // unsigned wrap == the reference's size_t arithmetic
-            if (ih >= p.ih)
-                continue;
-            for (uint32_t fw = 0; fw < p.ww; ++fw) {
-                const uint32_t iw = ow * p.sw + fw - p.pw;
-                if (iw >= p.iw)
-                    continue;
-                const Vec<T, V> x = *reinterpret_cast<const Vec<T, V>*>(sb + ((uint64_t)ih * p.iw + iw) * pitch);
-                ++cnt;
+                for (int k = 0; k < V; ++k)
+                    acc[k] = __uint_as_float(0xff7f0000u);   // bfloat16 lowest
+            }
 #pragma unroll
-                for (int k = 0; k < V; ++k) {
-                    if constexpr (MODE == B200CB_POOL_MAX) {
-                        const float xv = Elem<DT>::ld(x.v[k]);
-                        acc[k] = acc[k] > xv ? acc[k] : xv;
-                    } else if constexpr (DT == B200CB_DT_QS8) {
-                        iacc[k] += x.v[k];
-                    } else {
-                        acc[k] = rnd<DT>(__fadd_rn(acc[k], Elem<DT>::ld(x.v[k])));   // sum lives in the element type
-                    }
+            for (int k = 0; k < NW; ++k)   // the lowest value of the element type in every lane
+                wacc[k] = DT == B200CB_DT_QS8 ? 0x80808080u : DT == B200CB_DT_F16 ? 0xfbfffbffu : DT == B200CB_DT_BF16 ? 0xff7fff7fu : 0xff7fffffu;
+#define B200CB_POOL_FEED(X_)                                                                               \
+    do {                                                                                                   \
+        if constexpr (WORDS) {                                                                             \
+            const uint32_t* xw__ = reinterpret_cast<const uint32_t*>(&(X_));                               \
+            _Pragma("unroll") for (int k = 0; k < NW; ++k) wacc[k] = packed_max<DT>(wacc[k], xw__[k]);     \
+        } else {                                                                                           \
+            _Pragma("unroll") for (int k = 0; k < V; ++k) {                                                \
+                if constexpr (MODE == B200CB_POOL_MAX) {                                                   \
+                    const float xv__ = Elem<DT>::ld((X_).v[k]);                                            \
+                    acc[k] = acc[k] > xv__ ? acc[k] : xv__;                                                \
+                } else if constexpr (DT == B200CB_DT_QS8) {                                                \
+                    iacc[k] += (X_).v[k];                                                                  \
+                } else {                                                                                   \
+                    acc[k] = rnd<DT>(__fadd_rn(acc[k], Elem<DT>::ld((X_).v[k])));                          \
+                }                                                                                          \
+            }                                                                                              \
+        }                                                                                                  \
+    } while (0)
+            for (uint32_t fh = fh_lo; fh < fh_hi; ++fh) {
+                const T* rowp = sb + ((size_t)(h0 + (int32_t)fh) * p.iw + w0) * pitch;
+                uint32_t fw = fw_lo;
+                for (; fw + 3 <= fw_hi; fw += 3) {   // three independent loads in flight, fed in tap order
+                    const Vec<T, V> x0 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)fw * pitch);
+                    const Vec<T, V> x1 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)(fw + 1) * pitch);
+                    const Vec<T, V> x2 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)(fw + 2) * pitch);
+                    B200CB_POOL_FEED(x0);
+                    B200CB_POOL_FEED(x1);
+                    B200CB_POOL_FEED(x2);
+                }
+                for (; fw < fw_hi; ++fw) {
+                    const Vec<T, V> x0 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)fw * pitch);
+                    B200CB_POOL_FEED(x0);
                 }
             }
-        }
-        Vec<T, V> o;
+#undef B200CB_POOL_FEED
+            if constexpr (WORDS) {
+                Vec<T, V> o;
+                uint32_t* ow__ = reinterpret_cast<uint32_t*>(&o);
 #pragma unroll
-        for (int k = 0; k < V; ++k) {
-            float r;
-            if constexpr (MODE == B200CB_POOL_MAX) {
-                r = acc[k];
-            } else if constexpr (DT == B200CB_DT_QS8) {
-                // T(std::round(float(sum) / count)): count is the window size (include) or the fed count
-                const float c = MODE == B200CB_POOL_AVERAGE ? static_cast<float>(p.wh * p.ww) : static_cast<float>(cnt);
-                r = roundf(__fdiv_rn(static_cast<float>(iacc[k]), c));
-            } else {
-                const float c = MODE == B200CB_POOL_AVERAGE ? p.count_all : rnd<DT>(static_cast<float>(cnt));
-                r = __fdiv_rn(acc[k], c);
+                for (int k = 0; k < NW; ++k)
+                    ow__[k] = wacc[k];
+                *reinterpret_cast<Vec<T, V>*>(db) = o;
+                continue;
             }
-            o.v[k] = Elem<DT>::st(r);
+            const uint32_t cnt = (fh_hi - fh_lo) * (fw_hi - fw_lo);
+            Vec<T, V> o;
+#pragma unroll
+            for (int k = 0; k < V; ++k) {
+                float rr;
+                if constexpr (MODE == B200CB_POOL_MAX) {
+                    rr = acc[k];
+                } else if constexpr (DT == B200CB_DT_QS8) {
+                    // T(std::round(float(sum) / count)): count is the window size (include) or the fed count
+                    const float c = MODE == B200CB_POOL_AVERAGE ? static_cast<float>(p.wh * p.ww) : static_cast<float>(cnt);
+                    rr = roundf(__fdiv_rn(static_cast<float>(iacc[k]), c));
+                } else {
+                    const float c = MODE == B200CB_POOL_AVERAGE ? p.count_all : rnd<DT>(static_cast<float>(cnt));
+                    rr = __fdiv_rn(acc[k], c);
+                }
+                o.v[k] = Elem<DT>::st(rr);
+            }
+            *reinterpret_cast<Vec<T, V>*>(db) = o;
         }
-        *reinterpret_cast<Vec<T, V>*>(db) = o;
     }
 }
 
@@ -204,8 +247,14 @@ int pool_launch_v(const b200cb_pool_desc& d, const void* src, void* dst, cudaStr
         v = 4;
     }
     p.cg = d.c / v;
-    const uint64_t items = (uint64_t)d.n * d.oh * d.ow * p.cg;
-    const uint32_t grid = grid_for(items, 256);
+    const uint32_t row_items = p.layout == 0 ? d.ow * p.cg : d.ow;
+    p.tpr = 256;
+    while (p.tpr > 4 && p.tpr / 2 >= row_items)
+        p.tpr /= 2;
+    const uint64_t rows = p.layout == 0 ? (uint64_t)d.n * d.oh : (uint64_t)d.n * p.cg * d.oh;
+    if (rows > 0x7fffffffull || (uint64_t)row_items > 0x7fffffffull)
+        return B200CB_UNSUPPORTED_SHAPE;
+    const uint32_t grid = grid_for(rows * p.tpr, 256);
     const T* s = static_cast<const T*>(src);
     T* o = static_cast<T*>(dst);
     switch (v) {
@@ -294,17 +343,28 @@ __device__ __forceinline__ float q_apply(uint32_t mode, float x, float y) {
 __global__ void __launch_bounds__(256) elemwise_q_kernel(
         uint32_t mode, bool binary, uint64_t nvec, uint64_t n, const int8_t* __restrict__ a, float sa,
         const int8_t* __restrict__ b, float sb, int8_t* __restrict__ dst, RequantParams rq) {
+    // fast_div == 2 (host-proven finite quotients): the conversion-free sequence of the ConvBias epilogue
+    // (epilogue.cuh) -- bytes to float through PRMT, unguarded Markstein division, magic-number rounding
+    const bool fast = rq.fast_div == 2;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
-        const Vec<int8_t, 16> x = reinterpret_cast<const Vec<int8_t, 16>*>(a)[i];
-        Vec<int8_t, 16> y = x, o;
-        if (binary)
-            y = reinterpret_cast<const Vec<int8_t, 16>*>(b)[i];
+        const uint4 xv = reinterpret_cast<const uint4*>(a)[i];
+        const uint4 yv = binary ? reinterpret_cast<const uint4*>(b)[i] : xv;
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w}, yw[4] = {yv.x, yv.y, yv.z, yv.w};
+        uint32_t ow[4];
 #pragma unroll
-        for (int k = 0; k < 16; ++k) {
-            const float r = q_apply(mode, __fmul_rn((float)x.v[k], sa), __fmul_rn((float)y.v[k], sb));
-            o.v[k] = (int8_t)quant_s8(r, rq);
+        for (int w = 0; w < 4; ++w) {
+            const uint32_t xx = xw[w] ^ 0x80808080u, yy = yw[w] ^ 0x80808080u;
+            float xf[4] = {s8_to_float<0>(xx), s8_to_float<1>(xx), s8_to_float<2>(xx), s8_to_float<3>(xx)};
+            float yf[4] = {s8_to_float<0>(yy), s8_to_float<1>(yy), s8_to_float<2>(yy), s8_to_float<3>(yy)};
+            uint32_t ub[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const float r = q_apply(mode, __fmul_rn(xf[k], sa), __fmul_rn(yf[k], sb));
+                ub[k] = fast ? round_sat_s8_signed(div_by_scale_noguard(r, rq)) : static_cast<uint32_t>(quant_s8(r, rq));
+            }
+            ow[w] = pack_low_bytes(ub[0], ub[1], ub[2], ub[3]);
         }
-        reinterpret_cast<Vec<int8_t, 16>*>(dst)[i] = o;
+        reinterpret_cast<uint4*>(dst)[i] = make_uint4(ow[0], ow[1], ow[2], ow[3]);
     }
     if (blockIdx.x == 0 && threadIdx.x < n - nvec * 16) {
         const uint64_t i = nvec * 16 + threadIdx.x;
@@ -325,27 +385,43 @@ struct Raw<B200CB_DT_QS32> {
     using T = int32_t;
 };
 template <int SDT, int DDT>
+__device__ __forceinline__ typename Raw<DDT>::T cvt_one(typename Raw<SDT>::T x, float s_src, const RequantParams& rq) {
+    float v;
+    if constexpr (SDT == B200CB_DT_QS8 || SDT == B200CB_DT_QS32)
+        v = __fmul_rn(static_cast<float>(x), s_src);
+    else
+        v = Elem<SDT>::ld(x);
+    if constexpr (DDT == B200CB_DT_QS8) {
+        return (int8_t)quant_s8(v, rq);
+    } else if constexpr (DDT == B200CB_DT_QS32) {
+        float q = roundf(__fdiv_rn(v, rq.s_dst));
+        q = fminf(fmaxf(-2147483648.f, q), 2147483520.f);
+        return static_cast<int32_t>(q);
+    } else {
+        return Elem<DDT>::st(v);
+    }
+}
+// E elements per thread: 16 bytes of the narrower side per access
+template <int SDT, int DDT>
 __global__ void __launch_bounds__(256) typecvt_kernel(
         uint64_t n, const void* __restrict__ src_, void* __restrict__ dst_, float s_src, RequantParams rq) {
     using ST = typename Raw<SDT>::T;
     using DT_ = typename Raw<DDT>::T;
+    constexpr int E = 16 / (int)(sizeof(ST) < sizeof(DT_) ? sizeof(ST) : sizeof(DT_));
     const ST* src = static_cast<const ST*>(src_);
     DT_* dst = static_cast<DT_*>(dst_);
-    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) {
-        float v;
-        if constexpr (SDT == B200CB_DT_QS8 || SDT == B200CB_DT_QS32)
-            v = __fmul_rn(static_cast<float>(src[i]), s_src);
-        else
-            v = Elem<SDT>::ld(src[i]);
-        if constexpr (DDT == B200CB_DT_QS8) {
-            dst[i] = (int8_t)quant_s8(v, rq);
-        } else if constexpr (DDT == B200CB_DT_QS32) {
-            float q = roundf(__fdiv_rn(v, rq.s_dst));
-            q = fminf(fmaxf(-2147483648.f, q), 2147483520.f);
-            dst[i] = static_cast<int32_t>(q);
-        } else {
-            dst[i] = Elem<DDT>::st(v);
-        }
+    const uint64_t nvec = n / E;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
+        const Vec<ST, E> x = reinterpret_cast<const Vec<ST, E>*>(src)[i];
+        Vec<DT_, E> o;
+#pragma unroll
+        for (int k = 0; k < E; ++k)
+            o.v[k] = cvt_one<SDT, DDT>(x.v[k], s_src, rq);
+        reinterpret_cast<Vec<DT_, E>*>(dst)[i] = o;
+    }
+    if (blockIdx.x == 0 && threadIdx.x < n - nvec * E) {
+        const uint64_t i = nvec * E + threadIdx.x;
+        dst[i] = cvt_one<SDT, DDT>(src[i], s_src, rq);
     }
 }
 
@@ -519,8 +595,12 @@ int b200cb_elemwise_q(
     memset(&t, 0, sizeof(t));
     t.dst_scale = sd, t.src_scale = t.filter_scale = 1.f, t.bias_dtype = B200CB_DT_NONE;
     RequantParams rq = make_requant(t);
-    if (rq.fast_div == 2)
-        rq.fast_div = 1;   // the guarded division: dividends here are not bounded by an accumulator range
+    if (rq.fast_div) {
+        // |op(a * sa, b * sb)| <= 128 (|sa| + |sb|) (RELU / H_SWISH do not amplify): the unguarded division is
+        // exact whenever that bound over s_dst stays far below overflow (the test of make_requant)
+        const double rmax = 128.0 * (fabs((double)sa) + fabs((double)sb));
+        rq.fast_div = (isfinite(rmax) && rmax * (double)rq.inv_dst < 1152921504606846976.0) ? 2u : 1u;
+    }
     const uint64_t nvec = n / 16;
     elemwise_q_kernel<<<grid_for(nvec ? nvec : 1, 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
             mode, binary, nvec, n, static_cast<const int8_t*>(a), sa, static_cast<const int8_t*>(b), sb,
@@ -541,7 +621,7 @@ int b200cb_typecvt(
     if (rq.fast_div == 2)
         rq.fast_div = 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const uint32_t grid = grid_for(n, 256);
+    const uint32_t grid = grid_for(n / 4 + 1, 256);
 #define CVT(S_, D_)                                                                      \
     if (sdt == S_ && ddt == D_) {                                                        \
         typecvt_kernel<S_, D_><<<grid, 256, 0, s>>>(n, src, dst, s_src, rq);             \
