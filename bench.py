@@ -831,6 +831,9 @@ def main():
                 sys.stderr.write("bench.py: PARITY FAILED (qs8): %s\n" % json.dumps(p8r)[:4000])
                 sys.exit(1)
         extra.update(layer_tables(peaks))
+        # the operators either side of ConvBias (include/b200cb_nn.h), L2-cold
+        from tools import bench_nn
+        extra["adjacent_ops"] = bench_nn.run(peaks["hbm_gbs"])
         extra["layers_bf16"] = [{k: r[k] for k in ("name", "algo", "count", "ms", "tflops", "gbs", "bound", "frac_of_floor")}
                                 for r in rows]
 
