@@ -425,6 +425,9 @@ __global__ void __launch_bounds__(256) typecvt_kernel(
     }
 }
 
+inline size_t al256(size_t v) {
+    return (v + 255) & ~size_t(255);
+}
 // ---------------------------------------------------------------- deconvolution helpers
 // KRSC filter (OC, FH, FW, IC) -> (IC, FH, FW, OC), spatially flipped: the filter of the stride-1 convolution
 // over diff that equals the data gradient
@@ -456,10 +459,99 @@ __global__ void deconv_upsample_kernel(
     }
 }
 
-constexpr uint32_t KERNEL_DECONV = 16, KERNEL_BATCH_CONVBIAS = 17;
-inline size_t al256(size_t v) {
-    return (v + 255) & ~size_t(255);
+// ---- stride > 1 (dilation 1): phase decomposition.  Grad rows ih with (ih + pad) % s == a only receive filter rows
+// fh = a + s*j, so each of the s*s phases is a dense stride-1 correlation of diff with a J_a x J_b sub-filter
+// (J_a = ceil((F - a) / s)), written to a temporary (OH + J_a - 1) x (OW + J_b - 1) image; one interleave pass
+// scatters the temporaries into grad.  No multiply by an inserted zero is ever issued.
+struct PhaseGeom {
+    uint32_t s_h, s_w, nph;            // phases = s_h * s_w (<= 16)
+    uint32_t jh[4], jw[4];             // taps per phase along h / w (0: the phase receives nothing)
+    uint32_t th[4], tw[4];             // temporary extent per phase
+    size_t flt_off[16], tmp_off[16];   // workspace offsets
+    size_t flt_total, tmp_total;
+    b200cb_desc inner[16];
+};
+int phase_geometry(const b200cb_desc& f, PhaseGeom* g) {
+    if (f.stride_h > 4 || f.stride_w > 4 || f.dilate_h != 1 || f.dilate_w != 1)
+        return B200CB_UNSUPPORTED_PARAM;
+    g->s_h = f.stride_h, g->s_w = f.stride_w, g->nph = f.stride_h * f.stride_w;
+    for (uint32_t a = 0; a < f.stride_h; ++a) {
+        g->jh[a] = a < f.fh ? (f.fh - a + f.stride_h - 1) / f.stride_h : 0;
+        g->th[a] = g->jh[a] ? f.oh + g->jh[a] - 1 : 0;
+    }
+    for (uint32_t b = 0; b < f.stride_w; ++b) {
+        g->jw[b] = b < f.fw ? (f.fw - b + f.stride_w - 1) / f.stride_w : 0;
+        g->tw[b] = g->jw[b] ? f.ow + g->jw[b] - 1 : 0;
+    }
+    size_t fo = 0, to = 0;
+    for (uint32_t a = 0; a < f.stride_h; ++a)
+        for (uint32_t b = 0; b < f.stride_w; ++b) {
+            const uint32_t ph = a * f.stride_w + b;
+            g->flt_off[ph] = fo, g->tmp_off[ph] = to;
+            b200cb_desc& e = g->inner[ph];
+            memset(&e, 0, sizeof(e));
+            if (!g->jh[a] || !g->jw[b])
+                continue;
+            e.format = B200CB_FORMAT_NHWC, e.sparse = B200CB_SPARSE_DENSE, e.mode = B200CB_MODE_CROSS_CORRELATION;
+            e.nonline_mode = B200CB_NL_IDENTITY, e.compute_mode = f.compute_mode, e.bias_mode = B200CB_BIAS_NONE;
+            e.src_dtype = f.dst_dtype, e.filter_dtype = f.filter_dtype, e.dst_dtype = f.src_dtype;
+            e.bias_dtype = e.z_dtype = B200CB_DT_NONE;
+            e.src_scale = f.dst_scale, e.filter_scale = f.filter_scale, e.dst_scale = f.src_scale;
+            e.n = f.n, e.ic = f.oc, e.ih = f.oh, e.iw = f.ow, e.oc = f.ic, e.oh = g->th[a], e.ow = g->tw[b];
+            e.fh = g->jh[a], e.fw = g->jw[b], e.group = 1;
+            e.pad_h = g->jh[a] - 1, e.pad_w = g->jw[b] - 1, e.stride_h = e.stride_w = 1, e.dilate_h = e.dilate_w = 1;
+            fo += al256((size_t)f.oc * g->jh[a] * g->jw[b] * f.ic * dtype_size(f.filter_dtype));
+            to += al256((size_t)f.n * g->th[a] * g->tw[b] * f.ic * dtype_size(f.src_dtype));
+        }
+    g->flt_total = fo, g->tmp_total = to;
+    return B200CB_OK;
 }
+// sub-filter of phase (a, b): k[ic][jh'][jw'][oc] = w_eff[oc][a + s_h (J_a - 1 - jh')][b + s_w (J_b - 1 - jw')][ic],
+// w_eff = w (CROSS_CORRELATION) or w spatially flipped (CONVOLUTION)
+template <typename T>
+__global__ void deconv_phase_filter_kernel(
+        const T* __restrict__ w, T* __restrict__ o, uint32_t OC, uint32_t FH, uint32_t FW, uint32_t IC, uint32_t a,
+        uint32_t b, uint32_t sh, uint32_t sw, uint32_t JH, uint32_t JW, uint32_t flip) {
+    const uint64_t total = (uint64_t)IC * JH * JW * OC;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t oc = i % OC;
+        const uint32_t jw = (i / OC) % JW;
+        const uint32_t jh = (i / ((uint64_t)OC * JW)) % JH;
+        const uint32_t ic = i / ((uint64_t)OC * JW * JH);
+        uint32_t fh = a + sh * (JH - 1 - jh), fw = b + sw * (JW - 1 - jw);
+        if (flip)
+            fh = FH - 1 - fh, fw = FW - 1 - fw;
+        o[i] = w[(((uint64_t)oc * FH + fh) * FW + fw) * IC + ic];
+    }
+}
+struct PhasePtrs {
+    const uint4* tmp[16];
+    uint32_t th[4], tw[4];
+};
+// grad[n, ih, iw, :] = temporary of phase ((ih + p) % s_h, (iw + p) % s_w) at ((ih + p) / s_h, (iw + p) / s_w);
+// rows / columns no diff element reaches (beyond the temporary) are zero
+__global__ void deconv_interleave_kernel(
+        PhasePtrs pp, uint4* __restrict__ grad, uint32_t N, uint32_t IH, uint32_t IW, uint32_t cv, uint32_t sh,
+        uint32_t sw, uint32_t ph, uint32_t pw) {
+    const uint64_t total = (uint64_t)N * IH * IW * cv;
+    for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = i % cv;
+        const uint32_t iw = (i / cv) % IW;
+        const uint32_t ih = (i / ((uint64_t)cv * IW)) % IH;
+        const uint32_t n = i / ((uint64_t)cv * IW * IH);
+        const uint32_t a = (ih + ph) % sh, y = (ih + ph) / sh, b = (iw + pw) % sw, x = (iw + pw) / sw;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (y < pp.th[a] && x < pp.tw[b])
+            v = pp.tmp[a * sw + b][(((uint64_t)n * pp.th[a] + y) * pp.tw[b] + x) * cv + c];
+        grad[i] = v;
+    }
+}
+bool use_phases(const b200cb_desc& f) {
+    return (f.stride_h > 1 || f.stride_w > 1) && f.dilate_h == 1 && f.dilate_w == 1 && f.stride_h <= 4 && f.stride_w <= 4 &&
+           (f.ic * dtype_size(f.src_dtype)) % 16 == 0;
+}
+
+constexpr uint32_t KERNEL_DECONV = 16, KERNEL_BATCH_CONVBIAS = 17;
 
 struct DeconvGeom {
     b200cb_desc inner;       // the stride-1 forward convolution over (upsampled) diff
@@ -668,14 +760,36 @@ int b200cb_deconv_query(const b200cb_desc* fwd, b200cb_plan* plan) {
     if (rc != B200CB_OK)
         return rc;
     b200cb_plan inner;
-    rc = b200cb_query(&g.inner, &inner);
-    if (rc != B200CB_OK)
-        return rc;
+    uint64_t ws = 0;
+    bool phases = use_phases(*fwd);
+    if (phases) {
+        PhaseGeom pg;
+        if (phase_geometry(*fwd, &pg) != B200CB_OK)
+            phases = false;
+        uint64_t inner_ws = 0;
+        for (uint32_t ph = 0; phases && ph < pg.nph; ++ph) {
+            if (!pg.inner[ph].n)
+                continue;
+            if (b200cb_query(&pg.inner[ph], &inner) != B200CB_OK)
+                phases = false;   // (a phase the ConvBias kernels reject: fall back to the zero-upsampled form)
+            else
+                inner_ws = inner.workspace_bytes > inner_ws ? inner.workspace_bytes : inner_ws;
+        }
+        if (phases)
+            ws = pg.flt_total + pg.tmp_total + inner_ws;
+    }
+    if (!phases) {
+        rc = b200cb_query(&g.inner, &inner);
+        if (rc != B200CB_OK)
+            return rc;
+        ws = g.flt_bytes + g.up_bytes + inner.workspace_bytes;
+    }
     *plan = inner;
     plan->kernel = KERNEL_DECONV;
     plan->desc = *fwd;
-    plan->workspace_bytes = g.flt_bytes + g.up_bytes + inner.workspace_bytes;
-    // accounting of the gradient itself: the zero taps of the upsampled convolution are not useful work
+    plan->workspace_bytes = ws;
+    plan->reserved[0] = phases ? 1u : 0u;
+    // accounting of the gradient itself
     plan->flops = 2ull * fwd->n * fwd->oc * fwd->oh * fwd->ow * fwd->ic * fwd->fh * fwd->fw;
     plan->bytes = (uint64_t)fwd->n * fwd->oh * fwd->ow * fwd->oc * dtype_size(fwd->dst_dtype) +
                   (uint64_t)fwd->oc * fwd->fh * fwd->fw * fwd->ic * dtype_size(fwd->filter_dtype) +
@@ -694,6 +808,57 @@ int b200cb_deconv_launch(
     if (deconv_geometry(f, &g) != B200CB_OK)
         return B200CB_ERR_BAD_PLAN;
     b200cb_plan inner;
+    if (plan->reserved[0] == 1) {
+        PhaseGeom pg;
+        if (phase_geometry(f, &pg) != B200CB_OK || !workspace || ws_bytes < plan->workspace_bytes)
+            return pg.nph ? B200CB_ERR_WORKSPACE : B200CB_ERR_BAD_PLAN;
+        cudaStream_t s = static_cast<cudaStream_t>(stream);
+        uint8_t* ws = static_cast<uint8_t*>(workspace);
+        uint8_t* inner_ws = ws + pg.flt_total + pg.tmp_total;
+        const uint32_t es = dtype_size(f.filter_dtype);
+        PhasePtrs pp;
+        memset(&pp, 0, sizeof(pp));
+        for (uint32_t a = 0; a < pg.s_h; ++a)
+            pp.th[a] = pg.th[a];
+        for (uint32_t b = 0; b < pg.s_w; ++b)
+            pp.tw[b] = pg.tw[b];
+        for (uint32_t a = 0; a < pg.s_h; ++a)
+            for (uint32_t b = 0; b < pg.s_w; ++b) {
+                const uint32_t ph = a * pg.s_w + b;
+                if (!pg.inner[ph].n)
+                    continue;
+                void* k = ws + pg.flt_off[ph];
+                void* t = ws + pg.flt_total + pg.tmp_off[ph];
+                pp.tmp[ph] = static_cast<const uint4*>(t);
+                const uint64_t fl = (uint64_t)f.oc * pg.jh[a] * pg.jw[b] * f.ic;
+                const uint32_t flip = f.mode == B200CB_MODE_CONVOLUTION;
+                if (es == 1)
+                    deconv_phase_filter_kernel<uint8_t><<<grid_for(fl, 256), 256, 0, s>>>(
+                            static_cast<const uint8_t*>(filter), static_cast<uint8_t*>(k), f.oc, f.fh, f.fw, f.ic, a, b,
+                            pg.s_h, pg.s_w, pg.jh[a], pg.jw[b], flip);
+                else if (es == 2)
+                    deconv_phase_filter_kernel<uint16_t><<<grid_for(fl, 256), 256, 0, s>>>(
+                            static_cast<const uint16_t*>(filter), static_cast<uint16_t*>(k), f.oc, f.fh, f.fw, f.ic, a, b,
+                            pg.s_h, pg.s_w, pg.jh[a], pg.jw[b], flip);
+                else
+                    deconv_phase_filter_kernel<uint32_t><<<grid_for(fl, 256), 256, 0, s>>>(
+                            static_cast<const uint32_t*>(filter), static_cast<uint32_t*>(k), f.oc, f.fh, f.fw, f.ic, a, b,
+                            pg.s_h, pg.s_w, pg.jh[a], pg.jw[b], flip);
+                int rc = cuda_rc("deconv phase filter");
+                if (rc != B200CB_OK)
+                    return rc;
+                if (b200cb_query(&pg.inner[ph], &inner) != B200CB_OK)
+                    return B200CB_ERR_BAD_PLAN;
+                rc = b200cb_launch(&inner, diff, k, nullptr, nullptr, t, inner_ws, inner.workspace_bytes, stream);
+                if (rc != B200CB_OK)
+                    return rc;
+            }
+        const uint32_t cv = f.ic * dtype_size(f.src_dtype) / 16;
+        const uint64_t items = (uint64_t)f.n * f.ih * f.iw * cv;
+        deconv_interleave_kernel<<<grid_for(items, 256), 256, 0, s>>>(
+                pp, static_cast<uint4*>(grad), f.n, f.ih, f.iw, cv, pg.s_h, pg.s_w, f.pad_h, f.pad_w);
+        return cuda_rc("deconv interleave");
+    }
     if (b200cb_query_algo(&g.inner, plan->algo, &inner) != B200CB_OK)
         return B200CB_ERR_BAD_PLAN;
     if (!workspace || ws_bytes < g.flt_bytes + g.up_bytes + inner.workspace_bytes)

@@ -179,4 +179,9 @@ DECONV_CASES = [
     ("qs8_3x3_s1_p1", "qs8", 2, 16, 9, 11, 32, 3, 1, 1, 1, 0),
     ("qs8_4x4_s2_p1", "qs8", 2, 16, 12, 12, 16, 4, 2, 1, 1, 0),
     ("qs8_3x3_s2_p1_sat", "qs8", 1, 32, 10, 10, 64, 3, 2, 1, 1, 0),
+    # stride > filter (phases that receive nothing are zero), stride 3, flipped filter with stride 2
+    ("bf16_1x1_s2_p0", "bf16", 2, 16, 9, 9, 8, 1, 2, 0, 1, 0),
+    ("qs8_5x5_s3_p2", "qs8", 1, 16, 14, 14, 16, 5, 3, 2, 1, 0),
+    ("f16_3x3_s2_mode_convolution", "f16", 1, 8, 9, 9, 16, 3, 2, 1, 1, 1),
+    ("bf16_3x3_s2_dilate2_upsampled", "bf16", 1, 8, 13, 13, 16, 3, 2, 2, 2, 0),
 ]
