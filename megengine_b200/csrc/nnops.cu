@@ -90,7 +90,12 @@ struct PoolParams {
 template <int DT>
 __device__ __forceinline__ uint32_t packed_max(uint32_t a, uint32_t b) {
     if constexpr (DT == B200CB_DT_QS8) {
-        return __vmaxs4(a, b);
+        // a, b: two bytes each, biased to unsigned and widened to the fp16 bit patterns 0x0400 + u (normal numbers
+        // of one binade: their order is the order of u) -- see the pooling kernel; one native HMNMX2 per byte pair.
+        // (__vmaxs4 and max.s16x2 are emulated on sm_100: ~8 instructions per byte)
+        uint32_t r;
+        asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
+        return r;
     } else if constexpr (DT == B200CB_DT_F16) {
         uint32_t r;
         asm("max.f16x2 %0, %1, %2;" : "=r"(r) : "r"(a), "r"(b));
@@ -141,7 +146,8 @@ __global__ void __launch_bounds__(256) pool_kernel(
             const uint32_t fh_lo = h0 < 0 ? (uint32_t)-h0 : 0u, fw_lo = w0 < 0 ? (uint32_t)-w0 : 0u;
             const uint32_t fh_hi = min(p.wh, p.ih - (uint32_t)min(h0, (int32_t)p.ih)), fw_hi = min(p.ww, p.iw - (uint32_t)min(w0, (int32_t)p.iw));
             constexpr bool WORDS = MODE == B200CB_POOL_MAX && sizeof(T) * V >= 4;   // packed maxima on 32-bit words
-            constexpr int NW = WORDS ? (int)(sizeof(T) * V / 4) : 1;
+            constexpr bool Q8W = WORDS && DT == B200CB_DT_QS8;   // int8: accumulators widened to fp16 pairs (2 regs / word)
+            constexpr int NW = WORDS ? (int)(sizeof(T) * V / 4) * (Q8W ? 2 : 1) : 1;
             uint32_t wacc[NW];
             float acc[V];
             int32_t iacc[V];
@@ -157,10 +163,17 @@ __global__ void __launch_bounds__(256) pool_kernel(
             }
 #pragma unroll
             for (int k = 0; k < NW; ++k)   // the lowest value of the element type in every lane
-                wacc[k] = DT == B200CB_DT_QS8 ? 0x80808080u : DT == B200CB_DT_F16 ? 0xfbfffbffu : DT == B200CB_DT_BF16 ? 0xff7fff7fu : 0xff7fffffu;
+                wacc[k] = DT == B200CB_DT_QS8 ? 0x04000400u : DT == B200CB_DT_F16 ? 0xfbfffbffu : DT == B200CB_DT_BF16 ? 0xff7fff7fu : 0xff7fffffu;
 #define B200CB_POOL_FEED(X_)                                                                               \
     do {                                                                                                   \
-        if constexpr (WORDS) {                                                                             \
+        if constexpr (Q8W) {                                                                               \
+            const uint32_t* xw__ = reinterpret_cast<const uint32_t*>(&(X_));                               \
+            _Pragma("unroll") for (int k = 0; k < NW / 2; ++k) {                                           \
+                const uint32_t u__ = xw__[k] ^ 0x80808080u;                                                \
+                wacc[2 * k] = packed_max<DT>(wacc[2 * k], __byte_perm(u__, 0x04040404u, 0x5140));          \
+                wacc[2 * k + 1] = packed_max<DT>(wacc[2 * k + 1], __byte_perm(u__, 0x04040404u, 0x7362));  \
+            }                                                                                              \
+        } else if constexpr (WORDS) {                                                                      \
             const uint32_t* xw__ = reinterpret_cast<const uint32_t*>(&(X_));                               \
             _Pragma("unroll") for (int k = 0; k < NW; ++k) wacc[k] = packed_max<DT>(wacc[k], xw__[k]);     \
         } else {                                                                                           \
@@ -176,29 +189,60 @@ __global__ void __launch_bounds__(256) pool_kernel(
             }                                                                                              \
         }                                                                                                  \
     } while (0)
-            for (uint32_t fh = fh_lo; fh < fh_hi; ++fh) {
-                const T* rowp = sb + ((size_t)(h0 + (int32_t)fh) * p.iw + w0) * pitch;
-                uint32_t fw = fw_lo;
-                for (; fw + 3 <= fw_hi; fw += 3) {   // three independent loads in flight, fed in tap order
-                    const Vec<T, V> x0 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)fw * pitch);
-                    const Vec<T, V> x1 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)(fw + 1) * pitch);
-                    const Vec<T, V> x2 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)(fw + 2) * pitch);
-                    B200CB_POOL_FEED(x0);
-                    B200CB_POOL_FEED(x1);
-                    B200CB_POOL_FEED(x2);
+            if (p.wh == 3 && p.ww == 3) {
+                // the 3x3 window (ResNet stem pool): all nine loads issued before the first use
+                Vec<T, V> x[9];
+                bool ok[9];
+#pragma unroll
+                for (uint32_t t = 0; t < 9; ++t) {
+                    const uint32_t fh = t / 3, fw = t % 3;
+                    ok[t] = fh >= fh_lo && fh < fh_hi && fw >= fw_lo && fw < fw_hi;
+                    if (ok[t])
+                        x[t] = *reinterpret_cast<const Vec<T, V>*>(
+                                sb + ((size_t)(h0 + (int32_t)fh) * p.iw + (w0 + (int32_t)fw)) * pitch);
                 }
-                for (; fw < fw_hi; ++fw) {
-                    const Vec<T, V> x0 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)fw * pitch);
-                    B200CB_POOL_FEED(x0);
+#pragma unroll
+                for (uint32_t t = 0; t < 9; ++t)
+                    if (ok[t])
+                        B200CB_POOL_FEED(x[t]);
+            } else {
+                for (uint32_t fh = fh_lo; fh < fh_hi; ++fh) {
+                    const T* rowp = sb + ((size_t)(h0 + (int32_t)fh) * p.iw + w0) * pitch;
+                    uint32_t fw = fw_lo;
+                    for (; fw + 7 <= fw_hi; fw += 7) {   // seven independent loads in flight, fed in tap order
+                        Vec<T, V> x[7];
+#pragma unroll
+                        for (uint32_t t = 0; t < 7; ++t)
+                            x[t] = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)(fw + t) * pitch);
+#pragma unroll
+                        for (uint32_t t = 0; t < 7; ++t)
+                            B200CB_POOL_FEED(x[t]);
+                    }
+                    for (; fw + 2 <= fw_hi; fw += 2) {
+                        const Vec<T, V> x0 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)fw * pitch);
+                        const Vec<T, V> x1 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)(fw + 1) * pitch);
+                        B200CB_POOL_FEED(x0);
+                        B200CB_POOL_FEED(x1);
+                    }
+                    for (; fw < fw_hi; ++fw) {
+                        const Vec<T, V> x0 = *reinterpret_cast<const Vec<T, V>*>(rowp + (size_t)fw * pitch);
+                        B200CB_POOL_FEED(x0);
+                    }
                 }
             }
 #undef B200CB_POOL_FEED
             if constexpr (WORDS) {
                 Vec<T, V> o;
                 uint32_t* ow__ = reinterpret_cast<uint32_t*>(&o);
+                if constexpr (Q8W) {
 #pragma unroll
-                for (int k = 0; k < NW; ++k)
-                    ow__[k] = wacc[k];
+                    for (int k = 0; k < NW / 2; ++k)
+                        ow__[k] = __byte_perm(wacc[2 * k], wacc[2 * k + 1], 0x6420) ^ 0x80808080u;
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NW; ++k)
+                        ow__[k] = wacc[k];
+                }
                 *reinterpret_cast<Vec<T, V>*>(db) = o;
                 continue;
             }
