@@ -639,6 +639,12 @@ int deconv_geometry(const b200cb_desc& f, DeconvGeom* g) {
     return B200CB_OK;
 }
 
+// the kernels move 16-byte vectors: tensors must start on 16-byte boundaries (megdnn allocations are 256-byte
+// aligned; an offset view is reported as unsupported rather than faulting)
+inline bool aligned16(const void* p) {
+    return (reinterpret_cast<uintptr_t>(p) & 15u) == 0;
+}
+
 int cuda_rc(const char* what) {
     const cudaError_t e = cudaGetLastError();
     if (e != cudaSuccess) {
@@ -672,6 +678,8 @@ int b200cb_pooling(const b200cb_pool_desc* d, const void* src, void* dst, void* 
         return B200CB_UNSUPPORTED_FORMAT;
     if (d->format != B200CB_FORMAT_NHWC && d->format != B200CB_FORMAT_NCHW && d->format != B200CB_FORMAT_NCHW4)
         return B200CB_UNSUPPORTED_FORMAT;
+    if (!aligned16(src) || !aligned16(dst))
+        return B200CB_UNSUPPORTED_ALIGNMENT;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc;
     switch (d->dtype) {
@@ -693,6 +701,8 @@ int b200cb_elemwise(uint32_t mode, uint32_t dtype, uint64_t n, const void* a, co
         return B200CB_ERR_NULL;
     if (n == 0)
         return B200CB_OK;
+    if (!aligned16(a) || !aligned16(dst) || (binary && !aligned16(b)))
+        return B200CB_UNSUPPORTED_ALIGNMENT;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const uint32_t es = dtype_size(dtype);
     if (es != 2 && es != 4)
@@ -727,6 +737,8 @@ int b200cb_elemwise_q(
         return B200CB_ERR_NULL;
     if (n == 0)
         return B200CB_OK;
+    if (!aligned16(a) || !aligned16(dst) || (binary && !aligned16(b)))
+        return B200CB_UNSUPPORTED_ALIGNMENT;
     b200cb_desc t;
     memset(&t, 0, sizeof(t));
     t.dst_scale = sd, t.src_scale = t.filter_scale = 1.f, t.bias_dtype = B200CB_DT_NONE;
@@ -750,6 +762,8 @@ int b200cb_typecvt(
         return B200CB_ERR_NULL;
     if (n == 0)
         return B200CB_OK;
+    if (!aligned16(src) || !aligned16(dst))
+        return B200CB_UNSUPPORTED_ALIGNMENT;
     b200cb_desc t;
     memset(&t, 0, sizeof(t));
     t.dst_scale = s_dst, t.src_scale = t.filter_scale = 1.f, t.bias_dtype = B200CB_DT_NONE;

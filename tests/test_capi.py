@@ -229,3 +229,44 @@ def test_int8_epilogue_sass_has_no_contracted_packed_ops():
         assert plain == (rm // 3 if is_igemm8 else 0), (name, plain, rm)
         checked += 1
     assert checked >= 11, checked
+
+
+def test_adjacent_operator_argument_validation_without_gpu(lib):
+    """include/b200cb_nn.h: argument errors are reported before anything touches CUDA -- null pointers, unknown
+    modes, shapes the reference's deduction rejects, windows entirely in the padding, unaligned tensors."""
+    d = C.PoolDesc()
+    d.format, d.mode, d.dtype = C.FORMAT_NHWC, C.POOL_MAX, C.DT_BF16
+    d.n, d.c, d.ih, d.iw, d.oh, d.ow = 1, 8, 8, 8, 4, 4
+    d.window_h = d.window_w = d.stride_h = d.stride_w = 2
+    assert lib.b200cb_pooling(ctypes.byref(d), None, None, None) == -5
+    assert lib.b200cb_pooling(ctypes.byref(d), 4096, 8192 + 2, None) == 5          # dst not 16-byte aligned
+    d.oh = 5
+    assert lib.b200cb_pooling(ctypes.byref(d), 4096, 8192, None) == 3              # not the deduced extent
+    d.oh, d.pad_h, d.pad_w = 6, 2, 2
+    d.ow = 6
+    assert lib.b200cb_pooling(ctypes.byref(d), 4096, 8192, None) == 4              # a window lies in the padding
+    assert lib.b200cb_elemwise(12345, C.DT_F32, 16, 4096, 4096, 8192, None) == 4   # unknown mode
+    assert lib.b200cb_elemwise(C.ELEM_ADD, C.DT_F32, 16, 4096, None, 8192, None) == -5
+    assert lib.b200cb_elemwise(C.ELEM_ADD, C.DT_QS8, 16, 4096, 4096, 8192, None) == 2
+    assert lib.b200cb_elemwise(C.ELEM_RELU, C.DT_F32, 0, 4096, None, 8192, None) == 0  # empty tensor: nothing to do
+    assert lib.b200cb_elemwise_q(C.ELEM_MUL, 16, 4096, 1.0, 4096, 1.0, 8192, 1.0, None) == 4
+    assert lib.b200cb_typecvt(C.DT_F16, 0.0, C.DT_BF16, 0.0, 16, 4096, 8192, None) == 2   # pair not implemented
+    assert lib.b200cb_typecvt(C.DT_F32, 0.0, C.DT_BF16, 0.0, 16, 4096 + 4, 8192, None) == 5
+    # deconvolution: the descriptor names the forward convolution; extents must agree with it
+    f = K.make_desc("bf16", 2, 16, 12, 12, 32, 3, stride=2, pad=1, bias_mode=C.BIAS_NONE)
+    f.bias_dtype = C.DT_NONE
+    p = C.Plan()
+    assert lib.b200cb_deconv_query(ctypes.byref(f), ctypes.byref(p)) == 0
+    assert p.workspace_bytes > 0 and p.reserved[0] == 1           # stride 2: phase decomposition
+    assert p.flops == 2 * 2 * 32 * 6 * 6 * 16 * 9
+    f.oh = 7
+    assert lib.b200cb_deconv_query(ctypes.byref(f), ctypes.byref(p)) == 3
+    g = K.make_desc("bf16", 2, 16, 12, 12, 32, 1, pad=1, bias_mode=C.BIAS_NONE)
+    g.bias_dtype = C.DT_NONE
+    assert lib.b200cb_deconv_query(ctypes.byref(g), ctypes.byref(p)) == 4  # pad > dilated filter - 1: cropping, not implemented
+    # ConvolutionForward ignores the epilogue fields; BatchConvBias plans one image
+    c = K.make_desc("bf16", 4, 64, 14, 14, 128, 3, pad=1, nonline=C.NL_RELU, has_z=True)
+    assert lib.b200cb_convolution_query(ctypes.byref(c), ctypes.byref(p)) == 0
+    assert p.desc.has_z == 0 and p.desc.bias_mode == C.BIAS_NONE and p.desc.nonline_mode == C.NL_IDENTITY
+    assert lib.b200cb_batch_convbias_query(ctypes.byref(c), ctypes.byref(p)) == 0
+    assert p.desc.n == 4 and p.flops == 2 * 4 * 128 * 14 * 14 * 64 * 9
