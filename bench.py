@@ -496,6 +496,52 @@ def layer_tables(peaks):
     return out
 
 
+def config1_table(peaks, cpu=True):
+    """BASELINE config 1 (`configs[0]`, the reference's own CPU-runnable case): the ResNet-18 conv stack, fp32
+    NCHW, batch 8, 224x224, bias + ReLU.  GPU: every layer through the Float32 NCHW cell of the C-ABI (bf16 x 3
+    operand split), L2-cold, summed in network order; CPU: the reference's x86 megdnn ConvBias (oracle/_ref) on
+    1 thread and on all host threads, 1 warm-up + 2 timed passes per layer."""
+    from megengine_b200 import _capi as C
+    from tests import _cases as K
+    from tools import bench_layers as BL
+    lib = C.load()
+    pk = {"hbm_gbs": peaks["hbm_gbs"], "tf": peaks["tf_burst"]}
+    out = {"config": "ResNet-18 conv stack, fp32 NCHW, batch 8, 224x224, bias+ReLU"}
+    for n in (8, MICRO_BATCH):
+        ms, fl, bad = 0.0, 0.0, []
+        for layer in K.RESNET18_LAYERS:
+            r = BL.time_desc(lib, K.resnet18_desc(layer, n), 20, pk)
+            if "ms" not in r:
+                bad.append(layer[0])
+                continue
+            ms += r["ms"] * layer[-1]
+            fl += r["flops"] * layer[-1]
+        out["b200_batch%d" % n] = {"stack_ms": round(ms, 4), "images_per_s": round(n / ms * 1e3, 1),
+                                   "tflops": round(fl / ms / 1e9, 1), "unsupported_layers": bad,
+                                   "tolerance": "1e-3 max rel vs the fp32 oracle (tests/test_parity_gpu.py, every layer)"}
+    if cpu:
+        try:
+            from tests import _oracle as O
+            if O.have_ref():
+                import numpy as np
+                cores = len(os.sched_getaffinity(0))
+                for threads in sorted({1, cores}):
+                    tot, fl = 0.0, 0.0
+                    for layer in K.RESNET18_LAYERS:
+                        d = K.resnet18_desc(layer, 8)
+                        src, flt, bias, _ = K.gen_inputs(d, 1)
+                        _dst, secs, _algo = O.ref_convbias(d, src, flt, bias, None, handle_kind=0, threads=threads, repeat=3)
+                        t = float(np.median(list(secs)[1:]))
+                        tot += t * layer[-1]
+                        fl += 2.0 * d.n * d.oc * d.oh * d.ow * d.ic * d.fh * d.fw * layer[-1]
+                    out["reference_x86_%d_threads" % threads] = {"stack_ms": round(tot * 1e3, 2),
+                                                                 "images_per_s": round(8 / tot, 2),
+                                                                 "gflops": round(fl / tot / 1e9, 1)}
+        except Exception as e:  # noqa: BLE001 -- the CPU leg is a reported baseline, never a reason to fail the bench
+            out["reference_error"] = str(e)[:200]
+    return out
+
+
 def pinned_input(shape, dtype, kind):
     """host staging buffer of the end-to-end input.  'wc': page-locked write-combined memory
     (cudaHostAllocWriteCombined: the CPU only ever writes it, device DMA reads skip the cache snoops)."""
@@ -834,6 +880,7 @@ def main():
         # the operators either side of ConvBias (include/b200cb_nn.h), L2-cold
         from tools import bench_nn
         extra["adjacent_ops"] = bench_nn.run(peaks["hbm_gbs"])
+        extra["config1_resnet18_fp32_nchw"] = config1_table(peaks, cpu=not args.no_cpu_baseline)
         extra["layers_bf16"] = [{k: r[k] for k in ("name", "algo", "count", "ms", "tflops", "gbs", "bound", "frac_of_floor")}
                                 for r in rows]
 
