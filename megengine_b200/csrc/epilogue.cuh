@@ -145,7 +145,7 @@ __device__ __forceinline__ f32x2_t f2_add_rm(f32x2_t a, f32x2_t b) {
 }
 // loop-invariant operands of the packed requantize
 struct RequantPacked {
-    f32x2_t s_bias, inv, neg_s, half, magic, neg_i2f;
+    f32x2_t s_bias, inv, neg_s, half, magic, neg_i2f, neg_2p23, c4096;
     float s_bias1, s_z1;
 };
 // int32 -> float without the conversion pipe (I2F issues 16 lanes / clk / SM and was the busiest pipe of the
@@ -172,19 +172,40 @@ __device__ __forceinline__ RequantPacked make_requant_packed(const RequantParams
     r.half = f2_pack(0.5f, 0.5f);
     r.magic = f2_pack(8388608.f, 8388608.f);
     r.neg_i2f = f2_pack(-I2F_MAGIC, -I2F_MAGIC);
+    r.neg_2p23 = f2_pack(-8388608.f, -8388608.f);
+    r.c4096 = f2_pack(4096.f, 4096.f);
     return r;
 }
+// Any int32 -> float, correctly rounded (== I2F.RN), without the conversion pipe.  ncu on int8 ResNet-50 l1.c2 (rows
+// mode: 9 short MMAs per 8192 outputs): the XU pipe 92 % busy with nothing but I2FP -- the conversion, one per output,
+// bounded the epilogue (0.087 -> 0.072 ms with this form).  Everywhere else the extra 4.5 FMA / ALU instructions cost
+// more than the conversion pipe did (qs8 step 2.75 -> 2.90 ms when used in every layer), so only the rows-mode
+// epilogue selects it.  v = hi * 4096 + lo with hi = v >> 12 (|hi| < 2^19) and
+// lo = v & 4095: both convert exactly through magic-number adds, and one FMA  fma(float(hi), 4096, float(lo))
+// rounds the exact value v once.  3 ALU + 1.5 packed FMA-pipe instructions per element; b200cb_selftest(2) sweeps all
+// 2^32 accumulators against the I2F form.
+__device__ __forceinline__ f32x2_t i2f_pair(int32_t v0, int32_t v1, const RequantPacked& k) {
+    const f32x2_t hi = f2_add(f2_pack(__int_as_float((v0 >> 12) + static_cast<int32_t>(I2F_MAGIC_BITS)),
+                                      __int_as_float((v1 >> 12) + static_cast<int32_t>(I2F_MAGIC_BITS))), k.neg_i2f);
+    const f32x2_t lo = f2_add(f2_pack(__uint_as_float((static_cast<uint32_t>(v0) & 0xfffu) | 0x4B000000u),
+                                      __uint_as_float((static_cast<uint32_t>(v1) & 0xfffu) | 0x4B000000u)), k.neg_2p23);
+    return f2_fma(hi, k.c4096, lo);
+}
+
 // two RELU outputs at once: (acc + bias) pairs -> the two result bytes in the low bytes of lo / hi.
 // Same operation sequence as dequant + fmaxf + div_by_scale_noguard + round_sat_s8_nonneg.
-// MAGIC: sfb0 / sfb1 already carry I2F_MAGIC_BITS (acc + bias + magic, range proven by the caller)
-template <bool HAS_Z, bool MAGIC = false>
+// CVT selects the int32 -> float conversion: 0 = I2F (conversion pipe), 1 = sfb0 / sfb1 already carry
+// I2F_MAGIC_BITS (acc + bias + magic, range proven by the caller), 2 = i2f_pair (full range, FMA / ALU pipes only)
+template <bool HAS_Z, int CVT = 0>
 __device__ __forceinline__ void requant_pair_nonneg(
         int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
         uint32_t& hi) {
     f32x2_t x;
     f32x2_t a;
-    if constexpr (MAGIC)
+    if constexpr (CVT == 1)
         a = f2_add(f2_pack(__int_as_float(sfb0), __int_as_float(sfb1)), k.neg_i2f);   // exact
+    else if constexpr (CVT == 2)
+        a = i2f_pair(sfb0, sfb1, k);
     else
         a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
     if constexpr (HAS_Z) {
@@ -213,14 +234,16 @@ __device__ __forceinline__ void requant_pair_nonneg(
 }
 
 // the IDENTITY (any sign) form of the same: clamp to [-128, 127], round the magnitude, negate the byte
-template <bool HAS_Z, bool MAGIC = false>
+template <bool HAS_Z, int CVT = 0>
 __device__ __forceinline__ void requant_pair_signed(
         int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
         uint32_t& hi) {
     f32x2_t x;
     f32x2_t a;
-    if constexpr (MAGIC)
+    if constexpr (CVT == 1)
         a = f2_add(f2_pack(__int_as_float(sfb0), __int_as_float(sfb1)), k.neg_i2f);   // exact
+    else if constexpr (CVT == 2)
+        a = i2f_pair(sfb0, sfb1, k);
     else
         a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
     if constexpr (HAS_Z) {

@@ -200,7 +200,7 @@ __host__ __device__ constexpr uint32_t off_sd(uint32_t /*groups*/, uint32_t /*bn
 // pack -- all on the FMA / ALU pipes (see epilogue.cuh), written as two swizzled 16-byte pieces.
 // MAGIC: the bias slice in shared memory carries I2F_MAGIC_BITS and |acc + bias| < 2^22 was proven for the
 // chunk (epilogue.cuh): no conversion-pipe instruction is left in the sequence.
-template <bool HAS_Z, bool NONNEG, bool MAGIC>
+template <bool HAS_Z, bool NONNEG, int MAGIC>   // MAGIC: the CVT selector of requant_pair_* (epilogue.cuh)
 __device__ __forceinline__ void requant_row32(
         const uint32_t (&r)[32], const uint32_t* bcol, const uint8_t* zrow, uint8_t* drow, uint32_t h,
         uint32_t lane, const RequantParams& rq) {
@@ -1228,9 +1228,11 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 #define B200CB_RQ_CASE(Z_, R_)                                                      \
     do {                                                                            \
         if (magic)                                                                  \
-            requant_row32<Z_, R_, true>(r, bcol, zrow, drow, h, lane, p.rq);        \
+            requant_row32<Z_, R_, 1>(r, bcol, zrow, drow, h, lane, p.rq);           \
+        else if (!Z_ && rows)   /* rows mode: conversion-pipe bound (epilogue.cuh) */\
+            requant_row32<false, R_, 2>(r, bcol, zrow, drow, h, lane, p.rq);        \
         else                                                                        \
-            requant_row32<Z_, R_, false>(r, bcol, zrow, drow, h, lane, p.rq);       \
+            requant_row32<Z_, R_, 0>(r, bcol, zrow, drow, h, lane, p.rq);           \
     } while (0)
                         if (p.has_z) {
                             if (p.nonline == B200CB_NL_RELU)
@@ -1592,6 +1594,21 @@ __global__ void selftest_packed_kernel(const float* scales, int nscales, unsigne
                 ++local;
             requant_pair_signed<true>(a0, a1, zb0, zb1, kp, lo, hi);
             if ((lo & 0xffu) != scalar(a0, zb0, false) || (hi & 0xffu) != scalar(a1, zb1, false))
+                ++local;
+            // the conversion-free int32 -> float forms: full range (i2f_pair) against I2F.RN bit for bit, and the
+            // range-proven magic add on the accumulators inside its range
+            float c0, c1;
+            f2_unpack(i2f_pair(a0, a1, kp), c0, c1);
+            if (__float_as_uint(c0) != __float_as_uint(__int2float_rn(a0)) ||
+                __float_as_uint(c1) != __float_as_uint(__int2float_rn(a1)))
+                ++local;
+            requant_pair_nonneg<true, 2>(a0, a1, zb0, zb1, kp, lo, hi);
+            if ((lo & 0xffu) != scalar(a0, zb0, true) || (hi & 0xffu) != scalar(a1, zb1, true))
+                ++local;
+            const int32_t m0 = (a0 >> 10), m1 = (a1 >> 10);   // |m| < 2^21: inside the magic range
+            requant_pair_signed<true, 1>(m0 + static_cast<int32_t>(I2F_MAGIC_BITS), m1 + static_cast<int32_t>(I2F_MAGIC_BITS),
+                                         zb0, zb1, kp, lo, hi);
+            if ((lo & 0xffu) != scalar(m0, zb0, false) || (hi & 0xffu) != scalar(m1, zb1, false))
                 ++local;
         }
     }

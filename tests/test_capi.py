@@ -204,9 +204,9 @@ def test_int8_epilogue_sass_has_no_contracted_packed_ops():
     """Bit-exactness guard.  ptxas contracts mul.rn.f32x2 + add.rn.f32x2 into FFMA2 (see
     megengine_b200/csrc/epilogue.cuh), so the packed requantize keeps no product that feeds an add.  In
     every QuantizedS8 igemm kernel the machine code must then hold exactly the explicit FMAs of the
-    division (2 FFMA2 per FADD2.RM pair rounding); the only round-to-nearest FADD2s are the exact magic-number
-    subtractions of the conversion-free int -> float variants (a third of the igemm rounding sites, none in the
-    generic depthwise kernel) -- an add never follows a product."""
+    division (2 FFMA2 per FADD2.RM pair rounding) and of the conversion-free int32 -> float (one FFMA2 per pair in
+    the full-range variants); the only round-to-nearest FADD2s are the exact magic-number subtractions -- an add
+    never follows a product."""
     import re
     import shutil
     import subprocess
@@ -225,8 +225,13 @@ def test_int8_epilogue_sass_has_no_contracted_packed_ops():
         ffma2, rm, rz = f.count("FFMA2"), f.count("FADD2.RM"), f.count("FADD2.RZ")
         plain = len(re.findall(r"FADD2 ", f))
         assert rm > 0 and rm == rz, (name, rm, rz)
-        assert ffma2 == 2 * rm, (name, ffma2, rm)
-        assert plain == (rm // 3 if is_igemm8 else 0), (name, plain, rm)
+        # per rounding pair: the two FMAs of the division; the sites that convert int32 -> float on the FMA / ALU pipes
+        # over the full range (rows-mode epilogue: 2 of the 14 igemm sites, 16 pairs each) add one FMA and two exact
+        # FADD2s, the range-proven magic sites (4 igemm sites) one exact FADD2.  A contracted mul + add would add an
+        # FFMA2 and remove a FADD2.
+        n_split, n_magic = (32, 64) if is_igemm8 else (0, 0)
+        assert ffma2 == 2 * rm + n_split, (name, ffma2, rm)
+        assert plain == n_magic + 2 * n_split, (name, plain)
         checked += 1
     assert checked >= 11, checked
 
