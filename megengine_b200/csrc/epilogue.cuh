@@ -176,14 +176,16 @@ __device__ __forceinline__ RequantPacked make_requant_packed(const RequantParams
     r.c4096 = f2_pack(4096.f, 4096.f);
     return r;
 }
-// Any int32 -> float, correctly rounded (== I2F.RN), without the conversion pipe.  ncu on int8 ResNet-50 l1.c2 (rows
-// mode: 9 short MMAs per 8192 outputs): the XU pipe 92 % busy with nothing but I2FP -- the conversion, one per output,
-// bounded the epilogue (0.087 -> 0.072 ms with this form).  Everywhere else the extra 4.5 FMA / ALU instructions cost
-// more than the conversion pipe did (qs8 step 2.75 -> 2.90 ms when used in every layer), so only the rows-mode
-// epilogue selects it.  v = hi * 4096 + lo with hi = v >> 12 (|hi| < 2^19) and
-// lo = v & 4095: both convert exactly through magic-number adds, and one FMA  fma(float(hi), 4096, float(lo))
-// rounds the exact value v once.  3 ALU + 1.5 packed FMA-pipe instructions per element; b200cb_selftest(2) sweeps all
-// 2^32 accumulators against the I2F form.
+// Any int32 -> float, correctly rounded (== I2F.RN), without the conversion pipe: v = hi * 4096 + lo with
+// hi = v >> 12 (|hi| < 2^19) and lo = v & 4095 -- both convert exactly through magic-number adds, and one FMA
+// fma(float(hi), 4096, float(lo)) rounds the exact value v once.  3 ALU + 1.5 packed FMA-pipe instructions per
+// element; b200cb_selftest(2) sweeps all 2^32 accumulators against the I2F form.
+// Measured, not deduced: in the rows-mode epilogue (int8 ResNet-50 l1.c2: nine short MMAs per 8192 outputs) this
+// form is 17 % faster than I2F (0.087 -> 0.072 ms; ncu's `xu_realtime` triage metric read 92 % there while
+// `sm__inst_executed_pipe_xu` read 3 %, so the mechanism -- conversion latency in the dependent chain rather than
+// pipe occupancy -- is an inference); in every other layer the extra instructions cost more than the conversion did
+// (qs8 step 2.75 -> 2.90 ms when used everywhere: those epilogues are ALU / issue bound -- ALU pipe 57-69 %, issue
+// slots 71-77 % busy, profiles/r02/ncu_pipes_qs8_layer1.txt).  Only the rows-mode epilogue selects it.
 __device__ __forceinline__ f32x2_t i2f_pair(int32_t v0, int32_t v1, const RequantPacked& k) {
     const f32x2_t hi = f2_add(f2_pack(__int_as_float((v0 >> 12) + static_cast<int32_t>(I2F_MAGIC_BITS)),
                                       __int_as_float((v1 >> 12) + static_cast<int32_t>(I2F_MAGIC_BITS))), k.neg_i2f);

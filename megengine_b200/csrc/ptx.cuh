@@ -80,8 +80,33 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 #ifndef B200CB_WAIT_HINT_NS
 #define B200CB_WAIT_HINT_NS 20000
 #endif
+// B200CB_WAIT_BACKOFF_NS (experiment, off): after 4 failed polls a waiter sleeps this long between further polls.
+// ncu on the issue-bound int8 layers: a quarter of all issued instructions are the SYNCS / BRA / NANOSLEEP of waiting
+// warps (a hinted try_wait is re-issued every ~150 clk whatever the hint says) -- but taking them away changed
+// nothing: 300 / 1000 ns measured qs8 2.72 -> 2.76 ms, bf16 within noise (profiles/r02/wait_backoff.txt).
+#ifndef B200CB_WAIT_BACKOFF_NS
+#define B200CB_WAIT_BACKOFF_NS 0
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-#if B200CB_WAIT_HINT_NS > 0
+#if B200CB_WAIT_BACKOFF_NS > 0
+    asm volatile(
+            "{\n"
+            ".reg .pred P1;\n"
+            ".reg .u32 cnt;\n"
+            "mov.u32 cnt, 0;\n"
+            "LAB_WAIT:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n"
+            "@P1 bra DONE;\n"
+            "add.u32 cnt, cnt, 1;\n"
+            "setp.lt.u32 P1, cnt, 4;\n"
+            "@P1 bra LAB_WAIT;\n"
+            "nanosleep.u32 %3;\n"
+            "bra LAB_WAIT;\n"
+            "DONE:\n"
+            "}\n" ::"r"(bar),
+            "r"(parity), "r"(static_cast<uint32_t>(B200CB_WAIT_HINT_NS)), "r"(static_cast<uint32_t>(B200CB_WAIT_BACKOFF_NS))
+            : "memory");
+#elif B200CB_WAIT_HINT_NS > 0
     asm volatile(
             "{\n"
             ".reg .pred P1;\n"
