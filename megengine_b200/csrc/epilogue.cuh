@@ -102,6 +102,31 @@ __device__ __forceinline__ uint32_t round_sat_s8_signed(float v) {
     const uint32_t s = static_cast<uint32_t>(static_cast<int32_t>(__float_as_uint(c)) >> 31);
     return (m ^ s) - s;
 }
+// ---- the same rounding + clamp through ONE saturating conversion (B200CB_RQ_CVT): the int8 epilogue is bound by
+// the ALU pipe and the issue slots while the conversion pipe idles (ncu: ALU 57-69 %, XU 3 %), so the clamp
+// (FMNMX) and the second magic add move there.  roundf(v) = floor(v + 0.5) for v >= 0 and trunc(v -+ 0.5) in
+// general; the add is round-toward-zero (can never cross an integer), cvt.{rmi,rzi}.sat.s8 floors / truncates
+// exactly and saturates to [-128, 127] like the oracle's fmin(fmax(-128, roundf(v)), 127).
+#ifndef B200CB_RQ_CVT
+#define B200CB_RQ_CVT 1
+#endif
+__device__ __forceinline__ uint32_t cvt_floor_sat_s8(float t) {
+    int32_t r;
+    asm("cvt.rmi.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(t));
+    return static_cast<uint32_t>(r);
+}
+__device__ __forceinline__ uint32_t cvt_trunc_sat_s8(float t) {
+    int32_t r;
+    asm("cvt.rzi.sat.s8.f32 %0, %1;" : "=r"(r) : "f"(t));
+    return static_cast<uint32_t>(r);
+}
+__device__ __forceinline__ uint32_t round_sat_s8_nonneg_cvt(float v) {
+    return cvt_floor_sat_s8(__fadd_rz(v, 0.5f));
+}
+__device__ __forceinline__ uint32_t round_sat_s8_signed_cvt(float v) {
+    const float h = __uint_as_float(0x3f000000u | (__float_as_uint(v) & 0x80000000u));   // copysign(0.5, v)
+    return cvt_trunc_sat_s8(__fadd_rz(v, h));
+}
 // low bytes of four words -> one int8x4 word
 __device__ __forceinline__ uint32_t pack_low_bytes(uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     return __byte_perm(__byte_perm(a, b, 0x0040), __byte_perm(c, d, 0x0040), 0x5410);
@@ -226,6 +251,12 @@ __device__ __forceinline__ void requant_pair_nonneg(
     const f32x2_t q0 = f2_mul(x, k.inv);
     const f32x2_t e = f2_fma(q0, k.neg_s, x);   // x - q0 * s, exact
     const f32x2_t q1 = f2_fma(e, k.inv, q0);
+#if B200CB_RQ_CVT
+    float t0, t1;
+    f2_unpack(f2_add_rz(q1, k.half), t0, t1);
+    lo = cvt_floor_sat_s8(t0);
+    hi = cvt_floor_sat_s8(t1);
+#else
     float c0, c1;
     f2_unpack(q1, c0, c1);
     const f32x2_t u = f2_add_rm(f2_add_rz(f2_pack(fminf(c0, 127.f), fminf(c1, 127.f)), k.half), k.magic);
@@ -233,6 +264,7 @@ __device__ __forceinline__ void requant_pair_nonneg(
     f2_unpack(u, u0, u1);
     lo = __float_as_uint(u0);
     hi = __float_as_uint(u1);
+#endif
 }
 
 // the IDENTITY (any sign) form of the same: clamp to [-128, 127], round the magnitude, negate the byte
@@ -263,6 +295,14 @@ __device__ __forceinline__ void requant_pair_signed(
     const f32x2_t q1 = f2_fma(e, k.inv, q0);
     float c0, c1;
     f2_unpack(q1, c0, c1);
+#if B200CB_RQ_CVT
+    const f32x2_t hs = f2_pack(__uint_as_float(0x3f000000u | (__float_as_uint(c0) & 0x80000000u)),
+                               __uint_as_float(0x3f000000u | (__float_as_uint(c1) & 0x80000000u)));
+    float t0, t1;
+    f2_unpack(f2_add_rz(q1, hs), t0, t1);
+    lo = cvt_trunc_sat_s8(t0);
+    hi = cvt_trunc_sat_s8(t1);
+#else
     c0 = fminf(fmaxf(c0, -128.f), 127.f);
     c1 = fminf(fmaxf(c1, -128.f), 127.f);
     const f32x2_t u = f2_add_rm(f2_add_rz(f2_pack(fabsf(c0), fabsf(c1)), k.half), k.magic);
@@ -272,6 +312,7 @@ __device__ __forceinline__ void requant_pair_signed(
     const uint32_t s1 = static_cast<uint32_t>(static_cast<int32_t>(__float_as_uint(c1)) >> 31);
     lo = (__float_as_uint(u0) ^ s0) - s0;
     hi = (__float_as_uint(u1) ^ s1) - s1;
+#endif
 }
 
 __device__ __forceinline__ int32_t requant_s8(int32_t sfb, int32_t zq, uint32_t nl, const RequantParams& q) {

@@ -1556,6 +1556,11 @@ __global__ void selftest_fastq_kernel(const float* scales, int nscales, unsigned
                 ++local;
             if (r >= 0.f && (round_sat_s8_nonneg(div_by_scale_noguard(r, q)) & 0xffu) != want)
                 ++local;
+            // the single-conversion forms (cvt.{rzi,rmi}.sat.s8 after a round-toward-zero add of +-0.5)
+            if ((round_sat_s8_signed_cvt(div_by_scale_noguard(r, q)) & 0xffu) != want)
+                ++local;
+            if (r >= 0.f && (round_sat_s8_nonneg_cvt(div_by_scale_noguard(r, q)) & 0xffu) != want)
+                ++local;
         }
     }
     if (local)

@@ -224,13 +224,15 @@ def test_int8_epilogue_sass_has_no_contracted_packed_ops():
             continue  # QuantizedS8 -> QuantizedS8 kernels only (igemm KIND 2 / OUT32 0, depthwise KIND 3)
         ffma2, rm, rz = f.count("FFMA2"), f.count("FADD2.RM"), f.count("FADD2.RZ")
         plain = len(re.findall(r"FADD2 ", f))
-        assert rm > 0 and rm == rz, (name, rm, rz)
-        # per rounding pair: the two FMAs of the division; the sites that convert int32 -> float on the FMA / ALU pipes
-        # over the full range (rows-mode epilogue: 2 of the 14 igemm sites, 16 pairs each) add one FMA and two exact
+        # one FADD2.RZ (the +-0.5 of the rounding) per output pair; the clamp and the floor are a saturating
+        # conversion, so no FADD2.RM is left (epilogue.cuh, B200CB_RQ_CVT)
+        assert rz > 0 and rm == 0, (name, rm, rz)
+        # per pair: the two FMAs of the division; the sites that convert int32 -> float on the FMA / ALU pipes over
+        # the full range (rows-mode epilogue: 2 of the 14 igemm sites, 16 pairs each) add one FMA and two exact
         # FADD2s, the range-proven magic sites (4 igemm sites) one exact FADD2.  A contracted mul + add would add an
         # FFMA2 and remove a FADD2.
         n_split, n_magic = (32, 64) if is_igemm8 else (0, 0)
-        assert ffma2 == 2 * rm + n_split, (name, ffma2, rm)
+        assert ffma2 == 2 * rz + n_split, (name, ffma2, rz)
         assert plain == n_magic + 2 * n_split, (name, plain)
         checked += 1
     assert checked >= 11, checked
