@@ -1,7 +1,7 @@
 # round-2 final artefacts: smoke, full parity suite, driver-style bench lines, reference arm, ncu launch lists with DRAM
 # bytes (the kernels' share of the step), full captures of the new kernels (int8 rows-mode l1.c2, pooling)
-O=gpurun_out/r2final
-T=/tmp/ncu_r2f
+O=gpurun_out/r2final2
+T=/tmp/ncu_r2f2
 mkdir -p $O $T
 timeout 200 python -c "import __graft_entry__ as g; g.smoke()" > $O/smoke.log 2>&1; echo smoke=$?; tail -4 $O/smoke.log
 timeout 1200 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo pytest=$?; tail -3 $O/pytest_gpu.log
@@ -27,8 +27,8 @@ python - <<'PY'
 import json
 for f in ['bf16','qs8','bf16_short']:
     try:
-        b=json.load(open('gpurun_out/r2final/bench_%s.json'%f)); print(f, 'ms/mb %.4f TF %.1f value %.0f e2e %.0f' % (b['ms_per_microbatch_256'], b['tflops'], b['value'], b['e2e']['value']), b['clocks'], b['roofline']['frac'])
+        b=json.load(open('gpurun_out/r2final2/bench_%s.json'%f)); print(f, 'ms/mb %.4f TF %.1f value %.0f e2e %.0f' % (b['ms_per_microbatch_256'], b['tflops'], b['value'], b['e2e']['value']), b['clocks'], b['roofline']['frac'])
     except Exception as e: print(f, 'ERR', e)
-print(open('gpurun_out/r2final/bench_reference.json').read()[:600])
+print(open('gpurun_out/r2final2/bench_reference.json').read()[:600])
 PY
 du -sh $O; ls $O
