@@ -496,6 +496,45 @@ def layer_tables(peaks):
     return out
 
 
+def small_batch_latency(device):
+    """Serving-style latency of the 53-layer stack at batch 1 and 8 (bf16 NHWC): one micro-batch enqueued layer by
+    layer through the operator API (launch bound: ~11 us of host time per layer) against the same 54 launches
+    replayed as ONE captured CUDA graph."""
+    import torch
+    out = {}
+    for n in (1, 8):
+        _h, layers = build_layers("bf16", n, device)
+        for _ in range(3):
+            run_microbatch(layers)
+        torch.cuda.synchronize()
+
+        def timed(fn, reps=30):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(reps):
+                fn()
+            e1.record()
+            torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / reps
+        eager = timed(lambda: run_microbatch(layers))
+        g = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(device)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            run_microbatch(layers)
+            g.capture_begin()
+            run_microbatch(layers)
+            g.capture_end()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = timed(g.replay)
+        out["batch%d" % n] = {"eager_ms": round(eager, 4), "cuda_graph_ms": round(graph, 4),
+                              "images_per_s_graph": round(n / graph * 1e3, 1)}
+        del g, layers
+        torch.cuda.empty_cache()
+    return out
+
+
 def config1_table(peaks, cpu=True):
     """BASELINE config 1 (`configs[0]`, the reference's own CPU-runnable case): the ResNet-18 conv stack, fp32
     NCHW, batch 8, 224x224, bias + ReLU.  GPU: every layer through the Float32 NCHW cell of the C-ABI (bf16 x 3
@@ -881,6 +920,10 @@ def main():
         from tools import bench_nn
         extra["adjacent_ops"] = bench_nn.run(peaks["hbm_gbs"])
         extra["config1_resnet18_fp32_nchw"] = config1_table(peaks, cpu=not args.no_cpu_baseline)
+        try:
+            extra["latency_small_batch_bf16"] = small_batch_latency(device)
+        except Exception as e:  # noqa: BLE001 -- an extra; never a reason to fail the bench line
+            extra["latency_small_batch_bf16"] = {"error": str(e)[:200]}
         extra["layers_bf16"] = [{k: r[k] for k in ("name", "algo", "count", "ms", "tflops", "gbs", "bound", "frac_of_floor")}
                                 for r in rows]
 

@@ -445,22 +445,32 @@ __device__ __forceinline__ typename Raw<DDT>::T cvt_one(typename Raw<SDT>::T x, 
         return Elem<DDT>::st(v);
     }
 }
-// E elements per thread: 16 bytes of the narrower side per access
+// E elements per thread and access: 16 bytes of the WIDER side, so that consecutive lanes touch consecutive bytes on
+// both sides (a lane writing 64 contiguous bytes makes every store instruction a 64-byte-strided scatter)
 template <int SDT, int DDT>
 __global__ void __launch_bounds__(256) typecvt_kernel(
         uint64_t n, const void* __restrict__ src_, void* __restrict__ dst_, float s_src, RequantParams rq) {
     using ST = typename Raw<SDT>::T;
     using DT_ = typename Raw<DDT>::T;
-    constexpr int E = 16 / (int)(sizeof(ST) < sizeof(DT_) ? sizeof(ST) : sizeof(DT_));
+    constexpr int E = 16 / (int)(sizeof(ST) > sizeof(DT_) ? sizeof(ST) : sizeof(DT_));
     const ST* src = static_cast<const ST*>(src_);
     DT_* dst = static_cast<DT_*>(dst_);
     const uint64_t nvec = n / E;
     for (uint64_t i = blockIdx.x * (uint64_t)blockDim.x + threadIdx.x; i < nvec; i += (uint64_t)gridDim.x * blockDim.x) {
         const Vec<ST, E> x = reinterpret_cast<const Vec<ST, E>*>(src)[i];
         Vec<DT_, E> o;
+        if constexpr (SDT == B200CB_DT_QS8 && E == 4 && DDT != B200CB_DT_QS8 && DDT != B200CB_DT_QS32) {
+            // int8 -> float through PRMT + one exact FADD (epilogue.cuh) instead of four I2F.S8
+            const uint32_t w = *reinterpret_cast<const uint32_t*>(&x) ^ 0x80808080u;
+            const float f[4] = {s8_to_float<0>(w), s8_to_float<1>(w), s8_to_float<2>(w), s8_to_float<3>(w)};
 #pragma unroll
-        for (int k = 0; k < E; ++k)
-            o.v[k] = cvt_one<SDT, DDT>(x.v[k], s_src, rq);
+            for (int k = 0; k < 4; ++k)
+                o.v[k] = Elem<DDT>::st(__fmul_rn(f[k], s_src));
+        } else {
+#pragma unroll
+            for (int k = 0; k < E; ++k)
+                o.v[k] = cvt_one<SDT, DDT>(x.v[k], s_src, rq);
+        }
         reinterpret_cast<Vec<DT_, E>*>(dst)[i] = o;
     }
     if (blockIdx.x == 0 && threadIdx.x < n - nvec * E) {
@@ -771,7 +781,7 @@ int b200cb_typecvt(
     if (rq.fast_div == 2)
         rq.fast_div = 1;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const uint32_t grid = grid_for(n / 4 + 1, 256);
+    const uint32_t grid = grid_for(n / 4 + 1, 256);   // (>= one vector per thread for every pair)
 #define CVT(S_, D_)                                                                      \
     if (sdt == S_ && ddt == D_) {                                                        \
         typecvt_kernel<S_, D_><<<grid, 256, 0, s>>>(n, src, dst, s_src, rq);             \
