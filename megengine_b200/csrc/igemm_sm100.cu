@@ -765,6 +765,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 const uint32_t btap = p.flip ? (p.num_taps - 1 - tap) : tap;
                 for (uint32_t kc = 0; kc < p.num_kc; ++kc) {
                     TIMED_WAIT(0, bar_empty + 8 * stage, phase ^ 1);
+                    DBG_MARK(tissue__);   // slot 12: time inside the TMA issue block (back-pressure of the TMA unit)
                     if (elect_one()) {
                         const uint32_t full = bar_full + 8 * stage;
                         const uint32_t sa = sStage + stage * stage_bytes;
@@ -809,6 +810,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         }
                     }
                     __syncwarp();
+                    DBG_ADD(12, tissue__);
                     if (++stage == p.stages) {
                         stage = 0;
                         phase ^= 1;

@@ -17,7 +17,7 @@ lib = C.load()
 kind = sys.argv[1] if len(sys.argv) > 1 else "bf16"
 only = set(sys.argv[2:])
 names = ["empty", "tempty", "full", "tfull", "zfull", "zempty", "bres", "stwait", "tmem_ld", "body", "store", "zstore_rd",
-         "x12", "x13", "x14", "x15"]
+         "tma_issue", "x13", "x14", "x15"]
 # "pw" as the only layer name: the MobileNet pointwise table (tools/bench_layers.py) instead of ResNet-50
 if only == {"pw"}:
     from tools.bench_layers import MOBILENET_PW
