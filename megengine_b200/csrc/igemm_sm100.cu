@@ -78,6 +78,7 @@ struct IgemmParams {
     uint32_t has_bias, has_z, nonline;  // has_z: z arrives through the TMA ring (NHWC)
     // NCHW4 destination (N, OC/4, OH, OW, 4): dst and z are accessed in place by the epilogue
     uint32_t nz;  // z ring depth
+    uint32_t z_jit;  // 1: the z chunks of a tile are requested only once the previous tile's accumulator is complete
     uint32_t nchw4, z_direct;
     // 1: the epilogue copies its staged rows out with coalesced st.global instead of a TMA store.  A TMA
     // store queues behind every load the producer has in flight, so waiting for it to release a slab or
@@ -923,8 +924,18 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
         if (p.has_z) {
             const uint32_t ZD = nz / T::GROUPS;
             uint32_t zcnt = 0, zph = 0;  // per group: 4-bit slot counters / 1-bit phases, packed
-            uint32_t first = 0;
-            for (uint32_t ct = t_first; ct < t_end; ct += t_step, first = (first + NUM_CHUNKS) % T::GROUPS) {
+            uint32_t first = 0, ts = 0;
+            for (uint32_t ct = t_first; ct < t_end; ct += t_step, first = (first + NUM_CHUNKS) % T::GROUPS, ++ts) {
+                // Just-in-time z (z_jit): a z slot is occupied from its TMA issue until the epilogue has stored the
+                // chunk; requested a ring depth ahead it sits idle for two tile periods, and on the layers whose
+                // k-loop is long enough to want every kilobyte for A/B stages (ResNet l3.c3 / l4.c3) that idle
+                // residency is what caps the tile rate.  Here the request waits for the PREVIOUS tile's accumulator
+                // (tfull): one tile of lead.  No parity aliasing: tfull[acc] flips again only after epilogue(ts - 1)
+                // handed the accumulator back, which needs the z chunk issued just before this wait to have landed.
+                if (p.z_jit && ts > 0) {
+                    const uint32_t prev = ts - 1;
+                    mbar_wait(bar_tfull + 8 * (prev % NACC), (prev / NACC) & 1u);
+                }
                 const uint32_t m_blk = (ct / p.n_tiles) * C + crank, n_blk = ct % p.n_tiles;
                 if (m_blk >= p.m_tiles)
                     continue;  // phantom tile
@@ -2219,6 +2230,11 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     if (const char* e = getenv("B200CB_DIRECT"))
         plan->reserved[2] = (atoi(e) != 0 && !nchw4 && !rows) ? 2u : 0u;
 #endif
+#ifdef B200CB_TOOLS
+    if (const char* e = getenv("B200CB_ZJIT"))
+        if (atoi(e) != 0 && d.has_z && !nchw4 && !rows)
+            plan->reserved[2] |= 4u;
+#endif
     plan->reserved[3] = 0;  // 1: `filter` passed to launch is already packed (weight preprocess)
     plan->reserved[4] = (g.folded ? 1u : 0u) | (ring ? 2u : 0u);  // bit 0: W-folded (packed filter), bit 1: row ring
     plan->reserved[5] = kb_bytes | (nz << 16);
@@ -2561,6 +2577,7 @@ int launch_dense(
     }
     p.z = z;
     p.nz = (plan.reserved[5] >> 16) ? (plan.reserved[5] >> 16) : NZ_MIN;
+    p.z_jit = (plan.reserved[2] >> 2) & 1u;
     p.nonline = d.nonline_mode;
     p.rq = make_requant(d);
 #ifdef B200CB_DEBUG_TIMING
