@@ -754,20 +754,37 @@ def main():
     host_us_per_exec = sorted(t_host)[1] * 1e6 / n_layers
 
     # ---------------- timed region 2: end to end from host buffers
-    # The serving pipeline a user of the operator runs.  Per micro-batch, inside the timed region: the
-    # un-padded 3-channel input is copied from pinned host memory (H2D), zero-padded to the stem's 4 channels
-    # on the device (b200cb_relayout NHWC_PAD_C -- gopt's channel padding as a first-class op), run through
-    # the 53 layers, and the final activations are copied back (D2H) and read on the host.  Double buffered
-    # on copy streams: the H2D of micro-batch i+1 and the D2H of i-1 overlap the layers of i.
+    # The serving pipeline a user of the operators runs.  Per micro-batch, inside the timed region: the 3-channel
+    # int8 image batch is copied from pinned host memory (H2D, 38.5 MB), converted on the device to the network's
+    # dtype (b200cb_typecvt: QuantizedS8(1/64) -> BFloat16 / Float16, exact; the QuantizedS8 network takes it as is),
+    # zero-padded to the stem's channel count (b200cb_relayout NHWC_PAD_C -- gopt's channel padding as a first-class
+    # op), run through the 53 layers, reduced by the network's next operator -- the global average pool
+    # (b200cb_pooling) -- and the pooled features (256 x 2048) are copied back (D2H) and read on the host.  Double
+    # buffered on copy streams: the H2D of micro-batch i+1 and the D2H of i-1 overlap the layers of i.  (Round 1
+    # shipped bf16 images and read back the whole 7x7x2048 activations, 154 MB per micro-batch: at 8 GPUs that
+    # pipeline was bound by the host's aggregate DMA bandwidth, 139 GB/s, not by any GPU.)
     e2e = None
     if nhwc:
         es = S0.tensor.element_size()
-        h_in, h_in_kind = pinned_input((MICRO_BATCH, 224, 224, ic_real), S0.tensor.dtype, args.host_input)
-        h_in.copy_(gen_input(first // MICRO_BATCH).cpu())
+        img_scale = 1.0 / 64.0
+        h_in, h_in_kind = pinned_input((MICRO_BATCH, 224, 224, ic_real), torch.int8, args.host_input)
+        x0 = gen_input(first // MICRO_BATCH)
+        img = x0 if args.dtype == "qs8" else torch.clamp(torch.round(x0.float() * 32.0), -128, 127).to(torch.int8)
+        h_in.copy_(img.cpu())
+        del x0, img
+        to_net = args.dtype != "qs8"                           # int8 image -> 16-bit network input on the device
+        net_dt = {"bf16": C.DT_BF16, "f16": C.DT_F16, "qs8": C.DT_QS8}[args.dtype]
         d_raw = [torch.empty_like(h_in, device=device) for _ in range(2)]
+        d_cvt = [torch.empty(h_in.shape, dtype=S0.tensor.dtype, device=device) for _ in range(2)] if to_net else d_raw
         d_in = [mb.make_tensor(torch.zeros_like(S0.tensor), S0.layout.dtype) for _ in range(2)]
         d_out = [mb.make_tensor(torch.empty_like(DN.tensor), DN.layout.dtype) for _ in range(2)]
-        h_out = [torch.empty(DN.tensor.shape, dtype=DN.tensor.dtype).pin_memory() for _ in range(2)]
+        n_img, fh, fw, fc = DN.tensor.shape
+        d_feat = [torch.empty((n_img, 1, 1, fc), dtype=DN.tensor.dtype, device=device) for _ in range(2)]
+        h_out = [torch.empty((n_img, 1, 1, fc), dtype=DN.tensor.dtype).pin_memory() for _ in range(2)]
+        pd = C.PoolDesc()
+        pd.format, pd.mode, pd.dtype = C.FORMAT_NHWC, C.POOL_AVERAGE, net_dt
+        pd.n, pd.c, pd.ih, pd.iw, pd.oh, pd.ow = n_img, fc, fh, fw, 1, 1
+        pd.window_h, pd.window_w, pd.stride_h, pd.stride_w, pd.pad_h, pd.pad_w = fh, fw, fh, fw, 0, 0
         comp = torch.cuda.current_stream()
         s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
         ev_in = [torch.cuda.Event() for _ in range(2)]
@@ -783,16 +800,22 @@ def main():
                 d_raw[b].copy_(h_in, non_blocking=True)
                 ev_in[b].record(s_in)
             comp.wait_event(ev_in[b])
-            comp.wait_event(ev_out[b])                      # micro-batch i-2's result has left d_out[b]
+            comp.wait_event(ev_out[b])                      # micro-batch i-2's result has left d_feat[b]
+            if to_net:
+                rc = lib.b200cb_typecvt(C.DT_QS8, img_scale, net_dt, 0.0, pixels * ic_real, d_raw[b].data_ptr(),
+                                        d_cvt[b].data_ptr(), comp.cuda_stream)
+                assert rc == 0, C.strerror(rc)
             rc = lib.b200cb_relayout(C.RELAYOUT_NHWC_PAD_C, es, 1, ic_real, 1, pixels, ic_pad,
-                                     d_raw[b].data_ptr(), d_in[b].tensor.data_ptr(), comp.cuda_stream)
+                                     d_cvt[b].data_ptr(), d_in[b].tensor.data_ptr(), comp.cuda_stream)
             assert rc == 0, C.strerror(rc)
             ev_free[b].record(comp)
             run_microbatch(layers, d_in[b], d_out[b])
+            rc = lib.b200cb_pooling(ctypes.byref(pd), d_out[b].tensor.data_ptr(), d_feat[b].data_ptr(), comp.cuda_stream)
+            assert rc == 0, C.strerror(rc)
             ev_done[b].record(comp)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_done[b])
-                h_out[b].copy_(d_out[b].tensor, non_blocking=True)
+                h_out[b].copy_(d_feat[b], non_blocking=True)
                 ev_out[b].record(s_out)
 
         e2e_steps = max(1, min(args.steps, 3))
@@ -816,14 +839,39 @@ def main():
         e2e_ms = max_over_ranks((time.perf_counter() - t0) * 1e3)
         h_in_bytes = h_in.numel() * h_in.element_size()
         h_out_bytes = h_out[0].numel() * h_out[0].element_size()
+        # the result that reached the host is the pooling of the activations the last micro-batch left on the
+        # device: 2 images against the oracle's pooling (test infrastructure, after the timed region), bit for bit
+        result_check = None
+        if not args.no_validate and rank == 0:
+            try:
+                from tests import _nn as N
+                lb = (n_mb - 1) & 1
+                torch.cuda.synchronize()
+                k = 2
+                act = d_out[lb].tensor[:k].contiguous().cpu()
+                raw = act.view(torch.int16).numpy().view("uint16") if es == 2 else act.numpy()
+                od = N.pool_desc(C.FORMAT_NHWC, C.POOL_AVERAGE, net_dt, k, fc, fh, fw, (fh, fw), (fh, fw), 0)
+                want = N.pooling("oracle", od, raw.reshape(-1))
+                got_t = h_out[lb][:k].contiguous()
+                got = got_t.view(torch.int16).numpy().view("uint16") if es == 2 else got_t.numpy()
+                bad = int((got.reshape(-1) != want).sum())
+                result_check = {"images": k, "mismatching_elements": bad}
+                if bad:
+                    sys.stderr.write("bench.py: e2e result check FAILED: %d pooled features differ from the oracle\n" % bad)
+                    sys.exit(1)
+            except ImportError:
+                result_check = {"skipped": "oracle not importable"}
         e2e = {"value": args.global_batch * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
                "h2d_bytes_per_step": h_in_bytes * mbs * world, "d2h_bytes_per_step": h_out_bytes * mbs * world,
                "steps": e2e_steps, "h2d_bytes_per_gpu_microbatch": h_in_bytes, "d2h_bytes_per_gpu_microbatch": h_out_bytes,
-               "host_input_memory": h_in_kind,
+               "host_input_memory": h_in_kind, "host_input": "int8 images (256 x 224 x 224 x 3), scale 1/64",
+               "result": "global-average-pooled features (256 x %d) of the last layer's activations" % fc,
+               "result_check_vs_oracle": result_check,
                "host_copy_gbs_all_gpus": (h_in_bytes + h_out_bytes) * mbs * world * e2e_steps / (e2e_ms * 1e-3) / 1e9,
-               "pipeline": "per 256-image micro-batch: H2D of the un-padded 3-channel input, device channel padding "
-                           "(b200cb_relayout), 53 layers, D2H of the final activations; double-buffered on copy streams"}
-        del d_raw, d_in, d_out, h_out, h_in
+               "pipeline": "per 256-image micro-batch: H2D of the 3-channel int8 images, device TypeCvt to the network dtype "
+                           "(b200cb_typecvt) and channel padding (b200cb_relayout), 53 ConvBias layers, global average pool "
+                           "(b200cb_pooling), D2H of the pooled features; double-buffered on copy streams"}
+        del d_raw, d_cvt, d_in, d_out, d_feat, h_out, h_in
 
     # ---------------- parity (after the timed regions; never inside them)
     parity = None
