@@ -630,3 +630,32 @@ def test_int8_depthwise_3x3_window_kernel(case):
                     scales=(0.37, 0.71, None, 1.9, 23.0))
     _plan, info = _check(d, {"int_range": 127, "bias_range": 5000}, seed=131 + c)
     assert info["mismatch"] == 0
+
+
+FP16_DEFAULT_CASES = [
+    ("1x1_relu", 2, 64, 14, 14, 256, 1, 1, 0, C.NL_RELU, False),
+    ("3x3_z_relu", 2, 64, 14, 14, 128, 3, 1, 1, C.NL_RELU, True),
+    ("3x3_s2_hswish", 3, 32, 15, 15, 64, 3, 2, 1, C.NL_H_SWISH, False),
+    ("5x5_ic16_identity", 2, 16, 12, 12, 32, 5, 1, 2, C.NL_IDENTITY, False),
+]
+
+
+@pytest.mark.parametrize("case", FP16_DEFAULT_CASES, ids=[c[0] for c in FP16_DEFAULT_CASES])
+def test_fp16_default_compute_mode(case):
+    """Float16 with param.compute_mode = DEFAULT (what imperative F.conv2d sends): the naive oracle accumulates in
+    fp16, the B200 kernel -- like the reference's CUDA algorithms -- in fp32; the reference's CUDA tests compare the
+    two at 2e-2 (dnn/test/cuda/conv_bias.cpp:242-247,663-664) on shapes with K = IC * FH * FW up to a few hundred,
+    and so does this one (at K = 2304 the oracle's own fp16 accumulation error exceeds that bound).  Against the fp32
+    reference the kernel keeps its usual 2e-3."""
+    from . import _gpu as G
+    _name, n, ic, h, w, oc, f, s, pd, nl, has_z = case
+    d = K.make_desc("f16", n, ic, h, w, oc, f, stride=s, pad=pd, nonline=nl, has_z=has_z, compute_mode=C.COMPUTE_DEFAULT)
+    src, flt, bias, z = K.gen_inputs(d, 99)
+    want = O.oracle_convbias(d, src, flt, bias, z)            # fp16 accumulation
+    got, _plan = G.run_gpu(d, src, flt, bias, z)
+    err = O.megdnn_rel_err(O.to_f32(got, C.DT_F16), O.to_f32(want, C.DT_F16)).max()
+    assert err <= 2e-2, (K.desc_str(d), err)
+    d32 = d.copy()
+    d32.compute_mode = C.COMPUTE_FLOAT32
+    ok, info = G.compare(d32, got, None, K.fp32_reference(d32, src, flt, bias, z))
+    assert ok, info
