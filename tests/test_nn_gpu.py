@@ -211,3 +211,61 @@ def test_batch_convbias_per_image_filters(handle):
     opr.exec(tsrc, tflt, tbias, z, tdst, ws)
     torch.cuda.synchronize()
     assert int((_raw(tdst, tdst.layout.dtype) != want).sum()) == 0
+
+
+def test_deconvolution_is_the_adjoint_of_convolution_full_size(handle):
+    """Size-independent property at a size the oracle cannot finish: <conv(x, w), y> == <x, deconv(w, y)> exactly in
+    integers (QuantizedS8 operands, QuantizedS32 results) -- stride 2, so the phase decomposition, its sub-filters,
+    temporaries and the interleave pass are all on the path, against the forward kernel that the rest of the suite pins."""
+    n, ic, ih, oc, f, s, pd = 64, 64, 56, 128, 3, 2, 1
+    g = torch.Generator(device="cuda")
+    g.manual_seed(11)
+    q8, q32 = M.dtype.QuantizedS8, M.dtype.QuantizedS32
+    x = torch.randint(-20, 21, (n, ih, ih, ic), dtype=torch.int8, device="cuda", generator=g)
+    w = torch.randint(-20, 21, (oc, f, f, ic), dtype=torch.int8, device="cuda", generator=g)
+    fwd = M.ConvolutionForward(handle)
+    fwd.param.format, fwd.param.pad_h, fwd.param.pad_w, fwd.param.stride_h, fwd.param.stride_w = C.FORMAT_NHWC, pd, pd, s, s
+    X = M.TensorND(x, M.TensorLayout(tuple(x.shape), q8(0.5)))
+    W = M.TensorND(w, M.TensorLayout(tuple(w.shape), q8(0.25)))
+    lay = fwd.deduce_layout(X.layout, W.layout)
+    oh = lay.shape[1]
+    Y = _out(lay.shape, lay.dtype)
+    nb = fwd.get_workspace_in_bytes(X.layout, W.layout, Y.layout)
+    fwd.exec(X, W, Y, None, torch.empty(nb, dtype=torch.uint8, device="cuda") if nb else None)
+    y = torch.randint(-20, 21, (n, oh, oh, oc), dtype=torch.int8, device="cuda", generator=g)
+    bwd = M.ConvolutionBackwardData(handle)
+    bwd.param.format, bwd.param.pad_h, bwd.param.pad_w, bwd.param.stride_h, bwd.param.stride_w = C.FORMAT_NHWC, pd, pd, s, s
+    Yd = M.TensorND(y, M.TensorLayout(tuple(y.shape), q8(0.5)))
+    Gx = _out((n, ih, ih, ic), q32(0.125))
+    ws = torch.empty(bwd.get_workspace_in_bytes(W.layout, Yd.layout, Gx.layout), dtype=torch.uint8, device="cuda")
+    plan = bwd.exec(W, Yd, Gx, ws)
+    assert plan.reserved[0] == 1          # the phase decomposition ran
+    torch.cuda.synchronize()
+    lhs = int((Y.tensor.to(torch.int64) * y.to(torch.int64)).sum().item())
+    rhs = int((Gx.tensor.to(torch.int64) * x.to(torch.int64)).sum().item())
+    assert lhs == rhs and lhs != 0, (lhs, rhs)
+
+
+@pytest.mark.parametrize("dt", ["bf16", "qs8"])
+def test_max_pool_full_size_against_an_independent_reference(dt, handle):
+    """the ResNet stem pool at N = 256 (too large for the CPU oracle): max is exact in any arithmetic, so torch's
+    max_pool2d on the same tensor is an independent bit-exact reference for the packed-word maximum paths."""
+    n, c, hw = 256, 64, 112
+    g = torch.Generator(device="cuda")
+    g.manual_seed(5)
+    if dt == "bf16":
+        x = torch.randn((n, hw, hw, c), device="cuda", generator=g).to(torch.bfloat16)
+        mdt = M.dtype.BFloat16()
+    else:
+        x = torch.randint(-128, 128, (n, hw, hw, c), dtype=torch.int8, device="cuda", generator=g)
+        mdt = M.dtype.QuantizedS8(0.1)
+    opr = M.PoolingForward(handle)
+    p = opr.param
+    p.mode, p.format, p.window_h, p.window_w, p.stride_h, p.stride_w, p.pad_h, p.pad_w = C.POOL_MAX, C.FORMAT_NHWC, 3, 3, 2, 2, 1, 1
+    X = M.TensorND(x, M.TensorLayout(tuple(x.shape), mdt))
+    lay = opr.deduce_layout(X.layout)
+    Y = _out(lay.shape, mdt)
+    opr.exec(X, Y)
+    ref = torch.nn.functional.max_pool2d(x.permute(0, 3, 1, 2).float(), 3, 2, 1).permute(0, 2, 3, 1).to(x.dtype)
+    torch.cuda.synchronize()
+    assert torch.equal(Y.tensor, ref.contiguous())
