@@ -20,9 +20,10 @@ fi
 CUDA=${CUDA_HOME:-/usr/local/cuda}
 INC="-I$REF/dnn/include -I$GEN/gen -I$GEN/genfiles -I$ROOT/include -I$SRC -I$CUDA/include"
 OUT="$GEN/libmegdnn_b200.so"
-if [ ! -f "$OUT" ] || [ "$SRC/conv_bias_b200.cpp" -nt "$OUT" ] || \
-   [ "$SRC/conv_bias_b200.h" -nt "$OUT" ] || [ "$ROOT/include/b200cb.h" -nt "$OUT" ]; then
-    g++ -std=c++17 -O2 -fPIC -w -shared -o "$OUT" "$SRC/conv_bias_b200.cpp" $INC \
+if [ ! -f "$OUT" ] || [ "$SRC/conv_bias_b200.cpp" -nt "$OUT" ] || [ "$SRC/nn_b200.cpp" -nt "$OUT" ] || \
+   [ "$SRC/conv_bias_b200.h" -nt "$OUT" ] || [ "$SRC/nn_b200.h" -nt "$OUT" ] || [ "$ROOT/include/b200cb.h" -nt "$OUT" ] || \
+   [ "$ROOT/include/b200cb_nn.h" -nt "$OUT" ]; then
+    g++ -std=c++17 -O2 -fPIC -w -shared -o "$OUT" "$SRC/conv_bias_b200.cpp" "$SRC/nn_b200.cpp" $INC \
         -L"$LIB" -lb200cb -L"$GEN" -lmegdnn_ref -Wl,-rpath,'$ORIGIN' -Wl,-rpath,'$ORIGIN/../../megengine_b200/lib'
     echo "build_host.sh: built $OUT"
 fi

@@ -21,6 +21,7 @@
 #include <vector>
 
 #include "conv_bias_b200.h"
+#include "nn_b200.h"
 #include "megcore.h"
 #include "megdnn/dtype.h"
 #include "megdnn/handle.h"
@@ -205,6 +206,111 @@ bool run_case(Handle* host, cudaStream_t stream, const Case& c) {
     return all_ok;
 }
 
+// ---- the operators either side of ConvBias (megengine_b200/host/nn_b200.h): each B200 operator against the
+// reference's naive operator of the same class on the same TensorNDs, bit for bit
+bool same_bytes(const std::vector<uint8_t>& a, const std::vector<uint8_t>& b, const char* name) {
+    size_t bad = 0;
+    for (size_t i = 0; i < a.size(); ++i)
+        bad += a[i] != b[i];
+    printf("%s %-28s %zu / %zu bytes differ\n", bad ? "FAIL" : "PASS", name, bad, a.size());
+    return bad == 0;
+}
+
+int run_nn_cases(Handle* host, cudaStream_t stream) {
+    int failed = 0;
+    std::mt19937 rng(77);
+    // TypeCvt: QuantizedS32 -> QuantizedS8 (the requantize between int8 blocks), Float32 -> BFloat16, QuantizedS8 -> Float16
+    struct Cvt { const char* name; DType s, d; };
+    const Cvt cvts[] = {{"typecvt_qs32_qs8", dtype::QuantizedS32(0.0013f), dtype::QuantizedS8(0.9f)},
+                        {"typecvt_f32_bf16", dtype::Float32(), dtype::BFloat16()},
+                        {"typecvt_qs8_f16", dtype::QuantizedS8(0.3f), dtype::Float16()}};
+    for (auto& c : cvts) {
+        const size_t n = 100003;
+        TensorLayout ls({n}, c.s), ld({n}, c.d);
+        std::vector<uint8_t> hs, want(n * c.d.size()), got(n * c.d.size());
+        fill(hs, c.s, n, rng, 3.f);
+        host->create_operator<TypeCvt>()->exec(TensorND(hs.data(), ls), TensorND(want.data(), ld));
+        DevBuf ds(hs.size()), dd(got.size());
+        CUDA_OK(cudaMemcpyAsync(ds.p, hs.data(), hs.size(), cudaMemcpyHostToDevice, stream));
+        b200::create_type_cvt(host, stream)->exec(TensorND(ds.p, ls), TensorND(dd.p, ld));
+        CUDA_OK(cudaMemcpyAsync(got.data(), dd.p, got.size(), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        failed += !same_bytes(got, want, c.name);
+    }
+    // Elemwise: FUSE_ADD_RELU (the residual add gopt leaves when z-fusion is not legal), bf16 and fp16; H_SWISH fp32
+    struct El { const char* name; param::Elemwise::Mode mode; DType dt; int arity; };
+    const El els[] = {{"elemwise_add_relu_bf16", param::Elemwise::Mode::FUSE_ADD_RELU, dtype::BFloat16(), 2},
+                      {"elemwise_add_relu_f16", param::Elemwise::Mode::FUSE_ADD_RELU, dtype::Float16(), 2},
+                      {"elemwise_hswish_f32", param::Elemwise::Mode::H_SWISH, dtype::Float32(), 1}};
+    for (auto& c : els) {
+        TensorLayout l({3, 14, 14, 40}, c.dt);
+        const size_t n = l.total_nr_elems();
+        std::vector<uint8_t> ha, hb, want(n * c.dt.size()), got(n * c.dt.size());
+        fill(ha, c.dt, n, rng, 2.f);
+        fill(hb, c.dt, n, rng, 2.f);
+        auto ref = host->create_operator<ElemwiseForward>();
+        ref->param().mode = c.mode;
+        TensorNDArray in;
+        in.emplace_back(ha.data(), l);
+        if (c.arity > 1)
+            in.emplace_back(hb.data(), l);
+        ref->exec(in, TensorND(want.data(), l));
+        DevBuf da(ha.size()), db(hb.size()), dd(got.size());
+        CUDA_OK(cudaMemcpyAsync(da.p, ha.data(), ha.size(), cudaMemcpyHostToDevice, stream));
+        CUDA_OK(cudaMemcpyAsync(db.p, hb.data(), hb.size(), cudaMemcpyHostToDevice, stream));
+        auto dut = b200::create_elemwise(host, stream);
+        dut->param().mode = c.mode;
+        TensorNDArray din;
+        din.emplace_back(da.p, l);
+        if (c.arity > 1)
+            din.emplace_back(db.p, l);
+        dut->exec(din, TensorND(dd.p, l));
+        CUDA_OK(cudaMemcpyAsync(got.data(), dd.p, got.size(), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        failed += !same_bytes(got, want, c.name);
+    }
+    // Pooling: the ResNet stem max pool (bf16 NHWC), global average (QuantizedS8 NHWC), max pool NCHW4 int8
+    struct Po { const char* name; param::Pooling::Format fmt; param::Pooling::Mode mode; DType dt; size_t n, c, h, w, win, st, pad; };
+    const Po pos[] = {
+            {"pool_max3s2_bf16_nhwc", param::Pooling::Format::NHWC, param::Pooling::Mode::MAX, dtype::BFloat16(), 2, 64, 28, 28, 3, 2, 1},
+            {"pool_avg7_qs8_nhwc", param::Pooling::Format::NHWC, param::Pooling::Mode::AVERAGE, dtype::QuantizedS8(0.5f), 3, 128, 7, 7, 7, 7, 0},
+            {"pool_avgx3s2_f16_nhwc", param::Pooling::Format::NHWC, param::Pooling::Mode::AVERAGE_COUNT_EXCLUDE_PADDING, dtype::Float16(), 2, 24, 9, 11, 3, 2, 1},
+            {"pool_max3s2_qs8_nchw4", param::Pooling::Format::NCHW4, param::Pooling::Mode::MAX, dtype::QuantizedS8(0.5f), 2, 16, 15, 15, 3, 2, 1}};
+    for (auto& c : pos) {
+        auto ref = host->create_operator<PoolingForward>();
+        auto dut = b200::create_pooling(host, stream);
+        for (PoolingForward* o : {ref.get(), dut.get()}) {
+            auto& p = o->param();
+            p.format = c.fmt, p.mode = c.mode;
+            p.window_h = p.window_w = c.win, p.stride_h = p.stride_w = c.st, p.pad_h = p.pad_w = c.pad;
+        }
+        TensorLayout ls = c.fmt == param::Pooling::Format::NHWC ? TensorLayout({c.n, c.h, c.w, c.c}, c.dt)
+                                                                 : TensorLayout({c.n, c.c / 4, c.h, c.w, 4}, c.dt);
+        TensorLayout ld, ld2;
+        ld.dtype = ld2.dtype = c.dt;
+        ref->deduce_layout(ls, ld);
+        dut->deduce_layout(ls, ld2);
+        if (!ld.eq_layout(ld2)) {
+            printf("FAIL %-28s deduce_layout differs\n", c.name);
+            ++failed;
+            continue;
+        }
+        const size_t ne = ls.total_nr_elems(), no = ld.total_nr_elems();
+        std::vector<uint8_t> hs, want(no * c.dt.size()), got(no * c.dt.size());
+        fill(hs, c.dt, ne, rng, 2.f);
+        std::vector<dt_byte> ws(ref->get_workspace_in_bytes(ls, ld) + 64);
+        ref->exec(TensorND(hs.data(), ls), TensorND(want.data(), ld), Workspace(ws.data(), ws.size() - 64));
+        DevBuf ds(hs.size()), dd(got.size());
+        CUDA_OK(cudaMemcpyAsync(ds.p, hs.data(), hs.size(), cudaMemcpyHostToDevice, stream));
+        auto algos = dut->get_all_algorithms_info(ls, ld);
+        dut->exec(TensorND(ds.p, ls), TensorND(dd.p, ld), Workspace(nullptr, 0));
+        CUDA_OK(cudaMemcpyAsync(got.data(), dd.p, got.size(), cudaMemcpyDeviceToHost, stream));
+        CUDA_OK(cudaStreamSynchronize(stream));
+        failed += !(same_bytes(got, want, c.name) && algos.size() == 1);
+    }
+    return failed;
+}
+
 }  // namespace
 
 int main() {
@@ -331,6 +437,12 @@ int main() {
         CUDA_OK(cudaStreamSynchronize(stream));
         const double us = ((t1.tv_sec - t0.tv_sec) * 1e9 + (t1.tv_nsec - t0.tv_nsec)) / 1e3 / reps;
         printf("INFO host_us_per_exec %.2f (C++ binding, enqueue only, %d execs)\n", us, reps);
+    }
+    try {
+        failed += run_nn_cases(host.get(), stream);
+    } catch (const std::exception& e) {
+        printf("FAIL %-28s exception: %s\n", "nn_operators", e.what());
+        ++failed;
     }
     printf("dropin_driver: %d failed\n", failed);
     return failed ? 1 : 0;

@@ -32,4 +32,8 @@ def test_dropin_driver_all_cases_pass():
     print(r.stdout[-4000:], r.stderr[-2000:])
     assert r.returncode == 0, r.stdout[-4000:] + r.stderr[-2000:]
     assert "PASS nchw4_qs8_3x3_z_relu" in r.stdout and "PASS nhwc_bf16_3x3_z_relu" in r.stdout
+    # the operators either side of ConvBias through the reference's abstract TypeCvt / Elemwise / Pooling interfaces
+    for name in ("typecvt_qs32_qs8", "elemwise_add_relu_f16", "pool_max3s2_bf16_nhwc", "pool_avg7_qs8_nhwc",
+                 "pool_max3s2_qs8_nchw4"):
+        assert "PASS " + name in r.stdout, name
     assert "0 failed" in r.stdout
