@@ -193,13 +193,18 @@ __global__ void __launch_bounds__(256) pool_kernel(
                 // the 3x3 window (ResNet stem pool): all nine loads issued before the first use
                 Vec<T, V> x[9];
                 bool ok[9];
+                // one base pointer (tap (0, 0), possibly outside the image: only dereferenced where ok) and two
+                // strides: the kernel is bound by its index arithmetic, not by the loads
+                const ptrdiff_t rs = (ptrdiff_t)p.iw * pitch;
+                const T* p00 = sb + ((ptrdiff_t)h0 * p.iw + w0) * (ptrdiff_t)pitch;
+                const bool rok[3] = {fh_lo == 0 && fh_hi > 0, fh_lo <= 1 && fh_hi > 1, fh_hi > 2};
+                const bool cok[3] = {fw_lo == 0 && fw_hi > 0, fw_lo <= 1 && fw_hi > 1, fw_hi > 2};
 #pragma unroll
                 for (uint32_t t = 0; t < 9; ++t) {
                     const uint32_t fh = t / 3, fw = t % 3;
-                    ok[t] = fh >= fh_lo && fh < fh_hi && fw >= fw_lo && fw < fw_hi;
+                    ok[t] = rok[fh] && cok[fw];
                     if (ok[t])
-                        x[t] = *reinterpret_cast<const Vec<T, V>*>(
-                                sb + ((size_t)(h0 + (int32_t)fh) * p.iw + (w0 + (int32_t)fw)) * pitch);
+                        x[t] = *reinterpret_cast<const Vec<T, V>*>(p00 + (ptrdiff_t)fh * rs + (ptrdiff_t)fw * pitch);
                 }
 #pragma unroll
                 for (uint32_t t = 0; t < 9; ++t)
