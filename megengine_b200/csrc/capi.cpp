@@ -83,6 +83,12 @@ double igemm_cost(const b200cb_desc& d, const b200cb_plan& plan, uint32_t bn, in
     if (d.has_z && plan.kernel == KERNEL_IGEMM && d.format == B200CB_FORMAT_NHWC && (plan.reserved[5] >> 16) < 8 &&
         bn > 128 && (uint64_t)d.fh * d.fw * d.ic * dtype_size(d.src_dtype) <= 512)
         cost *= 2.5;
+    // QuantizedS8 residual layers whose 256-wide filter tile cannot stay resident (IgemmParams::b_res: K * BN > 64 KiB)
+    // run faster on the narrower tile that can (l4.c3: 128x128 resident 0.026 ms, 128x256 streamed 0.030)
+    if (d.has_z && plan.kernel == KERNEL_IGEMM && d.src_dtype == B200CB_DT_QS8 && !(plan.reserved[2] & 8u) && bn > 128 &&
+        d.format == B200CB_FORMAT_NHWC && d.group <= 1 && d.fh == 1 && d.fw == 1 && d.stride_h == 1 && d.stride_w == 1 &&
+        d.pad_h == 0 && d.pad_w == 0 && d.src_batch_stride == 0 && (uint64_t)d.ic * 128 <= 64 * 1024)
+        cost *= 2.5;
     return cost;
 }
 // ---- NCHW adapter (fp16 / bf16): the tensor-core kernels want channels innermost, so NCHW tensors are

@@ -78,6 +78,10 @@ struct IgemmParams {
     uint32_t has_bias, has_z, nonline;  // has_z: z arrives through the TMA ring (NHWC)
     // NCHW4 destination (N, OC/4, OH, OW, 4): dst and z are accessed in place by the epilogue
     uint32_t nz;  // z ring depth
+    // 1 (a_mode 0, single CTA): the CTA's filter tile (all k-blocks of ONE N tile) is loaded once and stays in shared
+    // memory; the grid is a multiple of n_tiles, so every tile of a CTA has the same N index and the pipeline
+    // stages carry the activations only (half the bytes in flight per tile on the residual 1x1 layers)
+    uint32_t b_res;
     uint32_t z_jit;  // 1: the z chunks of a tile are requested only once the previous tile's accumulator is complete
     uint32_t nchw4, z_direct;
     // 1: the epilogue copies its staged rows out with coalesced st.global instead of a TMA store.  A TMA
@@ -351,8 +355,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     // CTA pair: each CTA stages only its half of the filter tile's rows
     constexpr bool pair = PAIR != 0;
     const uint32_t b_rows = pair ? BN / 2 : BN;
-    const uint32_t stage_bytes = (stem || rows) ? a_bytes : a_bytes + b_rows * p.kb_bytes;
-    const uint32_t bres_bytes = stem ? p.stem_fh * BN * stem_rb : rows ? p.num_taps * p.num_kc * BN * p.kb_bytes : 0u;
+    const bool bres_tiled = p.b_res != 0;  // generic 1x1 path with the N tile's filter resident
+    const uint32_t stage_bytes = (stem || rows || bres_tiled) ? a_bytes : a_bytes + b_rows * p.kb_bytes;
+    const uint32_t bres_bytes = stem ? p.stem_fh * BN * stem_rb
+                                     : (rows || bres_tiled) ? p.num_taps * p.num_kc * BN * p.kb_bytes : 0u;
     const uint32_t sZ = smem_base + OFF_SZ;
     constexpr uint32_t NSLAB = T::nslab(BN);
     const uint32_t nz = p.nz;
@@ -749,6 +755,14 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
     } else if (warp == 0) {
         // ============================ TMA producer (A, B) ============================
         uint32_t stage = 0, phase = 0;
+        if (bres_tiled && t_first < t_end && elect_one()) {
+            // resident filter tile: every tile of this CTA has N index t_first % n_tiles (grid % n_tiles == 0)
+            const int32_t n0 = static_cast<int32_t>((t_first % p.n_tiles) * BN);
+            mbar_arrive_expect_tx(bar_bres, bres_bytes);
+            for (uint32_t kc = 0; kc < p.num_kc; ++kc)
+                tma_load_3d(sBres + kc * BN * p.kb_bytes, &p.tmB, bar_bres, static_cast<int32_t>(kc * p.kb_elems), 0, n0);
+        }
+        __syncwarp();
         for (uint32_t ct = t_first; ct < t_end; ct += t_step) {
             // a phantom tile (M tiles not a multiple of C) re-loads the last valid tile: every CTA of the
             // cluster must run the same k-loop because the filter slices are exchanged in lock step
@@ -799,7 +813,9 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                     static_cast<uint16_t>(fw * p.dil_w),
                                     static_cast<uint16_t>(fh * p.dil_h));
                         }
-                        if (C == 1) {
+                        if (bres_tiled) {
+                            // (filter resident: the stage is the activation tile alone)
+                        } else if (C == 1) {
                             tma_load_3d(sb, &p.tmB, full, c0, static_cast<int32_t>(btap), n0);
                         } else {
                             // this CTA's 1/C of the filter tile's rows, delivered to every CTA of the cluster
@@ -861,8 +877,12 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             constexpr uint32_t NM = decltype(NM_)::value;  // MMAs (32 bytes of K each) per k-block
             uint32_t stage = 0, phase = 0, acc = 0, acc_phase = 0;
             const uint32_t stage16 = stage_bytes >> 4;     // descriptor units are 16 bytes
-            const uint32_t a0 = desc_lo(sStage, 16), b0 = desc_lo(sStage + a_bytes, 16);
+            const uint32_t a0 = desc_lo(sStage, 16);
+            const uint32_t b0 = bres_tiled ? desc_lo(sBres, 16) : desc_lo(sStage + a_bytes, 16);
+            const uint32_t bres16 = (BN * p.kb_bytes) >> 4;  // resident filter: one k-block of the tile
             uint32_t soff = 0;
+            if (bres_tiled && t_first < t_end)
+                TIMED_WAIT(6, bar_bres, 0);
             for (uint32_t ct = t_first; ct < t_end; ct += t_step) {
                 TIMED_WAIT(1, bar_tempty + 8 * acc, acc_phase ^ 1);
                 tc_fence_after();
@@ -871,7 +891,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                 for (uint32_t kb = 0; kb < num_kb; ++kb) {
                     TIMED_WAIT(2, bar_full + 8 * stage, phase);
                     tc_fence_after();
-                    const uint32_t a_lo = a0 + soff, b_lo = b0 + soff;
+                    const uint32_t a_lo = a0 + soff, b_lo = b0 + (bres_tiled ? kb * bres16 : soff);
                     issue_first(taddr, a_lo, b_lo, accum);
                     accum = 1;
 #pragma unroll
@@ -1689,6 +1709,8 @@ cudaError_t launch_variant(
     const uint64_t cluster_tiles = (total_tiles + C - 1) / C;
     if (grid / C > cluster_tiles)
         grid = static_cast<uint32_t>(cluster_tiles) * C;
+    else if (p.b_res)  // every tile of a CTA must share one N index: tile step == grid == k * n_tiles
+        grid = grid < p.n_tiles ? p.n_tiles : grid / p.n_tiles * p.n_tiles;
     cfg.gridDim = dim3(grid, 1, 1);
     return cudaLaunchKernelEx(&cfg, kern, p);
 }
@@ -1894,6 +1916,27 @@ bool pick_direct_store(const b200cb_desc& d, bool nchw4, bool rows) {
     // direct path; it stays reachable through the tools build (B200CB_DIRECT=1) and its parity run.
     (void)d;
     return false;
+}
+
+// Resident filter tile (IgemmParams::b_res) for 1x1 stride-1 layers run by single CTAs: the CTA's N tile of the
+// filter (all k-blocks) is loaded once, the stages carry activations only.  What it buys is shared-memory
+// residency: on the residual 1x1 layers a slot is occupied from its TMA issue to the end of its MMA, and halving
+// the bytes a tile keeps in flight raises the tile rate the 227 KB can sustain.
+bool pick_bres(const b200cb_desc& d, uint32_t block_n, uint32_t k_bytes, uint32_t kb_bytes, uint64_t m_tiles) {
+    const uint32_t n_tiles = (d.oc + block_n - 1) / block_n;
+    const uint32_t num_kc = (k_bytes + kb_bytes - 1) / kb_bytes;
+    const uint32_t bres = num_kc * block_n * kb_bytes;
+    (void)m_tiles;
+    // the grid is cut to a multiple of n_tiles; the tile must leave room for the z ring and >= 2 stages
+    if (n_tiles > 16 || bres > 64 * 1024)
+        return false;
+    // measured (tools/exp_bres.py, tools/bench_layers.py --set pw; profiles/r02/exp_resident_filter.txt):
+    //  * low-K layers (K <= 64 bytes: MobileNetV2 / ShuffleNetV2 pointwise 16->96, 24->144, 32->192, 32->16) are
+    //    bound by the number of short TMA rows per tile, of which the filter tile is 1/2 .. 2/3: bf16 0.238 -> 0.130,
+    //    0.154 -> 0.060, 0.024 -> 0.019, 0.149 -> 0.096 ms (9-layer table 40 % -> 65 % of HBM; int8 13.5 % -> 24.6 %);
+    //  * QuantizedS8 layers with longer K gain 0-10 % (l4.c3 0.029 -> 0.026) and never lose more than 1 %;
+    //  * 16-bit layers with K >= 128 bytes are within +-2 % except l2.c3 (-8 %) and K = 512 (-3 %): streamed
+    return d.src_dtype == B200CB_DT_QS8 || k_bytes <= 64;
 }
 
 uint32_t pick_kb_bytes(uint32_t ic_bytes) {
@@ -2149,11 +2192,24 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         while (!pair && cluster > 1 && (m_tiles < 2 * cluster || (block_n / cluster) % 8 != 0))
             cluster /= 2;
     }
+    const bool pointwise = d.fh == 1 && d.fw == 1 && d.stride_h == 1 && d.stride_w == 1 &&
+                           d.pad_h == 0 && d.pad_w == 0 && dd.src_batch_stride == 0;
+    // resident filter tile: plain 1x1 layers on single CTAs (a_mode 0)
+    bool b_res = false;
+    const uint32_t bres_tile = ((g.ic * in_es + kb_bytes - 1) / kb_bytes) * block_n * kb_bytes;
+    if (pointwise && !stem && !rows && !pair && cluster == 1 && !nchw4 && !grouped) {
+        b_res = pick_bres(d, block_n, g.ic * in_es, kb_bytes, (M + IGEMM_BLOCK_M - 1) / IGEMM_BLOCK_M);
+#ifdef B200CB_TOOLS
+        if (const char* e = getenv("B200CB_BRES"))
+            b_res = atoi(e) != 0 && (d.oc + block_n - 1) / block_n <= 16 && bres_tile <= 96 * 1024;
+#endif
+    }
     const uint32_t stem_rb = g.stem4 ? 64u : 128u;
-    const uint32_t stage_b = stem   ? (g.stem4 ? 1 : 2) * d.fh * STEM_NJ * 16
-                             : rows ? rg.a_stage
-                                    : (IGEMM_BLOCK_M + (pair ? block_n / 2 : block_n)) * kb_bytes;
-    const uint32_t fixed = fixed0 + (stem ? d.fh * block_n * stem_rb : rows ? rg.bres : 0);
+    const uint32_t stage_b = stem    ? (g.stem4 ? 1 : 2) * d.fh * STEM_NJ * 16
+                             : rows  ? rg.a_stage
+                             : b_res ? IGEMM_BLOCK_M * kb_bytes
+                                     : (IGEMM_BLOCK_M + (pair ? block_n / 2 : block_n)) * kb_bytes;
+    const uint32_t fixed = fixed0 + (stem ? d.fh * block_n * stem_rb : rows ? rg.bres : b_res ? bres_tile : 0);
     uint32_t stages = (MAX_DYN_SMEM - fixed) / stage_b;
     // stem row ring: 16 row pairs + slack for the descriptor rows past OW (read, never stored)
     const bool ring = stem && g.ring;
@@ -2218,8 +2274,6 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
     plan->stages = stages;
     plan->grid = 0;  // resolved at launch from the device's SM count
     plan->smem_bytes = smem_total;
-    const bool pointwise = d.fh == 1 && d.fw == 1 && d.stride_h == 1 && d.stride_w == 1 &&
-                           d.pad_h == 0 && d.pad_w == 0 && dd.src_batch_stride == 0;
     plan->a_mode = stem ? 2 : rows ? 3 : (pointwise ? 0 : 1);
     for (auto& r : plan->reserved)
         r = 0;
@@ -2236,6 +2290,8 @@ int igemm_query(const b200cb_desc& d0, uint32_t block_n, b200cb_plan* plan) {
         if (atoi(e) != 0 && d.has_z && !nchw4 && !rows)
             plan->reserved[2] |= 4u;
 #endif
+    if (b_res)
+        plan->reserved[2] |= 8u;  // bit 3: resident filter tile (a_mode 0)
     plan->reserved[3] = 0;  // 1: `filter` passed to launch is already packed (weight preprocess)
     plan->reserved[4] = (g.folded ? 1u : 0u) | (ring ? 2u : 0u);  // bit 0: W-folded (packed filter), bit 1: row ring
     plan->reserved[5] = kb_bytes | (nz << 16);
@@ -2579,6 +2635,8 @@ int launch_dense(
     p.z = z;
     p.nz = (plan.reserved[5] >> 16) ? (plan.reserved[5] >> 16) : NZ_MIN;
     p.z_jit = (plan.reserved[2] >> 2) & 1u;
+    // (set by the query for 1x1 layers only: one tap; the forced-im2col debugging path keeps it)
+    p.b_res = (!stem && !rows && !p.pair && p.cluster == 1 && p.num_taps == 1) ? (plan.reserved[2] >> 3) & 1u : 0u;
     p.nonline = d.nonline_mode;
     p.rq = make_requant(d);
 #ifdef B200CB_DEBUG_TIMING

@@ -370,6 +370,73 @@ def test_pair_tiles_at_n8_against_full_oracle(layer, kind, knob):
     assert plan.reserved[7] == 1
 
 
+@pytest.mark.parametrize("name,d,opt", stage_cases("gemm_tiled") + stage_cases("int8"),
+                         ids=_ids(stage_cases("gemm_tiled") + stage_cases("int8")))
+def test_resident_filter_tile_forced_on_every_pointwise_case(name, d, opt, knob):
+    """IgemmParams::b_res (the CTA's filter tile loaded once, activation-only pipeline stages) forced on every
+    1x1 stride-1 case of every dtype through the tools build; cases of another shape ignore the knob."""
+    from . import _gpu as G
+    if not os.path.exists(G.TOOLS_LIB):
+        pytest.skip("tools build not present")
+    knob("B200CB_BRES", 1)
+    knob("B200CB_PAIR", 0)
+    _check(d, opt, lib=G.tools_lib())
+
+
+@pytest.mark.parametrize("kind,spec,n", [("qs8", "l1.c3", 256), ("qs8", "l4.c3", 256), ("qs8", "l2.bN.c1", 64),
+                                         ("bf16", "l3.c3", 64), ("f16", "l2.c3", 32),
+                                         ("bf16", (16, 112, 96), 64), ("f16", (24, 56, 144), 128),
+                                         ("bf16", (32, 112, 16), 64), ("qs8", (16, 112, 96), 64)],
+                         ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else str(v))
+def test_resident_filter_tile_full_size_equals_streamed(kind, spec, n, knob):
+    """Many tiles per CTA (grid cut to a multiple of n_tiles, every CTA keeps ONE N tile of the filter): the
+    resident-filter kernel must reproduce the streamed-filter kernel bit for bit (same MMA order), and the
+    oracle on 4096 samples.  QuantizedS8 and low-K 16-bit layers (MobileNetV2 pointwise: ic, hw, oc) are resident
+    by the product heuristic; the other 16-bit layers force it through the tools build."""
+    import torch
+    from . import _gpu as G
+    if isinstance(spec, tuple):
+        ic, hw, oc = spec
+        d = K.make_desc(kind, n, ic, hw, hw, oc, 1, nonline=C.NL_RELU)
+    else:
+        layer = [l for l in K.RESNET50_LAYERS if l[0] == spec][0]
+        d = K.resnet50_desc(layer, kind, n)
+    by_default = kind == "qs8" or d.ic * 2 <= 64
+    src, flt, bias, z = K.gen_inputs(d, 31, int_range=127, bias_range=5000)
+    outs = {}
+    for mode in ("resident", "streamed"):
+        if by_default and mode == "resident":
+            lib = None                                  # product library, product heuristic
+        else:
+            if not os.path.exists(G.TOOLS_LIB):
+                pytest.skip("tools build not present")
+            knob("B200CB_BRES", 1 if mode == "resident" else 0)
+            knob("B200CB_PAIR", 0)
+            lib = G.tools_lib()
+        rc, plan = G.plan_for(d, lib=lib)
+        assert rc == 0
+        assert bool(plan.reserved[2] & 8) == (mode == "resident"), (mode, plan.block_n)
+        t = [G.to_dev(a) for a in (src, flt, bias, z)]
+        out = torch.zeros(O.dst_elems(d), dtype=torch.int8 if kind == "qs8" else torch.int16, device="cuda")
+        G.launch(plan, t[0], t[1], t[2], t[3], out, lib=lib)
+        torch.cuda.synchronize()
+        outs[mode] = out.cpu().numpy()
+    assert np.array_equal(outs["resident"], outs["streamed"])
+    got = outs["resident"]
+    idx = np.random.default_rng(7).integers(0, got.size, 4096).astype(np.uint64)
+    if kind == "qs8":
+        want = O.oracle_convbias_sample(d, src, flt, bias, z, idx)
+        assert np.array_equal(got[idx.astype(np.int64)], want)
+    else:
+        d32 = d.copy()
+        d32.src_dtype = d32.filter_dtype = d32.dst_dtype = d32.bias_dtype = d32.z_dtype = C.DT_F32
+        d32.compute_mode = C.COMPUTE_DEFAULT
+        up = lambda a: None if a is None else O.to_f32(a, d.src_dtype)
+        want = O.oracle_convbias_sample(d32, up(src), up(flt), up(bias), up(z), idx)
+        err = O.megdnn_rel_err(O.to_f32(got.view(np.uint16), d.dst_dtype)[idx.astype(np.int64)], want)
+        assert err.max() <= (1e-2 if kind == "bf16" else 2e-3), err.max()
+
+
 @pytest.mark.parametrize("kind", ["bf16", "f16", "qs8"])
 def test_full_size_residual_layer_repeated_and_sampled(kind):
     """ResNet-50 l1.c3 at N = 256 (802816 x 256 outputs, residual z, one k-block per tile): the layer whose
