@@ -78,11 +78,9 @@ double igemm_cost(const b200cb_desc& d, const b200cb_plan& plan, uint32_t bn, in
     if (tiles < sms)
         return 1.0 + 1.0 / tiles;  // small problems: most tiles first
     double cost = 1.0 / bn;        // enough parallelism: widest first ...
-    // ... unless the wide tile leaves no room for a two-deep z ring per epilogue group: the residual
-    // stream then stalls every chunk (ResNet-50 l3.c3: 128x128 with the deep ring beats 128x256, r02 sweep)
-    if (d.has_z && plan.kernel == KERNEL_IGEMM && d.format == B200CB_FORMAT_NHWC && (plan.reserved[5] >> 16) < 8 &&
-        bn > 128 && (uint64_t)d.fh * d.fw * d.ic * dtype_size(d.src_dtype) <= 512)
-        cost *= 2.5;
+    // (round 2 had a rule here that sent ResNet-50 l3.c3 -- residual z, K = 512 bytes, no room for a two-deep z ring next
+    // to a 256-wide tile -- to 128x128 tiles; with the merge-free 16-bit epilogue the 256-wide tile wins again:
+    // 0.0550 vs 0.0590 ms, profiles/r02/exp_epilogue_tail_ab.txt)
     // QuantizedS8 residual layers whose 256-wide filter tile cannot stay resident (IgemmParams::b_res: K * BN > 64 KiB)
     // run faster on the narrower tile that can (l4.c3: 128x128 resident 0.026 ms, 128x256 streamed 0.030)
     if (d.has_z && plan.kernel == KERNEL_IGEMM && d.src_dtype == B200CB_DT_QS8 && !(plan.reserved[2] & 8u) && bn > 128 &&

@@ -1344,21 +1344,10 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                                     f2_pack(__uint_as_float(r[j * 4 + 2]), __uint_as_float(r[j * 4 + 3])),
                                     f2_pack(__uint_as_float(bv.z), __uint_as_float(bv.w)));
                         }
-                        if (p.has_z) {
-#pragma unroll
-                            for (uint32_t j = 0; j < PIECES; ++j) {
-                                const uint32_t off = (h * PIECES + j) ^ (lane & 7);
-                                const uint4 zv = *reinterpret_cast<const uint4*>(zrow + off * 16);
-                                const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
-#pragma unroll
-                                for (uint32_t w = 0; w < 4; ++w) {
-                                    if constexpr (KIND == KIND_BF16)
-                                        v[j * 4 + w] = f2_add(v[j * 4 + w], f2_pack(bf16lo(zw[w]), bf16hi(zw[w])));
-                                    else
-                                        v[j * 4 + w] = f2_add(v[j * 4 + w], f2_pack(f16lo(zw[w]), f16hi(zw[w])));
-                                }
-                            }
-                        }
+                        // convert + activation + staging store, instantiated once per z / no-z path: a common tail after
+                        // the `has_z` branch made ptxas shuffle all 32 value registers into one allocation at the merge
+                        // point (28 MOVs per 32 columns, ncu instruction profile of the low-K pointwise layers)
+                        auto finish16 = [&]() {
                         uint32_t o[16];
                         if (generic_act) {
 #pragma unroll
@@ -1386,6 +1375,25 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                             const uint32_t off = (h * PIECES + j) ^ (lane & 7);
                             *reinterpret_cast<uint4*>(drow + off * 16) =
                                     make_uint4(o[j * 4], o[j * 4 + 1], o[j * 4 + 2], o[j * 4 + 3]);
+                        }
+                        };
+                        if (p.has_z) {
+#pragma unroll
+                            for (uint32_t j = 0; j < PIECES; ++j) {
+                                const uint32_t off = (h * PIECES + j) ^ (lane & 7);
+                                const uint4 zv = *reinterpret_cast<const uint4*>(zrow + off * 16);
+                                const uint32_t zw[4] = {zv.x, zv.y, zv.z, zv.w};
+#pragma unroll
+                                for (uint32_t w = 0; w < 4; ++w) {
+                                    if constexpr (KIND == KIND_BF16)
+                                        v[j * 4 + w] = f2_add(v[j * 4 + w], f2_pack(bf16lo(zw[w]), bf16hi(zw[w])));
+                                    else
+                                        v[j * 4 + w] = f2_add(v[j * 4 + w], f2_pack(f16lo(zw[w]), f16hi(zw[w])));
+                                }
+                            }
+                            finish16();
+                        } else {
+                            finish16();
                         }
                     }
                 }
