@@ -34,6 +34,7 @@ struct RequantParams {
     float s_dst;    // scale of dst
     float inv_dst;  // RN(1 / s_dst) when `fast_div`, unused otherwise
     uint32_t fast_div;
+    float one;      // 1.0f as a RUN-TIME value (see the z dequantisation of requant_pair_*)
 };
 
 // host: fills RequantParams from the descriptor's scales (defined in igemm_sm100.cu)
@@ -170,8 +171,7 @@ __device__ __forceinline__ f32x2_t f2_add_rm(f32x2_t a, f32x2_t b) {
 }
 // loop-invariant operands of the packed requantize
 struct RequantPacked {
-    f32x2_t s_bias, inv, neg_s, half, magic, neg_i2f, neg_2p23, c4096;
-    float s_bias1, s_z1;
+    f32x2_t s_bias, inv, neg_s, half, magic, neg_i2f, neg_2p23, c4096, s_z, one, neg_zmagic;
 };
 // int32 -> float without the conversion pipe (I2F issues 16 lanes / clk / SM and was the busiest pipe of the
 // int8 epilogue): for v in [-2^22, 2^22) the integer add 0x4B400000 + v yields the bits of the float
@@ -188,10 +188,18 @@ constexpr uint32_t I2F_RANGE = 1u << 22;
 // adjacency of the sequence, the dequantisation with z, stays on scalar mul.rn.f32 / add.rn.f32 (never
 // contracted); everything after it has no product feeding an add: FMUL2 -> {FMNMX | FMUL2 | FFMA2
 // multiplicand}, explicit FFMA2s, FADD2.RZ -> FADD2.RM.
+// The dequantisation with z itself, x = RN(RN(a * s_bias) + RN(z * s_z)), is packed too: the sum is issued as
+// fma(RN(a * s_bias), one, RN(z * s_z)) with `one` == 1.0f arriving as a kernel parameter -- an FMA by a run-time 1 rounds
+// exactly like the add, and ptxas can neither fold a multiplier it does not know nor contract a product into an
+// instruction that already multiplies.  2 FMUL2 + 1 FFMA2 + 1 FADD2 per output PAIR instead of 4 FMUL + 4 FADD (the
+// z layers of the int8 ResNet-50 issued 405 instructions per 32 outputs, 128 of them these scalars; ncu instruction
+// profile profiles/r02/ncu_inst_qs8_l1c3.txt).  b200cb_selftest(2) sweeps it against the scalar form.
 __device__ __forceinline__ RequantPacked make_requant_packed(const RequantParams& q) {
     RequantPacked r;
     r.s_bias = f2_pack(q.s_bias, q.s_bias);
-    r.s_bias1 = q.s_bias, r.s_z1 = q.s_z;
+    r.s_z = f2_pack(q.s_z, q.s_z);
+    r.one = f2_pack(q.one, q.one);
+    r.neg_zmagic = f2_pack(-8388736.f, -8388736.f);
     r.inv = f2_pack(q.inv_dst, q.inv_dst);
     r.neg_s = f2_pack(-q.s_dst, -q.s_dst);
     r.half = f2_pack(0.5f, 0.5f);
@@ -236,12 +244,8 @@ __device__ __forceinline__ void requant_pair_nonneg(
     else
         a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
     if constexpr (HAS_Z) {
-        float a0, a1;
-        f2_unpack(a, a0, a1);
-        const float z0 = __fadd_rn(__uint_as_float(zbits0), -8388736.f);
-        const float z1 = __fadd_rn(__uint_as_float(zbits1), -8388736.f);
-        x = f2_pack(__fadd_rn(__fmul_rn(a0, k.s_bias1), __fmul_rn(z0, k.s_z1)),
-                    __fadd_rn(__fmul_rn(a1, k.s_bias1), __fmul_rn(z1, k.s_z1)));
+        const f32x2_t zf = f2_add(f2_pack(__uint_as_float(zbits0), __uint_as_float(zbits1)), k.neg_zmagic);  // exact
+        x = f2_fma(f2_mul(a, k.s_bias), k.one, f2_mul(zf, k.s_z));
     } else {
         x = f2_mul(a, k.s_bias);
     }
@@ -281,12 +285,8 @@ __device__ __forceinline__ void requant_pair_signed(
     else
         a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
     if constexpr (HAS_Z) {
-        float a0, a1;
-        f2_unpack(a, a0, a1);
-        const float z0 = __fadd_rn(__uint_as_float(zbits0), -8388736.f);
-        const float z1 = __fadd_rn(__uint_as_float(zbits1), -8388736.f);
-        x = f2_pack(__fadd_rn(__fmul_rn(a0, k.s_bias1), __fmul_rn(z0, k.s_z1)),
-                    __fadd_rn(__fmul_rn(a1, k.s_bias1), __fmul_rn(z1, k.s_z1)));
+        const f32x2_t zf = f2_add(f2_pack(__uint_as_float(zbits0), __uint_as_float(zbits1)), k.neg_zmagic);  // exact
+        x = f2_fma(f2_mul(a, k.s_bias), k.one, f2_mul(zf, k.s_z));
     } else {
         x = f2_mul(a, k.s_bias);
     }

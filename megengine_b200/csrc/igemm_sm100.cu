@@ -1555,6 +1555,7 @@ __global__ void selftest_div_kernel(const float* scales, int nscales, unsigned l
     for (int si = 0; si < nscales; ++si) {
         RequantParams q;
         q.s_bias = 1.f, q.s_z = 0.f, q.s_dst = scales[si], q.inv_dst = 1.0f / scales[si], q.fast_div = 1;
+        q.one = scales[4];  // 1.0f, read from memory
         RequantParams ref = q;
         ref.fast_div = 0;
         for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -1585,6 +1586,7 @@ __global__ void selftest_fastq_kernel(const float* scales, int nscales, unsigned
     for (int si = 0; si < nscales; ++si) {
         RequantParams q;
         q.s_bias = 1.f, q.s_z = 0.f, q.s_dst = scales[si], q.inv_dst = 1.0f / scales[si], q.fast_div = 2;
+        q.one = scales[4];
         RequantParams ref = q;
         ref.fast_div = 0;
         for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
@@ -1620,6 +1622,7 @@ __global__ void selftest_packed_kernel(const float* scales, int nscales, unsigne
         RequantParams q;
         q.s_bias = 0.0013f * (si + 1), q.s_z = 0.07f, q.s_dst = scales[si], q.inv_dst = 1.0f / scales[si];
         q.fast_div = 2;
+        q.one = scales[4];  // h_scales[4] == 1.0f: a run-time value here as in the product kernels (a kernel parameter there)
         const RequantPacked kp = make_requant_packed(q);
         for (unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
              i < (1ull << 32); i += (unsigned long long)gridDim.x * blockDim.x) {
@@ -1963,6 +1966,7 @@ RequantParams make_requant(const b200cb_desc& d) {
     q.s_bias = d.bias_dtype == B200CB_DT_QS32 ? d.bias_scale : d.src_scale * d.filter_scale;
     q.s_z = d.has_z ? d.z_scale : 0.f;
     q.s_dst = d.dst_scale;
+    q.one = 1.0f;
     const float y = 1.0f / d.dst_scale;
     q.inv_dst = y;
     q.fast_div = (isnormal(d.dst_scale) && isnormal(y) && d.dst_scale > 0.f) ? 1u : 0u;
