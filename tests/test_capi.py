@@ -205,8 +205,8 @@ def test_int8_epilogue_sass_has_no_contracted_packed_ops():
     megengine_b200/csrc/epilogue.cuh), so the packed requantize keeps no product that feeds an add.  In
     every QuantizedS8 igemm kernel the machine code must then hold exactly the explicit FMAs of the
     division (2 FFMA2 per FADD2.RM pair rounding) and of the conversion-free int32 -> float (one FFMA2 per pair in
-    the full-range variants); the only round-to-nearest FADD2s are the exact magic-number subtractions -- an add
-    never follows a product."""
+    the full-range variants) plus the one explicit FMA-by-one of the z dequantisation; the only round-to-nearest FADD2s are
+    the exact magic-number subtractions -- an add never follows a product."""
     import re
     import shutil
     import subprocess
@@ -232,8 +232,14 @@ def test_int8_epilogue_sass_has_no_contracted_packed_ops():
         # FADD2s, the range-proven magic sites (4 igemm sites) one exact FADD2.  A contracted mul + add would add an
         # FFMA2 and remove a FADD2.
         n_split, n_magic = (32, 64) if is_igemm8 else (0, 0)
-        assert ffma2 == 2 * rz + n_split, (name, ffma2, rz)
-        assert plain == n_magic + 2 * n_split, (name, plain)
+        # sites with a residual z (6 of the 14 igemm sites incl. the two NCHW4 ones; every second depthwise site):
+        # the dequantisation RN(RN(a * s_bias) + RN(z * s_z)) is two FMUL2s and ONE explicit FFMA2 by a run-time 1.0
+        # (rounds like the add, cannot be contracted), plus the exact FADD2 that turns the z bytes into floats
+        n_z = 96 if is_igemm8 else rz // 2
+        fmul2 = f.count("FMUL2")
+        assert ffma2 == 2 * rz + n_split + n_z, (name, ffma2, rz)
+        assert plain == n_magic + 2 * n_split + n_z, (name, plain)
+        assert fmul2 == 2 * rz + n_z, (name, fmul2)   # a * s_bias and x * (1 / s_dst) per pair, z * s_z per z pair
         checked += 1
     assert checked >= 11, checked
 
