@@ -227,28 +227,9 @@ __device__ __forceinline__ f32x2_t i2f_pair(int32_t v0, int32_t v1, const Requan
     return f2_fma(hi, k.c4096, lo);
 }
 
-// two RELU outputs at once: (acc + bias) pairs -> the two result bytes in the low bytes of lo / hi.
-// Same operation sequence as dequant + fmaxf + div_by_scale_noguard + round_sat_s8_nonneg.
-// CVT selects the int32 -> float conversion: 0 = I2F (conversion pipe), 1 = sfb0 / sfb1 already carry
-// I2F_MAGIC_BITS (acc + bias + magic, range proven by the caller), 2 = i2f_pair (full range, FMA / ALU pipes only)
-template <bool HAS_Z, int CVT = 0>
-__device__ __forceinline__ void requant_pair_nonneg(
-        int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
-        uint32_t& hi) {
-    f32x2_t x;
-    f32x2_t a;
-    if constexpr (CVT == 1)
-        a = f2_add(f2_pack(__int_as_float(sfb0), __int_as_float(sfb1)), k.neg_i2f);   // exact
-    else if constexpr (CVT == 2)
-        a = i2f_pair(sfb0, sfb1, k);
-    else
-        a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
-    if constexpr (HAS_Z) {
-        const f32x2_t zf = f2_add(f2_pack(__uint_as_float(zbits0), __uint_as_float(zbits1)), k.neg_zmagic);  // exact
-        x = f2_fma(f2_mul(a, k.s_bias), k.one, f2_mul(zf, k.s_z));
-    } else {
-        x = f2_mul(a, k.s_bias);
-    }
+// the part of requant_pair_* after the dequantisation: x = two dequantised values (RN-rounded floats), results in
+// the low bytes of lo / hi.  Shared with the quantized elementwise ADD kernels (nnops.cu).
+__device__ __forceinline__ void requant_tail_nonneg(f32x2_t x, const RequantPacked& k, uint32_t& lo, uint32_t& hi) {
     float x0, x1;
     f2_unpack(x, x0, x1);
     x = f2_pack(fmaxf(x0, 0.f), fmaxf(x1, 0.f));
@@ -270,26 +251,7 @@ __device__ __forceinline__ void requant_pair_nonneg(
     hi = __float_as_uint(u1);
 #endif
 }
-
-// the IDENTITY (any sign) form of the same: clamp to [-128, 127], round the magnitude, negate the byte
-template <bool HAS_Z, int CVT = 0>
-__device__ __forceinline__ void requant_pair_signed(
-        int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
-        uint32_t& hi) {
-    f32x2_t x;
-    f32x2_t a;
-    if constexpr (CVT == 1)
-        a = f2_add(f2_pack(__int_as_float(sfb0), __int_as_float(sfb1)), k.neg_i2f);   // exact
-    else if constexpr (CVT == 2)
-        a = i2f_pair(sfb0, sfb1, k);
-    else
-        a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
-    if constexpr (HAS_Z) {
-        const f32x2_t zf = f2_add(f2_pack(__uint_as_float(zbits0), __uint_as_float(zbits1)), k.neg_zmagic);  // exact
-        x = f2_fma(f2_mul(a, k.s_bias), k.one, f2_mul(zf, k.s_z));
-    } else {
-        x = f2_mul(a, k.s_bias);
-    }
+__device__ __forceinline__ void requant_tail_signed(f32x2_t x, const RequantPacked& k, uint32_t& lo, uint32_t& hi) {
     const f32x2_t q0 = f2_mul(x, k.inv);
     const f32x2_t e = f2_fma(q0, k.neg_s, x);
     const f32x2_t q1 = f2_fma(e, k.inv, q0);
@@ -313,6 +275,53 @@ __device__ __forceinline__ void requant_pair_signed(
     lo = (__float_as_uint(u0) ^ s0) - s0;
     hi = (__float_as_uint(u1) ^ s1) - s1;
 #endif
+}
+
+// two RELU outputs at once: (acc + bias) pairs -> the two result bytes in the low bytes of lo / hi.
+// Same operation sequence as dequant + fmaxf + div_by_scale_noguard + round_sat_s8_nonneg.
+// CVT selects the int32 -> float conversion: 0 = I2F (conversion pipe), 1 = sfb0 / sfb1 already carry
+// I2F_MAGIC_BITS (acc + bias + magic, range proven by the caller), 2 = i2f_pair (full range, FMA / ALU pipes only)
+template <bool HAS_Z, int CVT = 0>
+__device__ __forceinline__ void requant_pair_nonneg(
+        int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
+        uint32_t& hi) {
+    f32x2_t x;
+    f32x2_t a;
+    if constexpr (CVT == 1)
+        a = f2_add(f2_pack(__int_as_float(sfb0), __int_as_float(sfb1)), k.neg_i2f);   // exact
+    else if constexpr (CVT == 2)
+        a = i2f_pair(sfb0, sfb1, k);
+    else
+        a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
+    if constexpr (HAS_Z) {
+        const f32x2_t zf = f2_add(f2_pack(__uint_as_float(zbits0), __uint_as_float(zbits1)), k.neg_zmagic);  // exact
+        x = f2_fma(f2_mul(a, k.s_bias), k.one, f2_mul(zf, k.s_z));
+    } else {
+        x = f2_mul(a, k.s_bias);
+    }
+    requant_tail_nonneg(x, k, lo, hi);
+}
+
+// the IDENTITY (any sign) form of the same: clamp to [-128, 127], round the magnitude, negate the byte
+template <bool HAS_Z, int CVT = 0>
+__device__ __forceinline__ void requant_pair_signed(
+        int32_t sfb0, int32_t sfb1, uint32_t zbits0, uint32_t zbits1, const RequantPacked& k, uint32_t& lo,
+        uint32_t& hi) {
+    f32x2_t x;
+    f32x2_t a;
+    if constexpr (CVT == 1)
+        a = f2_add(f2_pack(__int_as_float(sfb0), __int_as_float(sfb1)), k.neg_i2f);   // exact
+    else if constexpr (CVT == 2)
+        a = i2f_pair(sfb0, sfb1, k);
+    else
+        a = f2_pack(__int2float_rn(sfb0), __int2float_rn(sfb1));
+    if constexpr (HAS_Z) {
+        const f32x2_t zf = f2_add(f2_pack(__uint_as_float(zbits0), __uint_as_float(zbits1)), k.neg_zmagic);  // exact
+        x = f2_fma(f2_mul(a, k.s_bias), k.one, f2_mul(zf, k.s_z));
+    } else {
+        x = f2_mul(a, k.s_bias);
+    }
+    requant_tail_signed(x, k, lo, hi);
 }
 
 __device__ __forceinline__ int32_t requant_s8(int32_t sfb, int32_t zq, uint32_t nl, const RequantParams& q) {

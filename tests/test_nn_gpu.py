@@ -116,6 +116,29 @@ def test_quantized_elemwise_bit_exact(i, handle):
     _bits_equal(_raw(dst, dst.layout.dtype), want, N.ELEM_Q_CASES[i])
 
 
+@pytest.mark.parametrize("mode", [C.ELEM_ADD, C.ELEM_FUSE_ADD_RELU])
+@pytest.mark.parametrize("scales", [(0.37, 0.71, 0.9), (0.11, 0.23, 0.19), (1.9, 23.0, 0.7), (0.013, 0.0071, 0.0005),
+                                    (3.0, 0.02, 19.99), (1.0, 1.0, 1.0)])
+def test_quantized_add_all_byte_pairs(mode, scales):
+    """The packed ADD / FUSE_ADD_RELU kernel (two outputs per instruction, the sum as an FMA by a run-time 1.0) over
+    EVERY pair of input bytes (65536 + a ragged tail) and scale triples that saturate, that round at .5 ties
+    (all ones) and that do neither: bit for bit the naive ElemwiseMultiType (oracle/nn_oracle.c)."""
+    sa, sb, sd = scales
+    v = np.arange(-128, 128, dtype=np.int8)
+    a = np.concatenate([np.repeat(v, 256), v[:7]]).astype(np.int8)
+    b = np.concatenate([np.tile(v, 256), v[5:12]]).astype(np.int8)
+    want = N.elemwise_q("oracle", mode, a, sa, b, sb, sd)
+    ta, tb = G.to_dev(a), G.to_dev(b)
+    td = torch.zeros(len(a), dtype=torch.int8, device="cuda")
+    rc = C.load().b200cb_elemwise_q(mode, len(a), ta.data_ptr(), np.float32(sa), tb.data_ptr(), np.float32(sb),
+                                    td.data_ptr(), np.float32(sd), torch.cuda.current_stream().cuda_stream)
+    assert rc == 0
+    torch.cuda.synchronize()
+    got = td.cpu().numpy()
+    bad = np.nonzero(got != want)[0]
+    assert bad.size == 0, (scales, bad[:5], a[bad[:5]], b[bad[:5]], got[bad[:5]], want[bad[:5]])
+
+
 @pytest.mark.parametrize("i", range(len(N.TYPECVT_CASES)))
 def test_typecvt_bit_exact(i, handle):
     sdt, ss, ddt, sd = N.TYPECVT_CASES[i]
