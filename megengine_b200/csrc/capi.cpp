@@ -1,6 +1,7 @@
 // C-ABI entry points (include/b200cb.h): algorithm table, heuristic, dispatch, error text.
 #include <math.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.h"
 
@@ -166,6 +167,69 @@ F32Layout f32_layout(const b200cb_desc& d, const b200cb_desc& e, uint64_t inner_
     return l;
 }
 
+// ---- pixel-pair fold of narrow 1x1 layers (MobileNetV2 / ShuffleNetV2 projections such as 32 -> 16 at 112x112): the
+// layer is bound by the number of short TMA rows per tile and stores 16 of a 64-column tile.  Two horizontally adjacent
+// pixels are viewed as one pixel of 2 * IC channels -- src, z and dst are the SAME memory under that view -- and the
+// filter becomes the block-diagonal (2 * OC) x (2 * IC) matrix [[W, 0], [0, W]] (built in the workspace by one tiny
+// launch per exec, with the bias repeated).  Half the tiles, activation rows twice as long, every product of the
+// original sum in the same order (the added terms are exact zeros): results are bit-identical.
+bool pw_fold_enabled() {
+#ifdef B200CB_TOOLS
+    if (const char* e = getenv("B200CB_PWFOLD"))
+        return atoi(e) != 0;
+#endif
+    return true;
+}
+bool is_pw_fold(const b200cb_desc& d) {
+    const bool s16 = (d.src_dtype == B200CB_DT_BF16 || d.src_dtype == B200CB_DT_F16) && d.dst_dtype == d.src_dtype;
+    const bool s8 = d.src_dtype == B200CB_DT_QS8 && d.dst_dtype == B200CB_DT_QS8;
+    if (!(s16 || s8) || d.filter_dtype != d.src_dtype || d.format != B200CB_FORMAT_NHWC || d.group > 1 ||
+        d.sparse != B200CB_SPARSE_DENSE)
+        return false;
+    if (d.fh != 1 || d.fw != 1 || d.stride_h != 1 || d.stride_w != 1 || d.pad_h || d.pad_w || d.iw % 2 != 0)
+        return false;
+    if (d.src_batch_stride || d.z_batch_stride || d.dst_batch_stride || d.bias_mode == B200CB_BIAS_FULL)
+        return false;
+    const uint32_t es = dtype_size(d.src_dtype);
+    // narrow on both sides: the folded layer still fits one 64-column tile and one 128-byte k-block
+    return 2 * d.oc <= 64 && 2 * d.ic * es <= 128 && (d.ic * es) % 16 == 0 && (d.oc * es) % 16 == 0 && pw_fold_enabled();
+}
+b200cb_desc pw_fold_equivalent(const b200cb_desc& d) {
+    b200cb_desc e = d;
+    e.ic = 2 * d.ic, e.oc = 2 * d.oc, e.iw = d.iw / 2, e.ow = d.ow / 2;
+    return e;
+}
+struct PwFoldLayout {
+    size_t flt, bias, inner, total;
+};
+PwFoldLayout pw_fold_layout(const b200cb_desc& d, uint64_t inner_ws) {
+    PwFoldLayout l{};
+    size_t off = 0;
+    l.flt = off, off += a256((size_t)4 * d.oc * d.ic * dtype_size(d.filter_dtype));
+    l.bias = off, off += a256((size_t)2 * d.oc * 4);
+    l.inner = off, off += a256(inner_ws);
+    l.total = off;
+    return l;
+}
+// filter (OC, IC) -> [[W, 0], [0, W]] (2 OC, 2 IC), bias (OC) -> (2 OC); one thread per 16-bit / 8-bit / 32-bit element
+template <typename T>
+__global__ void pw_fold_kernel(
+        const T* __restrict__ w, T* __restrict__ wf, uint32_t oc, uint32_t ic, const void* __restrict__ bias,
+        void* __restrict__ bf, uint32_t bias_es) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < 4 * oc * ic) {
+        const uint32_t r = i / (2 * ic), c = i % (2 * ic);   // row of the folded filter, column
+        const uint32_t ro = r % oc, half_r = r / oc, half_c = c / ic;
+        wf[i] = half_r == half_c ? w[ro * ic + c % ic] : T(0);
+    }
+    if (bias && i < 2 * oc) {
+        if (bias_es == 2)
+            static_cast<uint16_t*>(bf)[i] = static_cast<const uint16_t*>(bias)[i % oc];
+        else
+            static_cast<uint32_t*>(bf)[i] = static_cast<const uint32_t*>(bias)[i % oc];
+    }
+}
+
 int query_one(const b200cb_desc& d, int algo, b200cb_plan* plan) {
     const AlgoEntry& a = g_algos[algo];
     return a.kernel == KERNEL_IGEMM ? igemm_query(d, a.block_n, plan) : dwconv_query(d, plan);
@@ -222,6 +286,12 @@ int b200cb_query_algo(const b200cb_desc* desc, int algo, b200cb_plan* plan) {
         if (rc != B200CB_OK)
             return rc;
         plan->workspace_bytes = nchw_layout(*desc, e, plan->workspace_bytes).total;
+        plan->desc = *desc;
+    } else if (g_algos[algo].kernel == KERNEL_IGEMM && is_pw_fold(*desc)) {
+        rc = query_one(pw_fold_equivalent(*desc), algo, plan);
+        if (rc != B200CB_OK)
+            return rc;
+        plan->workspace_bytes = pw_fold_layout(*desc, plan->workspace_bytes).total;
         plan->desc = *desc;
     } else {
         rc = query_one(*desc, algo, plan);
@@ -336,6 +406,36 @@ int b200cb_launch(
             rc = relayout_transpose16(ws + l.dst, dst, d.n, OP, d.oc, OP, 0, d.dst_batch_stride, s);
         return rc;
     }
+    if (plan->kernel == KERNEL_IGEMM && is_pw_fold(plan->desc)) {
+        const b200cb_desc& d = plan->desc;
+        b200cb_plan inner;
+        int rc = query_one(pw_fold_equivalent(d), plan->algo, &inner);
+        if (rc != B200CB_OK)
+            return rc > 0 ? B200CB_ERR_BAD_PLAN : rc;
+        const PwFoldLayout l = pw_fold_layout(d, inner.workspace_bytes);
+        if (!workspace || workspace_bytes < l.total)
+            return B200CB_ERR_WORKSPACE;
+        if (!src || !filter || !dst || (d.has_z && !z) || (d.bias_mode != B200CB_BIAS_NONE && !bias))
+            return B200CB_ERR_NULL;
+        uint8_t* ws = static_cast<uint8_t*>(workspace);
+        const uint32_t total = 4 * d.oc * d.ic, blocks = (total + 255) / 256;
+        const void* b_in = d.bias_mode != B200CB_BIAS_NONE ? bias : nullptr;
+        if (dtype_size(d.filter_dtype) == 1)
+            pw_fold_kernel<int8_t><<<blocks, 256, 0, s>>>(
+                    static_cast<const int8_t*>(filter), reinterpret_cast<int8_t*>(ws + l.flt), d.oc, d.ic, b_in,
+                    ws + l.bias, dtype_size(d.bias_dtype));
+        else
+            pw_fold_kernel<uint16_t><<<blocks, 256, 0, s>>>(
+                    static_cast<const uint16_t*>(filter), reinterpret_cast<uint16_t*>(ws + l.flt), d.oc, d.ic, b_in,
+                    ws + l.bias, dtype_size(d.bias_dtype));
+        if (cudaGetLastError() != cudaSuccess) {
+            set_last_error("pw_fold launch", "cuda error");
+            return B200CB_ERR_CUDA;
+        }
+        inner.algo = plan->algo;
+        return igemm_launch(
+                inner, src, ws + l.flt, b_in ? ws + l.bias : nullptr, z, dst, ws + l.inner, inner.workspace_bytes, s);
+    }
     switch (plan->kernel) {
         case KERNEL_IGEMM:
             return igemm_launch(*plan, src, filter, bias, z, dst, workspace, workspace_bytes, s);
@@ -366,6 +466,8 @@ int b200cb_plan_num_launches(const b200cb_plan* plan) {
             return 0;
         return 2 + (nchw_depthwise(plan->desc) ? 0 : 1) + (plan->desc.has_z ? 1 : 0) + b200cb_plan_num_launches(&inner);
     }
+    if (plan->kernel == KERNEL_IGEMM && is_pw_fold(plan->desc))
+        return 2;  // block-diagonal filter + conv
     // NCHW4: src re-tile + filter re-tile (+ stem filter re-pack) + conv
     if (plan->kernel == KERNEL_IGEMM && plan->desc.format == B200CB_FORMAT_NCHW4)
         return plan->reserved[4] ? 4 : 3;

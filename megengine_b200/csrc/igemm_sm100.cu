@@ -1947,7 +1947,8 @@ bool pick_bres(const b200cb_desc& d, uint32_t block_n, uint32_t k_bytes, uint32_
     //    0.154 -> 0.060, 0.024 -> 0.019, 0.149 -> 0.096 ms (9-layer table 40 % -> 65 % of HBM; int8 13.5 % -> 24.6 %);
     //  * QuantizedS8 layers with longer K gain 0-10 % (l4.c3 0.029 -> 0.026) and never lose more than 1 %;
     //  * 16-bit layers with K >= 128 bytes are within +-2 % except l2.c3 (-8 %) and K = 512 (-3 %): streamed
-    return d.src_dtype == B200CB_DT_QS8 || k_bytes <= 64;
+    //  * the pixel-pair folded narrow layers (capi.cpp: 32 -> 16 runs as 64 -> 32, K = 128 bytes): 0.0580 -> 0.0557 ms
+    return d.src_dtype == B200CB_DT_QS8 || k_bytes <= 64 || (k_bytes <= 128 && d.oc <= 32);
 }
 
 uint32_t pick_kb_bytes(uint32_t ic_bytes) {

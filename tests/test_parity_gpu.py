@@ -4,6 +4,7 @@ error |x-y|/max(|x|,|y|,1) against the fp32 oracle (BASELINE.json north_star; me
 dnn/test/common/utils.h:189-193).  Case generators mirror dnn/test/cuda/conv_bias.cpp:83-124,
 234-265,650-714,1390-1439 and dnn/test/cuda/conv_bias_int8.cpp:798-835.
 """
+import ctypes
 import os
 import zlib
 
@@ -386,7 +387,7 @@ def test_resident_filter_tile_forced_on_every_pointwise_case(name, d, opt, knob)
 @pytest.mark.parametrize("kind,spec,n", [("qs8", "l1.c3", 256), ("qs8", "l4.c3", 256), ("qs8", "l2.bN.c1", 64),
                                          ("bf16", "l3.c3", 64), ("f16", "l2.c3", 32),
                                          ("bf16", (16, 112, 96), 64), ("f16", (24, 56, 144), 128),
-                                         ("bf16", (32, 112, 16), 64), ("qs8", (16, 112, 96), 64)],
+                                         ("bf16", (32, 28, 192), 64), ("qs8", (16, 112, 96), 64)],
                          ids=lambda v: "x".join(map(str, v)) if isinstance(v, tuple) else str(v))
 def test_resident_filter_tile_full_size_equals_streamed(kind, spec, n, knob):
     """Many tiles per CTA (grid cut to a multiple of n_tiles, every CTA keeps ONE N tile of the filter): the
@@ -439,6 +440,39 @@ def test_resident_filter_tile_full_size_equals_streamed(kind, spec, n, knob):
         want = O.oracle_convbias_sample(d32, up(src), up(flt), up(bias), up(z), idx)
         err = O.megdnn_rel_err(O.to_f32(got.view(np.uint16), d.dst_dtype)[idx.astype(np.int64)], want)
         assert err.max() <= (1e-2 if kind == "bf16" else 2e-3), err.max()
+
+
+PW_FOLD_CASES = [
+    # name, kind, n, ic, h, w, oc, has_z, nonline, bias_mode
+    ("bf16_32to16_112", "bf16", 16, 32, 112, 112, 16, False, C.NL_RELU, C.BIAS_CHANNEL),
+    ("f16_16to24_odd_h_z", "f16", 3, 16, 7, 10, 24, True, C.NL_IDENTITY, C.BIAS_CHANNEL),
+    ("bf16_24to32_nobias", "bf16", 2, 24, 9, 6, 32, False, C.NL_H_SWISH, C.BIAS_NONE),
+    ("qs8_32to16_z_relu", "qs8", 5, 32, 14, 14, 16, True, C.NL_RELU, C.BIAS_CHANNEL),
+    ("qs8_16to32_w2", "qs8", 2, 16, 5, 2, 32, False, C.NL_IDENTITY, C.BIAS_CHANNEL),
+    ("qs8_64to16_many_tiles", "qs8", 64, 64, 28, 28, 16, False, C.NL_RELU, C.BIAS_CHANNEL),
+]
+
+
+@pytest.mark.parametrize("case", PW_FOLD_CASES, ids=[c[0] for c in PW_FOLD_CASES])
+def test_pointwise_pixel_pair_fold(case, knob):
+    """Narrow 1x1 layers run as the pixel-pair folded layer (2 IC -> 2 OC over W / 2, block-diagonal filter built in
+    the workspace): the oracle's bar, and bit for bit the unfolded kernel (tools build, B200CB_PWFOLD=0) -- the
+    extra products are exact zeros."""
+    import torch
+    from . import _gpu as G
+    _name, kind, n, ic, h, w, oc, has_z, nl, bias_mode = case
+    d = K.make_desc(kind, n, ic, h, w, oc, 1, nonline=nl, has_z=has_z, bias_mode=bias_mode)
+    opt = {"int_range": 127, "bias_range": 3000} if kind == "qs8" else None
+    plan, _info = _check(d, opt)
+    assert plan.workspace_bytes >= 4 * oc * ic and C.load().b200cb_plan_num_launches(ctypes.byref(plan)) == 2
+    if not os.path.exists(G.TOOLS_LIB):
+        pytest.skip("tools build not present")
+    src, flt, bias, z = K.gen_inputs(d, 11, **(opt or {}))
+    got, _ = G.run_gpu(d, src, flt, bias, z)
+    knob("B200CB_PWFOLD", 0)
+    ref, plan0 = G.run_gpu(d, src, flt, bias, z, lib=G.tools_lib())
+    assert plan0.workspace_bytes == 0
+    assert np.array_equal(got, ref)
 
 
 @pytest.mark.parametrize("kind", ["bf16", "f16", "qs8"])
