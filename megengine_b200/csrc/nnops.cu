@@ -83,6 +83,7 @@ struct PoolParams {
     uint32_t cg;          // channel groups of V elements a thread handles (NHWC: c / V, NCHW4: c / 4, NCHW: c)
     uint32_t layout;      // 0 NHWC (pixel pitch c), 1 NCHW (planes), 2 NCHW4 (planes of 4-channel pixels)
     float count_all;      // window_h * window_w rounded to the element type (MeanIncludePooler::count)
+    float inv_count;      // AVERAGE with a power-of-two count: 1 / count (x * 2^-k == x / 2^k, bit for bit), else 0
     uint32_t tpr;         // threads per output row (power of two <= 256)
 };
 
@@ -264,7 +265,8 @@ __global__ void __launch_bounds__(256) pool_kernel(
                     rr = roundf(__fdiv_rn(static_cast<float>(iacc[k]), c));
                 } else {
                     const float c = MODE == B200CB_POOL_AVERAGE ? p.count_all : rnd<DT>(static_cast<float>(cnt));
-                    rr = __fdiv_rn(acc[k], c);
+                    // (the IEEE division is ~10 instructions; a power-of-two count divides exactly by multiplication)
+                    rr = (MODE == B200CB_POOL_AVERAGE && p.inv_count != 0.f) ? __fmul_rn(acc[k], p.inv_count) : __fdiv_rn(acc[k], c);
                 }
                 o.v[k] = Elem<DT>::st(rr);
             }
@@ -283,6 +285,10 @@ int pool_launch_v(const b200cb_pool_desc& d, const void* src, void* dst, cudaStr
     p.count_all = DT == B200CB_DT_F16   ? __half2float(__float2half_rn(cnt))   /* window sizes < 2048 are exact */
                   : DT == B200CB_DT_BF16 ? __bfloat162float(__float2bfloat16_rn(cnt))
                                          : cnt;
+    {
+        int ex = 0;
+        p.inv_count = (p.count_all > 0.f && frexpf(p.count_all, &ex) == 0.5f) ? 1.0f / p.count_all : 0.f;
+    }
     constexpr int VMAX = 16 / (int)sizeof(T);
     int v = 1;
     if (d.format == B200CB_FORMAT_NHWC) {
