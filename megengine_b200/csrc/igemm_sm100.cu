@@ -689,6 +689,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
             const uint32_t plane16 = plane_bytes >> 4, stage16 = stage_bytes >> 4, brow = BN * RB / 16u;
             const uint32_t a0 = desc_lo(sStage, 16), b0 = desc_lo(sBres, 16);
             const uint32_t FH = p.num_taps / p.FW, roww = p.PW * (RB / 16);
+            const bool fast33 = FH == 3 && p.FW == 3 && p.num_kc == 1;
             uint32_t soff = 0;
             auto mma4 = [&](uint32_t taddr, uint32_t a_lo, uint32_t b_lo) {
 #pragma unroll
@@ -716,6 +717,16 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
 #pragma unroll
                 for (uint32_t k = 1; k < NM; ++k)
                     mma_issue<KIND>(taddr, row_lo + 2 * k, ab_hi, b_lo + 2 * k, ab_hi, IDESC, 1);
+                if (fast33) {
+                    // 3x3 window, one channel block (ResNet l1 3x3): straight-line issue.  The generic loops below
+                    // cost ~34 uniform-datapath instructions per tap (three constant-bank loads, three branches, the
+                    // counters), ~300 clk for the 4 x 48 clk of tensor work of a 128 x 64 tap: the issuing thread, not
+                    // the tensor pipe, bounded the layer at ~80 clk per MMA (ncu instruction profile + tools/microbench/
+                    // mma_shift.cu, profiles/r02/microbench_mma_shift.txt)
+#pragma unroll
+                    for (uint32_t t = 1; t < 9; ++t)
+                        mma4(taddr, row_lo + (t / 3) * roww + (t % 3) * (RB / 16), b0 + t * brow);
+                } else {
                 bool skip = true;  // (fh, fw, kc) == (0, 0, 0) is done
                 for (uint32_t fh = 0; fh < FH; ++fh) {
                     uint32_t tap_lo = row_lo;
@@ -731,6 +742,7 @@ __global__ void __launch_bounds__(Traits<KIND, OUT32>::THREADS, 1)
                         tap_lo += RB / 16;  // next pixel
                     }
                     row_lo += roww;  // next input row
+                }
                 }
                 mma_commit(bar_empty + 8 * stage);
                 mma_commit(bar_tfull + 8 * acc);
